@@ -1,0 +1,137 @@
+"""Pin the CPU oracle against golden vectors produced by the unmodified reference modules."""
+import pytest
+import torch
+
+from oracle import altformer_oracle as O
+from tests import goldenlib as G
+
+TOL = 2e-5  # fp32 CPU vs fp32 CPU, different op order
+
+
+def _cot(t, seed=7):
+    return torch.randn(t.shape, generator=torch.Generator().manual_seed(seed))
+
+
+def _run(fn, state, x, need_dx):
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in state.items()}
+    x = x.clone().requires_grad_(need_dx)
+    y = fn(x, params)
+    (y * _cot(y)).sum().backward()
+    return y, x.grad, params
+
+
+def _compare(case, y, dx, params, tol=TOL):
+    G.check_entry(case["y"], y, tol, "y")
+    if "dx" in case:
+        G.check_entry(case["dx"], dx, tol, "dx")
+    n = 0
+    for k, e in case.items():
+        if k.startswith("grad."):
+            g = params[k[5:]].grad
+            ref_norm = e["norm"] if isinstance(e, dict) else float(e.double().norm())
+            if ref_norm < 1e-4:  # analytically-zero gradients: absolute check
+                assert g is None or float(g.norm()) < 1e-3, k
+            else:
+                G.check_entry(e, g, 20 * tol, k)
+            n += 1
+        elif k.startswith("buf."):
+            G.check_entry(e, params[k[4:]], tol, k)
+    return n
+
+
+def test_graphs():
+    g = G.load("graphs")
+    assert torch.equal(O.spatial_graph("SHRE"), g["SHRE"])
+    assert torch.equal(O.spatial_graph("LMDHG"), g["LMDHG"])
+
+
+@pytest.mark.parametrize("name,cin,cout,N,T,V,train,seed,dx", [
+    ("agcn_3_128_train", 3, 128, 2, 8, 22, True, 11, False),
+    ("agcn_3_128_eval", 3, 128, 2, 8, 22, False, 11, False),
+    ("agcn_3_128_v46_train", 3, 128, 2, 6, 46, True, 12, False),
+    ("agcn_64_64_train", 64, 64, 2, 8, 22, True, 13, True),
+    ("agcn_32_64_train", 32, 64, 2, 8, 22, True, 14, True),
+])
+def test_agcn(name, cin, cout, N, T, V, train, seed, dx):
+    A = O.spatial_graph(V)
+    st = O.random_state(O.agcn_spec("", cin, cout, V), seed)
+    x = 0.5 * torch.randn(N, cin, T, V, generator=torch.Generator().manual_seed(seed + 100))
+    y, gx, params = _run(lambda x, p: O.agcn_forward(x, p, "", A, train), st, x, dx)
+    assert _compare(G.load(name), y, gx, params) >= 18
+
+
+@pytest.mark.parametrize("name,train", [("unit2d_32_train", True), ("unit2d_32_eval", False)])
+def test_unit2d(name, train):
+    st = O.random_state(O.unit2d_spec("", 32, 32, 9), 21)
+    x = torch.randn(2, 32, 12, 22, generator=torch.Generator().manual_seed(121))
+    y, gx, params = _run(lambda x, p: O.unit2d_forward(x, p, "", train), st, x, True)
+    _compare(G.load(name), y, gx, params)
+
+
+def test_tcn_gcn_unit():
+    spec = O.OrderedDict()
+    spec.update(O.agcn_spec("gcn1.", 64, 64, 22))
+    spec.update(O.unit2d_spec("tcn1.", 64, 64, 9))
+    st = O.random_state(spec, 31)
+    x = torch.randn(2, 64, 8, 22, generator=torch.Generator().manual_seed(131))
+    A = O.spatial_graph(22)
+    y, gx, params = _run(lambda x, p: O.tcn_gcn_forward(x, p, "", A, True), st, x, True)
+    _compare(G.load("tcn_gcn_64_train"), y, gx, params)
+
+
+@pytest.mark.parametrize("name,D,B,L,seed", [("block_64_L22", 64, 3, 22, 41), ("block_128_L8", 128, 2, 8, 42)])
+def test_block(name, D, B, L, seed):
+    st = O.random_state(O.block_spec("", D), seed)
+    x = torch.randn(B, L, D, generator=torch.Generator().manual_seed(seed + 100))
+    y, gx, params = _run(lambda x, p: O.block_forward(x, p, ""), st, x, True)
+    _compare(G.load(name), y, gx, params)
+
+
+@pytest.mark.parametrize("kind,seed", [("ST", 51), ("TS", 52)])
+def test_stage(kind, seed):
+    spec = (O.st_spec if kind == "ST" else O.ts_spec)("", 14, 8, 22, 32, 64, 2)
+    st = O.random_state(spec, seed)
+    x = torch.randn(2, 32, 8, 22, generator=torch.Generator().manual_seed(seed + 100))
+    fn = O.st_forward if kind == "ST" else O.ts_forward
+    y, gx, params = _run(lambda x, p: fn(x, p, ""), st, x, True)
+    _compare(G.load("st_small" if kind == "ST" else "ts_small"), y, gx, params)
+
+
+@pytest.mark.parametrize("name,style,N,T,V,cls,seed,train", [
+    ("model_ST_22", "ST", 2, 8, 22, 14, 61, True),
+    ("model_TS_22", "TS", 2, 8, 22, 14, 62, True),
+    ("model_both_22", None, 2, 8, 22, 28, 63, True),
+    ("model_ST_46_eval", "ST", 1, 8, 46, 14, 64, False),
+])
+def test_model(name, style, N, T, V, cls, seed, train):
+    case = G.load(name)
+    st = O.random_state(O.model_spec(3, cls, T, V), seed)
+    x, _ = O.synthetic_batch(N, T, V, cls, seed + 100)
+    A = O.spatial_graph(V)
+    y, _, params = _run(lambda x, p: O.model_forward(x, p, A, style, train), st, x, False)
+    _compare(case, y, None, params, tol=5e-5)
+    # every gradient norm the reference produced, and no gradient where it produced none
+    for k, n in case["grad_norms"].items():
+        g = params[k].grad
+        assert g is not None, k
+        if n > 1e-4:
+            assert abs(float(g.double().norm()) - n) / n < 2e-3, (k, float(g.norm()), n)
+    live = {k for k, v in params.items() if v.is_floating_point() and v.requires_grad and v.grad is not None}
+    assert live == set(case["grad_norms"].keys())
+
+
+def test_state_dict_contract():
+    meta = G.load("meta")
+    spec = O.model_spec(3, 28, 32, 22)
+    assert [(k, tuple(s)) for k, s in spec.items()] == [(k, tuple(s)) for k, s in meta["state_keys"]]
+    assert len(spec) == 366
+
+
+def test_streams_match_reference_loops():
+    x = torch.randn(2, 5, 22, 3)
+    b = O.bone_stream(x)
+    assert torch.allclose(b[0, 3, 7], x[0, 3, 7] - x[0, 3, 6])
+    assert torch.allclose(b[:, :, 0], torch.zeros_like(b[:, :, 0]))
+    m = O.motion_stream(x)
+    assert torch.allclose(m[1, 2], x[1, 3] - x[1, 2]) and float(m[:, -1].abs().max()) == 0.0
