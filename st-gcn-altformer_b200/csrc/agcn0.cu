@@ -1,0 +1,762 @@
+// gcn0 = unit_agcn(3 -> C_out), the bandwidth-bound adaptive graph convolution that opens the model
+// (reference: model/unit_agcn.py:73-93, constructed at model/AltFormer/ST_GCN_AltFormer.py:43-48).
+//
+// With C_in = 3 everything before the 128-channel expansion is tiny, so the layer is restructured as
+//   r[pos] = ( z_0, z_1, z_2, x ) in R^12,  z_i[n,t,v,:] = sum_u x[n,t,u,:] * M_i[n,u,v]
+//   y[pos] = relu( BN(sum_i Wd_i z_i + b) + BN_down(Wdn x + bdn) ) = relu( Wfold * [r - E r ; 1] )
+// and both BatchNorms' batch statistics follow from E[r] and Cov(r) (12 + 78 numbers) without ever
+// materialising the (N,128,T,V) pre-activation.  Attention scores use the Gram form
+//   S_i[u,v] = ( sum_ab (Wa_i^T Wb_i)[a,b] G[a,u,b,v] + ... ) / (IC*T),  G = sum_t x[t,u,a] x[t,v,b]
+// which removes the 1024-long theta/phi contraction.  The (N,T,V,3) input is read directly; the
+// 128-channel output is produced by one bf16 mma.sync k-step per 16 positions and written once.
+//
+//   gcn0_scores_kernel   per sample: M_i = softmax_u(S_i) + A_i + PA_i, per-sample moments of r
+//   gcn0_finalize_kernel 1 CTA: fp64 reduce of moments -> E, Cov -> BN stats -> folded weights
+//   gcn0_apply_kernel    per (sample, frame chunk): z -> A operand -> MMA -> ReLU -> coalesced store
+// Backward (parameter gradients only): gcn0_bwd_q / fin1 / dz / fin2, see afb_gcn0_bwd.
+#include "common.cuh"
+
+namespace afb {
+namespace {
+
+constexpr int NR = AFB_GCN0_NR;
+constexpr int NMOM = AFB_GCN0_NMOM;
+constexpr int NSTAT = AFB_GCN0_NSTAT_BASE;
+constexpr int kThreads = 256;
+
+__host__ __device__ constexpr int a4(int n) { return (n + 3) & ~3; }  // keep smem sections 16-byte aligned
+__host__ __device__ constexpr int tri(int j, int k) { return NR + j * NR - (j * (j - 1)) / 2 + (k - j); }  // j <= k
+
+struct Coef {  // per subset: C (3x3), e (3), f (3)
+  float v[3][16];
+};
+
+__device__ void compute_coef(const afb_gcn0_fwd_t& p, float (*coef)[16]) {
+  for (int t = threadIdx.x; t < 45; t += blockDim.x) {
+    const int i = t / 15, q = t % 15;
+    const float* Wa = p.Wa[i];
+    const float* Wb = p.Wb[i];
+    float acc = 0.f;
+    if (q < 9) {
+      const int a = q / 3, b = q % 3;
+      for (int c = 0; c < p.IC; ++c) acc += Wa[c * 3 + a] * Wb[c * 3 + b];
+    } else if (q < 12) {
+      const int a = q - 9;
+      for (int c = 0; c < p.IC; ++c) acc += Wa[c * 3 + a] * p.bb[i][c];
+    } else {
+      const int b = q - 12;
+      for (int c = 0; c < p.IC; ++c) acc += p.ba[i][c] * Wb[c * 3 + b];
+    }
+    coef[i][q] = acc;
+  }
+}
+
+// g[a][b] = sum_t x[t,u,a] x[t,v,b], su[a] = sum_t x[t,u,a], sv[b] = sum_t x[t,v,b]
+__device__ __forceinline__ void gram_pair(const float* xs, int T, int V, int u, int v, float (&g)[9], float (&su)[3], float (&sv)[3]) {
+#pragma unroll
+  for (int q = 0; q < 9; ++q) g[q] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { su[a] = 0.f; sv[a] = 0.f; }
+  for (int t = 0; t < T; ++t) {
+    const float* xu = xs + (t * V + u) * 3;
+    const float* xv = xs + (t * V + v) * 3;
+    const float u0 = xu[0], u1 = xu[1], u2 = xu[2], v0 = xv[0], v1 = xv[1], v2 = xv[2];
+    g[0] += u0 * v0; g[1] += u0 * v1; g[2] += u0 * v2;
+    g[3] += u1 * v0; g[4] += u1 * v1; g[5] += u1 * v2;
+    g[6] += u2 * v0; g[7] += u2 * v1; g[8] += u2 * v2;
+    su[0] += u0; su[1] += u1; su[2] += u2;
+    sv[0] += v0; sv[1] += v1; sv[2] += v2;
+  }
+}
+
+// r[0..8] = z (subset-major, channel-minor), r[9..11] = x   for position (t, v) of the staged frames
+__device__ __forceinline__ void position_r(const float* xs, const float* Ms, int V, int tl, int v, float (&r)[NR]) {
+#pragma unroll
+  for (int j = 0; j < 9; ++j) r[j] = 0.f;
+  const float* xt = xs + tl * V * 3;
+  for (int u = 0; u < V; ++u) {
+    const float x0 = xt[u * 3], x1 = xt[u * 3 + 1], x2 = xt[u * 3 + 2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float m = Ms[(i * V + u) * V + v];
+      r[i * 3 + 0] += x0 * m; r[i * 3 + 1] += x1 * m; r[i * 3 + 2] += x2 * m;
+    }
+  }
+  r[9] = xt[v * 3]; r[10] = xt[v * 3 + 1]; r[11] = xt[v * 3 + 2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward 1: mixing matrices + per-sample moments
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) gcn0_scores_kernel(const afb_gcn0_fwd_t p) {
+  extern __shared__ float sm[];
+  const int T = p.T, V = p.V, n = blockIdx.x;
+  float* xs = sm;                    // [T*V*3]
+  float* Ms = xs + T * V * 3;        // [3][V][V]
+  float* red = Ms + 3 * V * V;       // [8][NMOM]
+  __shared__ float coef[3][16];
+  const float* xg = p.x + (int64_t)n * T * V * 3;
+  for (int i = threadIdx.x; i < T * V * 3; i += blockDim.x) xs[i] = xg[i];
+  compute_coef(p, coef);
+  __syncthreads();
+  const float inv = 1.0f / (float)(p.IC * T);
+  for (int pr = threadIdx.x; pr < V * V; pr += blockDim.x) {
+    const int u = pr / V, v = pr % V;
+    float g[9], su[3], sv[3];
+    gram_pair(xs, T, V, u, v, g, su, sv);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) s += coef[i][q] * g[q];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) s += coef[i][9 + a] * su[a] + coef[i][12 + a] * sv[a];
+      Ms[(i * V + u) * V + v] = s * inv;
+    }
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < 3 * V; col += blockDim.x) {  // softmax over u for fixed (i, v)
+    const int i = col / V, v = col % V;
+    float mx = -INFINITY;
+    for (int u = 0; u < V; ++u) mx = fmaxf(mx, Ms[(i * V + u) * V + v]);
+    float den = 0.f;
+    for (int u = 0; u < V; ++u) den += __expf(Ms[(i * V + u) * V + v] - mx);
+    const float rden = 1.0f / den;
+    for (int u = 0; u < V; ++u) {
+      const int idx = (i * V + u) * V + v;
+      const float m = __expf(Ms[idx] - mx) * rden + p.A[idx] + p.PA[idx];
+      Ms[idx] = m;
+      p.Mmat[(int64_t)n * 3 * V * V + idx] = m;
+    }
+  }
+  __syncthreads();
+  float acc[NMOM - 6];  // 90 used
+#pragma unroll
+  for (int j = 0; j < 90; ++j) acc[j] = 0.f;
+  for (int pos = threadIdx.x; pos < T * V; pos += blockDim.x) {
+    float r[NR];
+    position_r(xs, Ms, V, pos / V, pos % V, r);
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      acc[j] += r[j];
+#pragma unroll
+      for (int k = j; k < NR; ++k) acc[tri(j, k)] += r[j] * r[k];
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 90; ++j) {
+    const float s = warp_sum(acc[j]);
+    if (lane == 0) red[warp * NMOM + j] = s;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < NMOM; j += blockDim.x) {
+    float s = 0.f;
+    if (j < 90)
+      for (int w = 0; w < kThreads / 32; ++w) s += red[w * NMOM + j];
+    p.moments[(int64_t)n * NMOM + j] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward 2: statistics + folded weights (single CTA)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) gcn0_finalize_kernel(const afb_gcn0_fwd_t p) {
+  __shared__ double dred[10][NMOM];
+  __shared__ double E[NR];
+  __shared__ double Cov[NR][NR];
+  const int tid = threadIdx.x;
+  const int col = tid % NMOM, rl = tid / NMOM;
+  if (rl < 10) {
+    double s = 0.0;
+    for (int n = rl; n < p.N; n += 10) s += (double)p.moments[(int64_t)n * NMOM + col];
+    dred[rl][col] = s;
+  }
+  __syncthreads();
+  if (tid < NMOM) {
+    double s = 0.0;
+    for (int l = 0; l < 10; ++l) s += dred[l][tid];
+    dred[0][tid] = s;
+  }
+  __syncthreads();
+  const double m = (double)p.N * p.T * p.V;
+  if (tid < NR) E[tid] = dred[0][tid] / m;
+  __syncthreads();
+  if (tid < NR * NR) {
+    const int j = tid / NR, k = tid % NR;
+    const int a = j < k ? j : k, b = j < k ? k : j;
+    Cov[j][k] = dred[0][tri(a, b)] / m - E[j] * E[k];
+  }
+  __syncthreads();
+  if (tid < NR) p.stats[tid] = (float)E[tid];
+  if (tid < NR * NR) p.stats[NR + tid] = (float)Cov[tid / NR][tid % NR];
+  for (int o = tid; o < p.Cout; o += blockDim.x) {
+    double w[NR];
+    double b = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      for (int a = 0; a < 3; ++a) w[i * 3 + a] = p.Wd[i][o * 3 + a];
+      b += p.bd[i][o];
+    }
+    for (int a = 0; a < 3; ++a) w[9 + a] = p.Wdn[o * 3 + a];
+    double mean_h = b, mean_d = p.bdn[o], var_h = 0.0, var_d = 0.0;
+    for (int j = 0; j < 9; ++j) {
+      mean_h += w[j] * E[j];
+      for (int k = 0; k < 9; ++k) var_h += w[j] * Cov[j][k] * w[k];
+    }
+    for (int j = 9; j < 12; ++j) {
+      mean_d += w[j] * E[j];
+      for (int k = 9; k < 12; ++k) var_d += w[j] * Cov[j][k] * w[k];
+    }
+    if (var_h < 0.0) var_h = 0.0;
+    if (var_d < 0.0) var_d = 0.0;
+    // mean of the pre-BN activations at the batch centre (used to fold the constant term)
+    const double ctr_h = mean_h, ctr_d = mean_d;
+    if (p.training) {
+      const double unb = m > 1.0 ? m / (m - 1.0) : 1.0;
+      p.bn_rm[o] = (float)((1.0 - p.momentum) * p.bn_rm[o] + p.momentum * mean_h);
+      p.bn_rv[o] = (float)((1.0 - p.momentum) * p.bn_rv[o] + p.momentum * var_h * unb);
+      p.dn_rm[o] = (float)((1.0 - p.momentum) * p.dn_rm[o] + p.momentum * mean_d);
+      p.dn_rv[o] = (float)((1.0 - p.momentum) * p.dn_rv[o] + p.momentum * var_d * unb);
+    } else {
+      mean_h = p.bn_rm[o]; var_h = p.bn_rv[o];
+      mean_d = p.dn_rm[o]; var_d = p.dn_rv[o];
+    }
+    const double rstd_h = 1.0 / sqrt(var_h + (double)p.eps), rstd_d = 1.0 / sqrt(var_d + (double)p.eps);
+    const double sh = p.bn_g[o] * rstd_h, sd = p.dn_g[o] * rstd_d;
+    float* wf = p.Wfold + o * 16;
+    for (int j = 0; j < 9; ++j) wf[j] = (float)(sh * w[j]);
+    for (int j = 9; j < 12; ++j) wf[j] = (float)(sd * w[j]);
+    wf[12] = (float)(sh * (ctr_h - mean_h) + p.bn_b[o] + sd * (ctr_d - mean_d) + p.dn_b[o]);
+    wf[13] = wf[14] = wf[15] = 0.f;
+    p.stats[NSTAT + o] = (float)mean_h;
+    p.stats[NSTAT + p.Cout + o] = (float)rstd_h;
+    p.stats[NSTAT + 2 * p.Cout + o] = (float)mean_d;
+    p.stats[NSTAT + 3 * p.Cout + o] = (float)rstd_d;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward 3: apply
+// ---------------------------------------------------------------------------------------------
+constexpr int kARow = 24;  // bf16 elements per A-operand row (16 used): 48 B rows keep LDS.32 conflict-free
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f), "f"(0.f), "f"(0.f), "f"(0.f));
+}
+
+// COUT: output channels (compile time for the MMA path).  TT frames per CTA, P = TT*V positions.
+template <bool MMA, typename TY, int COUT>
+__global__ void __launch_bounds__(kThreads) gcn0_apply_kernel(const afb_gcn0_fwd_t p, int TT, int chunks) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int V = p.V, T = p.T;
+  const int n = blockIdx.x / chunks, t0 = (blockIdx.x % chunks) * TT;
+  const int tt = min(TT, T - t0);
+  const int P = tt * V, P16 = (TT * V + 15) / 16 * 16;
+  const int Cout = MMA ? COUT : p.Cout;
+  float* Ms = reinterpret_cast<float*>(smraw);        // [3*V*V]
+  float* xs = Ms + a4(3 * V * V);                     // [TT*V*3]
+  float* ctr = xs + a4(TT * V * 3);                   // [16]
+  uint8_t* after = reinterpret_cast<uint8_t*>(ctr + 16);
+  const float* Mg = p.Mmat + (int64_t)n * 3 * V * V;
+  for (int i = threadIdx.x; i < 3 * V * V; i += blockDim.x) Ms[i] = Mg[i];
+  const float* xg = p.x + ((int64_t)n * T + t0) * V * 3;
+  for (int i = threadIdx.x; i < P * 3; i += blockDim.x) xs[i] = xg[i];
+  if (threadIdx.x < 16) ctr[threadIdx.x] = threadIdx.x < NR ? p.stats[threadIdx.x] : 0.f;
+  const int64_t row0 = ((int64_t)n * T + t0) * V;
+
+  if constexpr (MMA) {
+    bf16* Aop = reinterpret_cast<bf16*>(after);                        // [P16][kARow]
+    bf16* tile = Aop + P16 * kARow;                                    // [P16][COUT + 8]
+    constexpr int kTileRow = COUT + 8;
+    // B fragments of all COUT/8 n-tiles live in registers for the whole kernel
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tq = lane & 3;
+    uint32_t bfrag[COUT / 8][2];
+#pragma unroll
+    for (int nt = 0; nt < COUT / 8; ++nt) {
+      const float* wf = p.Wfold + (nt * 8 + g) * 16;
+      bfrag[nt][0] = pack_bf16(wf[2 * tq], wf[2 * tq + 1]);
+      bfrag[nt][1] = pack_bf16(wf[2 * tq + 8], wf[2 * tq + 9]);
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < P16 * 4; it += blockDim.x) {
+      const int pos = it >> 2, i = it & 3;
+      bf16* dst = Aop + pos * kARow + i * 4;  // slots: [0..8] z, [9..11] x, [12] one, [13..15] zero
+      if (pos >= P) {
+        if (i < 3) { dst = Aop + pos * kARow + i * 3; dst[0] = dst[1] = dst[2] = __float2bfloat16_rn(0.f); }
+        else { dst = Aop + pos * kARow + 9; for (int q = 0; q < 7; ++q) dst[q] = __float2bfloat16_rn(0.f); }
+        continue;
+      }
+      const int tl = pos / V, v = pos % V;
+      const float* xt = xs + tl * V * 3;
+      if (i < 3) {
+        float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+        for (int u = 0; u < V; ++u) {
+          const float m = Ms[(i * V + u) * V + v];
+          z0 += xt[u * 3] * m; z1 += xt[u * 3 + 1] * m; z2 += xt[u * 3 + 2] * m;
+        }
+        dst = Aop + pos * kARow + i * 3;
+        dst[0] = __float2bfloat16_rn(z0 - ctr[i * 3]);
+        dst[1] = __float2bfloat16_rn(z1 - ctr[i * 3 + 1]);
+        dst[2] = __float2bfloat16_rn(z2 - ctr[i * 3 + 2]);
+      } else {
+        dst = Aop + pos * kARow + 9;
+        dst[0] = __float2bfloat16_rn(xt[v * 3] - ctr[9]);
+        dst[1] = __float2bfloat16_rn(xt[v * 3 + 1] - ctr[10]);
+        dst[2] = __float2bfloat16_rn(xt[v * 3 + 2] - ctr[11]);
+        dst[3] = __float2bfloat16_rn(1.f);
+        dst[4] = dst[5] = dst[6] = __float2bfloat16_rn(0.f);
+      }
+    }
+    __syncthreads();
+    for (int mt = warp; mt < P16 / 16; mt += kThreads / 32) {
+      uint32_t a[4];
+      const bf16* ar = Aop + (mt * 16 + g) * kARow;
+      a[0] = *reinterpret_cast<const uint32_t*>(ar + 2 * tq);
+      a[1] = *reinterpret_cast<const uint32_t*>(ar + 8 * kARow + 2 * tq);
+      a[2] = *reinterpret_cast<const uint32_t*>(ar + 2 * tq + 8);
+      a[3] = *reinterpret_cast<const uint32_t*>(ar + 8 * kARow + 2 * tq + 8);
+#pragma unroll
+      for (int nt = 0; nt < COUT / 8; ++nt) {
+        float d[4];
+        mma_bf16_16816(d, a, bfrag[nt][0], bfrag[nt][1]);
+        bf16* o0 = tile + (mt * 16 + g) * kTileRow + nt * 8 + 2 * tq;
+        *reinterpret_cast<uint32_t*>(o0) = pack_bf16(fmaxf(d[0], 0.f), fmaxf(d[1], 0.f));
+        *reinterpret_cast<uint32_t*>(o0 + 8 * kTileRow) = pack_bf16(fmaxf(d[2], 0.f), fmaxf(d[3], 0.f));
+      }
+    }
+    __syncthreads();
+    bf16* yg = reinterpret_cast<bf16*>(p.y) + row0 * COUT;
+    for (int idx = threadIdx.x; idx < P * (COUT / 8); idx += blockDim.x) {
+      const int r = idx / (COUT / 8), c8 = idx % (COUT / 8);
+      *reinterpret_cast<uint4*>(yg + (int64_t)r * COUT + c8 * 8) = *reinterpret_cast<const uint4*>(tile + r * kTileRow + c8 * 8);
+    }
+  } else {
+    float* Aop = reinterpret_cast<float*>(after);   // [TT*V][13]
+    float* Wf = Aop + TT * V * 13;                  // [Cout][13]
+    for (int i = threadIdx.x; i < Cout * 13; i += blockDim.x) Wf[i] = p.Wfold[(i / 13) * 16 + (i % 13)];
+    __syncthreads();
+    for (int pos = threadIdx.x; pos < P; pos += blockDim.x) {
+      float r[NR];
+      position_r(xs, Ms, V, pos / V, pos % V, r);
+#pragma unroll
+      for (int j = 0; j < NR; ++j) Aop[pos * 13 + j] = r[j] - ctr[j];
+      Aop[pos * 13 + 12] = 1.f;
+    }
+    __syncthreads();
+    TY* yg = reinterpret_cast<TY*>(p.y) + row0 * Cout;
+    for (int idx = threadIdx.x; idx < P * Cout; idx += blockDim.x) {
+      const int pos = idx / Cout, c = idx % Cout;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 13; ++j) acc += Aop[pos * 13 + j] * Wf[c * 13 + j];
+      stf<TY>(yg + idx, fmaxf(acc, 0.f));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+// workspace layout (floats): Q [Cout][16] | U [Cout][16] | cvec [16] | Kmat [9][9 -> 96] | gram [3][16]
+__host__ __device__ inline int ws_Q(int) { return 0; }
+__host__ __device__ inline int ws_U(int cout) { return 16 * cout; }
+__host__ __device__ inline int ws_c(int cout) { return 32 * cout; }
+__host__ __device__ inline int ws_K(int cout) { return 32 * cout + 16; }
+__host__ __device__ inline int ws_gram(int cout) { return 32 * cout + 16 + 96; }
+
+// pass 1: Q[o][j] = sum_pos g1[pos,o] * (r_j - E_j)  (j < 12),  Q[o][12] = sum_pos g1[pos,o]
+template <typename TY>
+__global__ void __launch_bounds__(kThreads) gcn0_bwd_q_kernel(const afb_gcn0_bwd_t b, int TT, int chunks) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const afb_gcn0_fwd_t& p = b.f;
+  const int V = p.V, T = p.T, Cout = p.Cout;
+  const int n = blockIdx.x / chunks, t0 = (blockIdx.x % chunks) * TT;
+  const int tt = min(TT, T - t0);
+  const int P = tt * V;
+  float* Ms = reinterpret_cast<float*>(smraw);
+  float* xs = Ms + 3 * V * V;
+  float* ctr = xs + TT * V * 3;
+  float* Aop = ctr + 16;             // [TT*V][13]
+  float* part = Aop + TT * V * 13;   // [kThreads][13]
+  const float* Mg = p.Mmat + (int64_t)n * 3 * V * V;
+  for (int i = threadIdx.x; i < 3 * V * V; i += blockDim.x) Ms[i] = Mg[i];
+  const float* xg = p.x + ((int64_t)n * T + t0) * V * 3;
+  for (int i = threadIdx.x; i < P * 3; i += blockDim.x) xs[i] = xg[i];
+  if (threadIdx.x < 16) ctr[threadIdx.x] = threadIdx.x < NR ? p.stats[threadIdx.x] : 0.f;
+  __syncthreads();
+  for (int pos = threadIdx.x; pos < P; pos += blockDim.x) {
+    float r[NR];
+    position_r(xs, Ms, V, pos / V, pos % V, r);
+#pragma unroll
+    for (int j = 0; j < NR; ++j) Aop[pos * 13 + j] = r[j] - ctr[j];
+    Aop[pos * 13 + 12] = 1.f;
+  }
+  __syncthreads();
+  const int64_t row0 = ((int64_t)n * T + t0) * V;
+  const TY* dy = reinterpret_cast<const TY*>(b.dy) + row0 * Cout;
+  const TY* y = reinterpret_cast<const TY*>(p.y) + row0 * Cout;
+  const int o = threadIdx.x % Cout, part_id = threadIdx.x / Cout, nparts = kThreads / Cout;
+  float acc[13];
+#pragma unroll
+  for (int j = 0; j < 13; ++j) acc[j] = 0.f;
+  if (part_id < nparts) {
+    for (int pos = part_id; pos < P; pos += nparts) {
+      const float yv = ldf<TY>(y + (int64_t)pos * Cout + o);
+      if (yv > 0.f) {
+        const float g1 = ldf<TY>(dy + (int64_t)pos * Cout + o);
+#pragma unroll
+        for (int j = 0; j < 13; ++j) acc[j] += g1 * Aop[pos * 13 + j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 13; ++j) part[threadIdx.x * 13 + j] = acc[j];
+  __syncthreads();
+  for (int e = threadIdx.x; e < Cout * 13; e += blockDim.x) {
+    const int oo = e / 13, j = e % 13;
+    float s = 0.f;
+    for (int q = 0; q < nparts; ++q) s += part[(q * Cout + oo) * 13 + j];
+    atomicAdd(b.ws + ws_Q(Cout) + oo * 16 + j, s);
+  }
+}
+
+// finalize 1: BN / conv_d / down gradients, and U, c, K for the dz pass (single CTA, thread per channel)
+__global__ void gcn0_bwd_fin1_kernel(const afb_gcn0_bwd_t b) {
+  const afb_gcn0_fwd_t& p = b.f;
+  const int Cout = p.Cout;
+  __shared__ float E[NR];
+  __shared__ float Cov[NR][NR];
+  extern __shared__ float shm[];  // per channel: u[9], coefK, dbeta  -> [Cout][12]
+  if (threadIdx.x < NR) E[threadIdx.x] = p.stats[threadIdx.x];
+  for (int i = threadIdx.x; i < NR * NR; i += blockDim.x) Cov[i / NR][i % NR] = p.stats[NR + i];
+  __syncthreads();
+  const double m = (double)p.N * p.T * p.V;
+  for (int o = threadIdx.x; o < Cout; o += blockDim.x) {
+    float w[NR];
+    for (int i = 0; i < 3; ++i)
+      for (int a = 0; a < 3; ++a) w[i * 3 + a] = p.Wd[i][o * 3 + a];
+    for (int a = 0; a < 3; ++a) w[9 + a] = p.Wdn[o * 3 + a];
+    const float rstd_h = p.stats[NSTAT + Cout + o], rstd_d = p.stats[NSTAT + 3 * Cout + o];
+    const float ga = p.bn_g[o], gd = p.dn_g[o];
+    const float* Q = b.ws + ws_Q(Cout) + o * 16;
+    const float dbeta = Q[12];
+    float dgam = 0.f, dgam_d = 0.f;
+    for (int j = 0; j < 9; ++j) dgam += w[j] * Q[j];
+    for (int j = 9; j < 12; ++j) dgam_d += w[j] * Q[j];
+    dgam *= rstd_h;
+    dgam_d *= rstd_d;
+    atomicAdd(b.dbn_g + o, dgam);
+    atomicAdd(b.dbn_b + o, dbeta);
+    atomicAdd(b.ddn_g + o, dgam_d);
+    atomicAdd(b.ddn_b + o, dbeta);
+    for (int j = 0; j < 9; ++j) {
+      float cw = 0.f;
+      for (int k = 0; k < 9; ++k) cw += Cov[j][k] * w[k];
+      atomicAdd(b.dWd[j / 3] + o * 3 + (j % 3), ga * rstd_h * (Q[j] - dgam * rstd_h * cw));
+    }
+    for (int j = 9; j < 12; ++j) {
+      float cw = 0.f;
+      for (int k = 9; k < 12; ++k) cw += Cov[j][k] * w[k];
+      atomicAdd(b.dWdn + o * 3 + (j - 9), gd * rstd_d * (Q[j] - dgam_d * rstd_d * cw));
+    }
+    // conv biases feeding a batch-stat BN have exactly zero gradient (dbd, dbdn += 0)
+    float* U = b.ws + ws_U(Cout) + o * 16;
+    for (int j = 0; j < 9; ++j) {
+      U[j] = ga * rstd_h * w[j];
+      shm[o * 12 + j] = w[j];
+    }
+    for (int j = 9; j < 16; ++j) U[j] = 0.f;
+    shm[o * 12 + 9] = (float)(ga * rstd_h * rstd_h * dgam / m);   // K coefficient
+    shm[o * 12 + 10] = (float)(ga * rstd_h * dbeta / m);          // c coefficient
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 9 + 81; e += blockDim.x) {
+    float s = 0.f;
+    if (e < 9) {
+      for (int o = 0; o < Cout; ++o) s += shm[o * 12 + e] * shm[o * 12 + 10];
+      b.ws[ws_c(Cout) + e] = s;
+    } else {
+      const int k = (e - 9) / 9, j = (e - 9) % 9;
+      for (int o = 0; o < Cout; ++o) s += shm[o * 12 + k] * shm[o * 12 + 9] * shm[o * 12 + j];
+      b.ws[ws_K(Cout) + k * 9 + j] = s;
+    }
+  }
+}
+
+// pass 2 (one CTA per sample): dz -> dM -> dPA, dS -> Gram-form gradients of theta/phi
+template <typename TY, int CPL>
+__global__ void __launch_bounds__(kThreads) gcn0_bwd_dz_kernel(const afb_gcn0_bwd_t b) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const afb_gcn0_fwd_t& p = b.f;
+  const int V = p.V, T = p.T, Cout = p.Cout, n = blockIdx.x;
+  float* xs = reinterpret_cast<float*>(smraw);   // [T*V*3]
+  float* Ms = xs + T * V * 3;                    // [3VV]
+  float* dM = Ms + 3 * V * V;                    // [3VV]
+  float* dz = dM + 3 * V * V;                    // [T*V][9]
+  float* cK = dz + T * V * 9;                    // c[9], pad to 16, K[81], E[12]
+  float* red = cK + 16 + 96 + 16;                // [8][48]
+  const float* xg = p.x + (int64_t)n * T * V * 3;
+  for (int i = threadIdx.x; i < T * V * 3; i += blockDim.x) xs[i] = xg[i];
+  const float* Mg = p.Mmat + (int64_t)n * 3 * V * V;
+  for (int i = threadIdx.x; i < 3 * V * V; i += blockDim.x) Ms[i] = Mg[i];
+  for (int i = threadIdx.x; i < 16 + 96; i += blockDim.x) cK[i] = b.ws[ws_c(Cout) + i];
+  if (threadIdx.x < 16) cK[16 + 96 + threadIdx.x] = threadIdx.x < NR ? p.stats[threadIdx.x] : 0.f;
+  const float* cvec = cK;
+  const float* Kmat = cK + 16;
+  const float* E = cK + 16 + 96;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float U[CPL][9];
+#pragma unroll
+  for (int q = 0; q < CPL; ++q)
+#pragma unroll
+    for (int j = 0; j < 9; ++j) U[q][j] = b.ws[ws_U(Cout) + (lane * CPL + q) * 16 + j];
+  __syncthreads();
+  const TY* dy = reinterpret_cast<const TY*>(b.dy) + (int64_t)n * T * V * Cout;
+  const TY* y = reinterpret_cast<const TY*>(p.y) + (int64_t)n * T * V * Cout;
+  for (int pos = warp; pos < T * V; pos += kThreads / 32) {
+    float part[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) part[j] = 0.f;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane * CPL + q;
+      const float yv = ldf<TY>(y + (int64_t)pos * Cout + c);
+      const float g1 = yv > 0.f ? ldf<TY>(dy + (int64_t)pos * Cout + c) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) part[j] += g1 * U[q][j];
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) part[j] = warp_sum(part[j]);
+    // lane k < 9 computes the centred z_k of this position
+    const int tl = pos / V, v = pos % V;
+    float rc = 0.f;
+    if (lane < 9) {
+      const int i = lane / 3, a = lane % 3;
+      const float* xt = xs + tl * V * 3;
+      for (int u = 0; u < V; ++u) rc += xt[u * 3 + a] * Ms[(i * V + u) * V + v];
+      rc -= E[lane];
+    }
+    float corr = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float rk = __shfl_sync(0xffffffffu, rc, k);
+      if (lane < 9) corr += rk * Kmat[k * 9 + lane];
+    }
+    if (lane < 9) {
+      float mine = part[0];
+#pragma unroll
+      for (int j = 1; j < 9; ++j) mine = lane == j ? part[j] : mine;
+      dz[pos * 9 + lane] = mine - cvec[lane] - corr;
+    }
+  }
+  __syncthreads();
+  // dM_i[u][v] = sum_{t,a} x[t,u,a] * dz[(t,v)][3i+a]
+  for (int e = threadIdx.x; e < 3 * V * V; e += blockDim.x) {
+    const int i = e / (V * V), u = (e / V) % V, v = e % V;
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float* xu = xs + (t * V + u) * 3;
+      const float* d = dz + (t * V + v) * 9 + i * 3;
+      s += xu[0] * d[0] + xu[1] * d[1] + xu[2] * d[2];
+    }
+    dM[e] = s;
+    atomicAdd(b.dPA + e, s);
+  }
+  __syncthreads();
+  // dS = P * (dM - sum_u P*dM) per column (i, v);  P = M - (A + PA)
+  for (int col = threadIdx.x; col < 3 * V; col += blockDim.x) {
+    const int i = col / V, v = col % V;
+    float dot = 0.f;
+    for (int u = 0; u < V; ++u) {
+      const int idx = (i * V + u) * V + v;
+      const float pr = Ms[idx] - p.A[idx] - p.PA[idx];
+      dot += pr * dM[idx];
+    }
+    for (int u = 0; u < V; ++u) {
+      const int idx = (i * V + u) * V + v;
+      const float pr = Ms[idx] - p.A[idx] - p.PA[idx];
+      dM[idx] = pr * (dM[idx] - dot);
+    }
+  }
+  __syncthreads();
+  float acc[45];
+#pragma unroll
+  for (int q = 0; q < 45; ++q) acc[q] = 0.f;
+  for (int pr = threadIdx.x; pr < V * V; pr += blockDim.x) {
+    const int u = pr / V, v = pr % V;
+    float g[9], su[3], sv[3];
+    gram_pair(xs, T, V, u, v, g, su, sv);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float ds = dM[(i * V + u) * V + v];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) acc[i * 15 + q] += ds * g[q];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { acc[i * 15 + 9 + a] += ds * su[a]; acc[i * 15 + 12 + a] += ds * sv[a]; }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 45; ++q) {
+    const float s = warp_sum(acc[q]);
+    if (lane == 0) red[warp * 48 + q] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 45) {
+    float s = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w * 48 + threadIdx.x];
+    const float inv = 1.0f / (float)(p.IC * T);
+    atomicAdd(b.ws + ws_gram(Cout) + (threadIdx.x / 15) * 16 + threadIdx.x % 15, s * inv);
+  }
+}
+
+// finalize 2: chain rule through C = Wa^T Wb, e = Wa^T bb, f = Wb^T ba
+__global__ void gcn0_bwd_fin2_kernel(const afb_gcn0_bwd_t b) {
+  const afb_gcn0_fwd_t& p = b.f;
+  for (int e = threadIdx.x; e < 3 * p.IC; e += blockDim.x) {
+    const int i = e / p.IC, c = e % p.IC;
+    const float* G = b.ws + ws_gram(p.Cout) + i * 16;  // dC[9], de[3], df[3]
+    const float* Wa = p.Wa[i] + c * 3;
+    const float* Wb = p.Wb[i] + c * 3;
+    float dbb = 0.f, dba = 0.f;
+    for (int a = 0; a < 3; ++a) {
+      float s = 0.f;
+      for (int q = 0; q < 3; ++q) s += Wb[q] * G[a * 3 + q];
+      atomicAdd(b.dWa[i] + c * 3 + a, s + p.bb[i][c] * G[9 + a]);
+      dbb += Wa[a] * G[9 + a];
+    }
+    for (int q = 0; q < 3; ++q) {
+      float s = 0.f;
+      for (int a = 0; a < 3; ++a) s += Wa[a] * G[a * 3 + q];
+      atomicAdd(b.dWb[i] + c * 3 + q, s + p.ba[i][c] * G[12 + q]);
+      dba += Wb[q] * G[12 + q];
+    }
+    atomicAdd(b.dba[i] + c, dba);
+    atomicAdd(b.dbb[i] + c, dbb);
+  }
+}
+
+int pick_tt(int T, int V) {
+  int tt = 192 / V;
+  if (tt < 1) tt = 1;
+  if (tt > T) tt = T;
+  return tt;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes, const char* what) {
+  if (bytes <= 48 * 1024) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%zu) failed: %s", what, bytes, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+int check_fwd_args(const afb_gcn0_fwd_t* p) {
+  AFB_REQUIRE(p && p->x && p->A && p->PA && p->Mmat && p->moments && p->stats && p->Wfold && p->y, "gcn0: null pointer");
+  for (int i = 0; i < 3; ++i)
+    AFB_REQUIRE(p->Wa[i] && p->ba[i] && p->Wb[i] && p->bb[i] && p->Wd[i] && p->bd[i], "gcn0: null weight pointer");
+  AFB_REQUIRE(p->Wdn && p->bdn && p->bn_g && p->bn_b && p->dn_g && p->dn_b && p->bn_rm && p->bn_rv && p->dn_rm && p->dn_rv,
+              "gcn0: null BN pointer");
+  AFB_REQUIRE(p->N > 0 && p->T > 0 && p->V > 0 && p->V <= 64, "gcn0: bad shape N=%d T=%d V=%d (V<=64)", p->N, p->T, p->V);
+  AFB_REQUIRE(p->Cout % 32 == 0 && p->Cout <= 256, "gcn0: Cout=%d unsupported", p->Cout);
+  return 0;
+}
+
+}  // namespace
+}  // namespace afb
+
+using namespace afb;
+
+extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
+  int rc = check_fwd_args(p);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(s);
+  const int T = p->T, V = p->V;
+  {
+    const size_t smem = ((size_t)T * V * 3 + 3 * V * V + 8 * NMOM) * sizeof(float);
+    AFB_REQUIRE(smem <= 220 * 1024, "gcn0: T*V too large for the per-sample shared-memory stage (%zu B)", smem);
+    if ((rc = set_smem(gcn0_scores_kernel, smem, "gcn0_scores"))) return rc;
+    gcn0_scores_kernel<<<p->N, kThreads, smem, st>>>(*p);
+    if ((rc = check_launch("gcn0_scores"))) return rc;
+  }
+  gcn0_finalize_kernel<<<1, 1024, 0, st>>>(*p);
+  if ((rc = check_launch("gcn0_finalize"))) return rc;
+  const int TT = pick_tt(T, V), chunks = ceil_div(T, TT);
+  const int P16 = (TT * V + 15) / 16 * 16;
+  const size_t head = ((size_t)a4(3 * V * V) + a4(TT * V * 3) + 16) * sizeof(float);
+  const bool mma = !p->precise && p->y_dtype == AFB_BF16 && p->Cout == 128;
+  if (mma) {
+    const size_t smem = head + (size_t)P16 * kARow * 2 + (size_t)P16 * (128 + 8) * 2;
+    if ((rc = set_smem(gcn0_apply_kernel<true, bf16, 128>, smem, "gcn0_apply"))) return rc;
+    gcn0_apply_kernel<true, bf16, 128><<<p->N * chunks, kThreads, smem, st>>>(*p, TT, chunks);
+  } else {
+    const size_t smem = head + ((size_t)TT * V * 13 + (size_t)p->Cout * 13) * sizeof(float);
+    if (p->y_dtype == AFB_BF16) {
+      if ((rc = set_smem(gcn0_apply_kernel<false, bf16, 0>, smem, "gcn0_apply"))) return rc;
+      gcn0_apply_kernel<false, bf16, 0><<<p->N * chunks, kThreads, smem, st>>>(*p, TT, chunks);
+    } else {
+      if ((rc = set_smem(gcn0_apply_kernel<false, float, 0>, smem, "gcn0_apply"))) return rc;
+      gcn0_apply_kernel<false, float, 0><<<p->N * chunks, kThreads, smem, st>>>(*p, TT, chunks);
+    }
+  }
+  return check_launch("gcn0_apply");
+}
+
+extern "C" int afb_gcn0_bwd(const afb_gcn0_bwd_t* b, afb_stream s) {
+  AFB_REQUIRE(b && b->dy && b->ws && b->dPA && b->dWdn && b->dbdn && b->dbn_g && b->dbn_b && b->ddn_g && b->ddn_b, "gcn0_bwd: null pointer");
+  for (int i = 0; i < 3; ++i)
+    AFB_REQUIRE(b->dWa[i] && b->dba[i] && b->dWb[i] && b->dbb[i] && b->dWd[i] && b->dbd[i], "gcn0_bwd: null gradient pointer");
+  const afb_gcn0_fwd_t* p = &b->f;
+  int rc = check_fwd_args(p);
+  if (rc) return rc;
+  AFB_REQUIRE(p->training, "gcn0_bwd: only training-mode BatchNorm is differentiated");
+  AFB_REQUIRE(kThreads % p->Cout == 0 || p->Cout == 256, "gcn0_bwd: Cout=%d unsupported", p->Cout);
+  cudaStream_t st = as_stream(s);
+  const int T = p->T, V = p->V, Cout = p->Cout;
+  cudaError_t e = cudaMemsetAsync(b->ws, 0, sizeof(float) * AFB_GCN0_BWD_WS(Cout), st);
+  if (e != cudaSuccess) { set_error("gcn0_bwd: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+  const int TT = pick_tt(T, V), chunks = ceil_div(T, TT);
+  {
+    const size_t smem = ((size_t)3 * V * V + TT * V * 3 + 16 + (size_t)TT * V * 13 + kThreads * 13) * sizeof(float);
+    if (p->y_dtype == AFB_BF16) {
+      if ((rc = set_smem(gcn0_bwd_q_kernel<bf16>, smem, "gcn0_bwd_q"))) return rc;
+      gcn0_bwd_q_kernel<bf16><<<p->N * chunks, kThreads, smem, st>>>(*b, TT, chunks);
+    } else {
+      if ((rc = set_smem(gcn0_bwd_q_kernel<float>, smem, "gcn0_bwd_q"))) return rc;
+      gcn0_bwd_q_kernel<float><<<p->N * chunks, kThreads, smem, st>>>(*b, TT, chunks);
+    }
+    if ((rc = check_launch("gcn0_bwd_q"))) return rc;
+  }
+  gcn0_bwd_fin1_kernel<<<1, 256, (size_t)Cout * 12 * sizeof(float), st>>>(*b);
+  if ((rc = check_launch("gcn0_bwd_fin1"))) return rc;
+  {
+    const size_t smem = ((size_t)T * V * 3 + 6 * V * V + (size_t)T * V * 9 + 16 + 96 + 16 + 8 * 48) * sizeof(float);
+    AFB_REQUIRE(smem <= 220 * 1024, "gcn0_bwd: T*V too large for the per-sample shared-memory stage (%zu B)", smem);
+#define LAUNCH_DZ(TYPE, CPL_)                                                              \
+  do {                                                                                     \
+    if ((rc = set_smem(gcn0_bwd_dz_kernel<TYPE, CPL_>, smem, "gcn0_bwd_dz"))) return rc;   \
+    gcn0_bwd_dz_kernel<TYPE, CPL_><<<p->N, kThreads, smem, st>>>(*b);                      \
+  } while (0)
+    const int cpl = Cout / 32;
+    AFB_REQUIRE(cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8, "gcn0_bwd: Cout=%d unsupported", Cout);
+    if (p->y_dtype == AFB_BF16) {
+      if (cpl == 1) LAUNCH_DZ(bf16, 1); else if (cpl == 2) LAUNCH_DZ(bf16, 2); else if (cpl == 4) LAUNCH_DZ(bf16, 4); else LAUNCH_DZ(bf16, 8);
+    } else {
+      if (cpl == 1) LAUNCH_DZ(float, 1); else if (cpl == 2) LAUNCH_DZ(float, 2); else if (cpl == 4) LAUNCH_DZ(float, 4); else LAUNCH_DZ(float, 8);
+    }
+#undef LAUNCH_DZ
+    if ((rc = check_launch("gcn0_bwd_dz"))) return rc;
+  }
+  gcn0_bwd_fin2_kernel<<<1, 128, 0, st>>>(*b);
+  return check_launch("gcn0_bwd_fin2");
+}

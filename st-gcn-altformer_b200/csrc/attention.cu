@@ -1,0 +1,186 @@
+// Small-sequence multi-head attention (sequence length L <= 64: joints per frame or frames per joint).
+// Reference: model/AltFormer/model_ST.py:49-67.  One warp owns one (sequence, head): q/k/v slices
+// live in that warp's shared memory, scores and probabilities never leave the SM (the reference
+// materialises a [B, heads, L, L] tensor per block).  fp32 math on CUDA cores; the layout of qkv is the
+// one nn.Linear(dim, 3*dim) + reshape(B, L, 3, heads, dh) implies: feature = s*D + h*dh + d.
+#include "common.cuh"
+
+namespace afb {
+namespace {
+
+constexpr int kSmemBudget = 200 * 1024;
+
+template <typename T>
+__device__ __forceinline__ void load_slice(float* dst, const T* src, int L, int dh, int ld, int lane) {
+  // dst [L][dh+1] fp32; src points at (row 0, first feature of the head)
+  for (int l = 0; l < L; ++l)
+    for (int d = lane; d < dh; d += 32) dst[l * (dh + 1) + d] = ldf<T>(src + (int64_t)l * ld + d);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ o, int64_t items, int L, int heads,
+                                                       int dh, float scale, int per_warp_floats) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (item >= items) return;
+  const int h = (int)(item % heads);
+  const int64_t b = item / heads;
+  const int D = heads * dh, ld = 3 * D, st = dh + 1;
+  float* q = sm + (size_t)warp * per_warp_floats;
+  float* k = q + L * st;
+  float* v = k + L * st;
+  float* prow = v + L * st;
+  const T* base = qkv + (b * L) * ld + h * dh;
+  load_slice<T>(q, base, L, dh, ld, lane);
+  load_slice<T>(k, base + D, L, dh, ld, lane);
+  load_slice<T>(v, base + 2 * D, L, dh, ld, lane);
+  __syncwarp();
+  const int j0 = lane, j1 = lane + 32;
+  for (int i = 0; i < L; ++i) {
+    float s0 = -INFINITY, s1 = -INFINITY;
+    if (j0 < L) {
+      float a = 0.f;
+      for (int d = 0; d < dh; ++d) a += q[i * st + d] * k[j0 * st + d];
+      s0 = a * scale;
+    }
+    if (j1 < L) {
+      float a = 0.f;
+      for (int d = 0; d < dh; ++d) a += q[i * st + d] * k[j1 * st + d];
+      s1 = a * scale;
+    }
+    const float mx = warp_max(fmaxf(s0, s1));
+    const float e0 = j0 < L ? __expf(s0 - mx) : 0.f, e1 = j1 < L ? __expf(s1 - mx) : 0.f;
+    const float inv = 1.0f / warp_sum(e0 + e1);
+    if (j0 < L) prow[j0] = e0 * inv;
+    if (j1 < L) prow[j1] = e1 * inv;
+    __syncwarp();
+    for (int d = lane; d < dh; d += 32) {
+      float a = 0.f;
+      for (int j = 0; j < L; ++j) a += prow[j] * v[j * st + d];
+      stf<T>(o + (b * L + i) * D + h * dh + d, a);
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dO, T* __restrict__ dqkv,
+                                                       int64_t items, int L, int heads, int dh, float scale, int per_warp_floats) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (item >= items) return;
+  const int h = (int)(item % heads);
+  const int64_t b = item / heads;
+  const int D = heads * dh, ld = 3 * D, st = dh + 1, ps = L + 1;
+  float* q = sm + (size_t)warp * per_warp_floats;
+  float* k = q + L * st;
+  float* v = k + L * st;
+  float* go = v + L * st;
+  float* P = go + L * st;   // [L][L+1]
+  float* dS = P + L * ps;   // [L][L+1], already multiplied by `scale`
+  const T* base = qkv + (b * L) * ld + h * dh;
+  load_slice<T>(q, base, L, dh, ld, lane);
+  load_slice<T>(k, base + D, L, dh, ld, lane);
+  load_slice<T>(v, base + 2 * D, L, dh, ld, lane);
+  load_slice<T>(go, dO + (b * L) * D + h * dh, L, dh, D, lane);
+  __syncwarp();
+  const int j0 = lane, j1 = lane + 32;
+  for (int i = 0; i < L; ++i) {
+    float s0 = -INFINITY, s1 = -INFINITY, g0 = 0.f, g1 = 0.f;
+    if (j0 < L) {
+      float a = 0.f, c = 0.f;
+      for (int d = 0; d < dh; ++d) { a += q[i * st + d] * k[j0 * st + d]; c += go[i * st + d] * v[j0 * st + d]; }
+      s0 = a * scale; g0 = c;
+    }
+    if (j1 < L) {
+      float a = 0.f, c = 0.f;
+      for (int d = 0; d < dh; ++d) { a += q[i * st + d] * k[j1 * st + d]; c += go[i * st + d] * v[j1 * st + d]; }
+      s1 = a * scale; g1 = c;
+    }
+    const float mx = warp_max(fmaxf(s0, s1));
+    const float e0 = j0 < L ? __expf(s0 - mx) : 0.f, e1 = j1 < L ? __expf(s1 - mx) : 0.f;
+    const float inv = 1.0f / warp_sum(e0 + e1);
+    const float p0 = e0 * inv, p1 = e1 * inv;
+    const float delta = warp_sum(p0 * g0 + p1 * g1);
+    if (j0 < L) { P[i * ps + j0] = p0; dS[i * ps + j0] = scale * p0 * (g0 - delta); }
+    if (j1 < L) { P[i * ps + j1] = p1; dS[i * ps + j1] = scale * p1 * (g1 - delta); }
+  }
+  __syncwarp();
+  T* obase = dqkv + (b * L) * ld + h * dh;
+  for (int d = lane; d < dh; d += 32) {
+    for (int i = 0; i < L; ++i) {  // dQ[i][d] = sum_j dS[i][j] k[j][d]
+      float a = 0.f;
+      for (int j = 0; j < L; ++j) a += dS[i * ps + j] * k[j * st + d];
+      stf<T>(obase + (int64_t)i * ld + d, a);
+    }
+    for (int j = 0; j < L; ++j) {  // dK[j][d] = sum_i dS[i][j] q[i][d];  dV[j][d] = sum_i P[i][j] dO[i][d]
+      float a = 0.f, c = 0.f;
+      for (int i = 0; i < L; ++i) { a += dS[i * ps + j] * q[i * st + d]; c += P[i * ps + j] * go[i * st + d]; }
+      stf<T>(obase + D + (int64_t)j * ld + d, a);
+      stf<T>(obase + 2 * D + (int64_t)j * ld + d, c);
+    }
+  }
+}
+
+template <typename K>
+int configure_smem(K kernel, int bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("attention: cudaFuncSetAttribute(%d) failed: %s", bytes, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace afb
+
+using namespace afb;
+
+extern "C" int afb_attention_fwd(const void* qkv, void* o, int dt, int64_t B, int L, int heads, int dh, float scale, afb_stream s) {
+  AFB_REQUIRE(qkv && o && B > 0, "attention_fwd: bad args");
+  AFB_REQUIRE(L >= 1 && L <= 64 && dh >= 1 && dh <= 64, "attention: L=%d dh=%d unsupported (L<=64, dh<=64)", L, dh);
+  const int per_warp = 3 * L * (dh + 1) + L + 3;
+  int warps = kSmemBudget / (per_warp * 4);
+  if (warps > 8) warps = 8;
+  AFB_REQUIRE(warps >= 1, "attention: tile does not fit shared memory");
+  const int64_t items = B * heads;
+  const int smem = warps * per_warp * 4;
+  const int grid = ceil_div(items, warps);
+  int rc;
+  if (dt == AFB_BF16) {
+    if ((rc = configure_smem(attn_fwd_kernel<bf16>, smem))) return rc;
+    attn_fwd_kernel<bf16><<<grid, warps * 32, smem, as_stream(s)>>>((const bf16*)qkv, (bf16*)o, items, L, heads, dh, scale, per_warp);
+  } else {
+    if ((rc = configure_smem(attn_fwd_kernel<float>, smem))) return rc;
+    attn_fwd_kernel<float><<<grid, warps * 32, smem, as_stream(s)>>>((const float*)qkv, (float*)o, items, L, heads, dh, scale, per_warp);
+  }
+  return check_launch("attention_fwd");
+}
+
+extern "C" int afb_attention_bwd(const void* qkv, const void* dO, void* dqkv, int dt, int64_t B, int L, int heads, int dh,
+                                 float scale, afb_stream s) {
+  AFB_REQUIRE(qkv && dO && dqkv && B > 0, "attention_bwd: bad args");
+  AFB_REQUIRE(L >= 1 && L <= 64 && dh >= 1 && dh <= 64, "attention: L=%d dh=%d unsupported (L<=64, dh<=64)", L, dh);
+  const int per_warp = 4 * L * (dh + 1) + 2 * L * (L + 1) + 2;
+  int warps = kSmemBudget / (per_warp * 4);
+  if (warps > 4) warps = 4;
+  AFB_REQUIRE(warps >= 1, "attention: tile does not fit shared memory");
+  const int64_t items = B * heads;
+  const int smem = warps * per_warp * 4;
+  const int grid = ceil_div(items, warps);
+  int rc;
+  if (dt == AFB_BF16) {
+    if ((rc = configure_smem(attn_bwd_kernel<bf16>, smem))) return rc;
+    attn_bwd_kernel<bf16><<<grid, warps * 32, smem, as_stream(s)>>>((const bf16*)qkv, (const bf16*)dO, (bf16*)dqkv, items, L, heads, dh,
+                                                                   scale, per_warp);
+  } else {
+    if ((rc = configure_smem(attn_bwd_kernel<float>, smem))) return rc;
+    attn_bwd_kernel<float><<<grid, warps * 32, smem, as_stream(s)>>>((const float*)qkv, (const float*)dO, (float*)dqkv, items, L, heads,
+                                                                     dh, scale, per_warp);
+  }
+  return check_launch("attention_bwd");
+}

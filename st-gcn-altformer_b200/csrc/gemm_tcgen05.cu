@@ -1,0 +1,658 @@
+// tcgen05 / TMEM / TMA GEMMs for sm_100a.
+//
+//   gemm_tn_kernel : C[M,N] = epilogue(A[M,K] * B[N,K]^T)   nn.Linear forward, dX, and the 9x1
+//                    temporal conv as an implicit GEMM (per-tap row-shifted TMA loads).
+//   gemm_dw_kernel : dW[N1,N2] += G[M,N1]^T * X[M,N2]       weight gradients, contraction over
+//                    token rows (both operands MN-major), split over CTAs, fp32 atomics.
+//
+// Structure (one CTA per SM, persistent over tiles; 6 warps):
+//   warp 0    TMA producer  : cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx
+//   warp 1    MMA issuer    : one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into one of
+//                             two TMEM accumulator stages; tcgen05.commit releases smem / signals
+//   warps 2-5 epilogue      : tcgen05.ld 32 lanes x 32 columns -> smem transpose -> coalesced
+//                             fused epilogue (bias, pos-embed, GELU, DropPath scale, residual)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace afb {
+namespace {
+
+constexpr int BM = 128;       // rows per tile == TMEM lanes
+constexpr int BK = 64;        // bf16 elements per k-block row == 128 bytes == swizzle span
+constexpr int kThreads = 192;
+constexpr int kEpiWarps = 4;
+constexpr int kScratchStride = 36;  // floats; 144 B rows keep float4 writes conflict-free
+constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;  // 4 s: a protocol bug traps instead of hanging
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (visible as a launch error) instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (global_ns() - t0 > kWaitTimeoutNs) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane/row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (sm_100 format): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 |
+// SWIZZLE_128B (2) <<61.   K-major tiles: rows of 128 B, 8-row groups 1024 B apart (SBO).
+// MN-major tiles: 64-element (128 B) MN runs, 8 k-rows per 1024 B atom (SBO), next 64 MN at LBO.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32, A/B bf16, majors, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN> struct TnCfg {
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BN >= 256 ? 512 : (BN >= 128 ? 256 : (BN >= 64 ? 128 : 64));
+  static constexpr int kScratchBytes = kEpiWarps * 32 * kScratchStride * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+struct TnArgs {
+  int m_tiles_per_batch, n_tiles, total_tiles, k_blocks;
+  int rows_per_batch, batches, N;
+  int kb_per_tap, tap_row_stride, tap_pad;
+  void* C;
+  void* C2;
+  int ldc, out_dtype, act;
+  float alpha;
+  const float* bias;
+  const float* pos;
+  int pos_rows;
+  const void* aux;
+  int aux_dtype, ldaux;
+  const void* residual;
+  int res_dtype, ldres;
+  const float* row_scale;
+  int row_scale_div;
+};
+
+template <int BN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnArgs p) {
+  using Cfg = TnCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const uint32_t sA = base;
+  const uint32_t sB = base + Cfg::kStages * Cfg::kABytes;
+  float* scratch = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  const uint32_t bar0 = base + Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * Cfg::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes + 8 * (2 * Cfg::kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        const int mt = tile / p.n_tiles;
+        const int batch = mt / p.m_tiles_per_batch;
+        const int m0 = (mt % p.m_tiles_per_batch) * BM;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          const int tap = kb / p.kb_per_tap;
+          const int kc = (kb - tap * p.kb_per_tap) * BK;
+          tma_load_3d(&tmA, full_bar(stage), sA + stage * Cfg::kABytes, kc, m0 + (tap - p.tap_pad) * p.tap_row_stride, batch);
+          if (!B_MN) {
+            tma_load_2d(&tmB, full_bar(stage), sB + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)  // 64(k) x 64(n) boxes, N contiguous
+              tma_load_2d(&tmB, full_bar(stage), sB + stage * Cfg::kBBytes + j * (64 * 128), n_blk * BN + j * 64, kb * BK);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = sA + stage * Cfg::kABytes;
+          const uint32_t b_addr = sB + stage * Cfg::kBBytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = make_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_desc(b_addr + k * 2048, 64 * 128, 1024) : make_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue warps ----------------------------------------
+    const int ew = warp - 2;        // scratch slot
+    const int lane_grp = warp & 3;  // TMEM lane quarter this warp may access
+    float* my = scratch + ew * 32 * kScratchStride;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int sub_row = lane >> 4;        // 0/1: which of the two rows handled per iteration
+    const int cpair = (lane & 15) * 2;    // column pair inside the 32-column chunk
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      const int batch = mt / p.m_tiles_per_batch;
+      const int m0 = (mt % p.m_tiles_per_batch) * BM;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row_base_local = m0 + lane_grp * 32;  // row inside the batch
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
+        if (ch == BN / 32 - 1) {  // all TMEM reads of this accumulator are done
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(my + lane * kScratchStride + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const int n = n_blk * BN + ch * 32 + cpair;
+        float b0 = 0.f, b1 = 0.f;
+        if (p.bias != nullptr) { b0 = p.bias[n]; b1 = p.bias[n + 1]; }
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const int r = it * 2 + sub_row;
+          const int row_local = row_base_local + r;
+          if (row_local < p.rows_per_batch) {
+            const int64_t row = (int64_t)batch * p.rows_per_batch + row_local;
+            const float2 a = *reinterpret_cast<const float2*>(my + r * kScratchStride + cpair);
+            float v0 = a.x * p.alpha + b0, v1 = a.y * p.alpha + b1;
+            if (p.pos != nullptr) {
+              const float2 pe = *reinterpret_cast<const float2*>(p.pos + (int64_t)(row % p.pos_rows) * p.N + n);
+              v0 += pe.x; v1 += pe.y;
+            }
+            if (p.act == AFB_ACT_GELU) {
+              if (p.C2 != nullptr) st2_dyn(p.C2, row * p.ldc + n, p.out_dtype, v0, v1);
+              v0 = gelu_f(v0); v1 = gelu_f(v1);
+            } else if (p.act == AFB_ACT_GELU_BWD) {
+              const float2 h = ld2_dyn(p.aux, row * p.ldaux + n, p.aux_dtype);
+              v0 *= gelu_grad_f(h.x); v1 *= gelu_grad_f(h.y);
+            } else if (p.act == AFB_ACT_RELU) {
+              v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);
+            }
+            if (p.row_scale != nullptr) {
+              const float sc = p.row_scale[row / p.row_scale_div];
+              v0 *= sc; v1 *= sc;
+            }
+            if (p.residual != nullptr) {
+              const float2 rr = ld2_dyn(p.residual, row * p.ldres + n, p.res_dtype);
+              v0 += rr.x; v1 += rr.y;
+            }
+            st2_dyn(p.C, row * p.ldc + n, p.out_dtype, v0, v1);
+          }
+        }
+        __syncwarp();
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dW kernel: contraction over rows.  A = G^T (MN-major, M-dim = N1 tile of 128), B = X^T (MN-major,
+// N-dim = N2 tile of BN2).  Each CTA owns one (n1 tile, n2 tile, row-split) and accumulates its row
+// blocks in TMEM, then adds its partial into dW with fp32 atomics.
+// ---------------------------------------------------------------------------------------------
+template <int BN2> struct DwCfg {
+  static constexpr int kStages = BN2 >= 256 ? 4 : 6;
+  static constexpr int kABytes = 64 * 128 * 2;      // 64 rows x 128 n1
+  static constexpr int kBBytes = 64 * BN2 * 2;      // 64 rows x BN2 n2
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BN2 >= 256 ? 256 : (BN2 >= 128 ? 128 : 64);
+  static constexpr int kScratchBytes = kEpiWarps * 32 * kScratchStride * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 256 + 1024;
+};
+
+struct DwArgs {
+  int n1_tiles, n2_tiles, splits;
+  int row_blocks_per_batch, total_row_blocks;
+  int N1, N2;
+  int x_row_shift;
+  float* dW;
+  long long ld1, ld2;
+  float alpha;
+};
+
+template <int BN2>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const DwArgs p) {
+  using Cfg = DwCfg<BN2>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t sA = base;
+  const uint32_t sB = base + Cfg::kStages * Cfg::kABytes;
+  float* scratch = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  const uint32_t bar0 = base + Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (Cfg::kStages + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * Cfg::kStages);
+  const uint32_t tmem_slot = bar0 + 8u * (2 * Cfg::kStages + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes + 8 * (2 * Cfg::kStages + 1));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work decomposition: blockIdx.x = (tile, split)
+  const int split = blockIdx.x % p.splits;
+  const int tile = blockIdx.x / p.splits;
+  const int n2_blk = tile % p.n2_tiles;
+  const int n1_blk = tile / p.n2_tiles;
+  const int per = (p.total_row_blocks + p.splits - 1) / p.splits;
+  const int rb_begin = split * per;
+  const int rb_end = min(rb_begin + per, p.total_row_blocks);
+  const int n_rb = max(rb_end - rb_begin, 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmG);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (n_rb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int rb = rb_begin; rb < rb_end; ++rb) {
+          const int batch = rb / p.row_blocks_per_batch;
+          const int r0 = (rb % p.row_blocks_per_batch) * 64;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_3d(&tmG, full_bar(stage), sA + stage * Cfg::kABytes + j * 8192, n1_blk * 128 + j * 64, r0, batch);
+#pragma unroll
+          for (int j = 0; j < BN2 / 64; ++j)
+            tma_load_3d(&tmX, full_bar(stage), sB + stage * Cfg::kBBytes + j * 8192, n2_blk * BN2 + j * 64, r0 + p.x_row_shift, batch);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(128, BN2, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < n_rb; ++i) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = sA + stage * Cfg::kABytes;
+          const uint32_t b_addr = sB + stage * Cfg::kBBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 16 contraction rows per MMA = two 8-row atoms
+            const uint64_t adesc = make_desc(a_addr + k * 2048, 8192, 1024);
+            const uint64_t bdesc = make_desc(b_addr + k * 2048, 8192, 1024);
+            umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar);
+      }
+    } else {
+      const int ew = warp - 2;
+      const int lane_grp = warp & 3;
+      float* my = scratch + ew * 32 * kScratchStride;
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      for (int ch = 0; ch < BN2 / 32; ++ch) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(ch * 32), v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(my + lane * kScratchStride + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const int n2 = n2_blk * BN2 + ch * 32 + lane;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int n1 = n1_blk * 128 + lane_grp * 32 + r;
+          if (n1 < p.N1 && n2 < p.N2) atomicAdd(p.dW + n1 * p.ld1 + n2 * p.ld2, p.alpha * my[r * kScratchStride + lane]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 tensor [d2][d1][d0] (d0 contiguous), strides in elements; 128B swizzle; OOB reads give zero.
+int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
+             uint32_t box0, uint32_t box1, int rank) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled unavailable (driver too old?)");
+    return AFB_ERR_DRIVER;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (ptr %p dims %llu,%llu,%llu strides %llu,%llu box %u,%u)", (int)r, ptr,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)stride1,
+              (unsigned long long)stride2, box0, box1);
+    return AFB_ERR_DRIVER;
+  }
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, bool B_MN>
+int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const TnArgs& a, cudaStream_t st) {
+  using Cfg = TnCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("gemm_tn: cudaFuncSetAttribute(%d B) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
+  gemm_tn_kernel<BN, B_MN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  return check_launch("gemm_tn");
+}
+
+template <int BN2>
+int launch_dw(const CUtensorMap& tmG, const CUtensorMap& tmX, const DwArgs& a, cudaStream_t st) {
+  using Cfg = DwCfg<BN2>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_dw_kernel<BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("gemm_dw: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int grid = a.n1_tiles * a.n2_tiles * a.splits;
+  gemm_dw_kernel<BN2><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmG, tmX, a);
+  return check_launch("gemm_dw");
+}
+
+}  // namespace
+}  // namespace afb
+
+using namespace afb;
+
+extern "C" int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s) {
+  AFB_REQUIRE(p && p->A && p->B && p->C, "gemm_tn: null operand");
+  AFB_REQUIRE(p->taps >= 1 && p->k_per_tap > 0, "gemm_tn: bad taps/k");
+  AFB_REQUIRE(p->N % 64 == 0, "gemm_tn: N=%d must be a multiple of 64", p->N);
+  AFB_REQUIRE(p->lda % 8 == 0 && p->ldb % 8 == 0 && p->ldc % 2 == 0, "gemm_tn: leading dims must be 16-byte aligned");
+  AFB_REQUIRE(p->taps == 1 || p->k_per_tap % BK == 0, "gemm_tn: k_per_tap %% 64 != 0 with taps > 1");
+  AFB_REQUIRE(p->k_per_tap % 8 == 0, "gemm_tn: k_per_tap %% 8 != 0");
+  AFB_REQUIRE(((uintptr_t)p->A & 15) == 0 && ((uintptr_t)p->B & 15) == 0, "gemm_tn: operands must be 16-byte aligned");
+  AFB_REQUIRE(p->rows_per_batch > 0 && p->batches > 0, "gemm_tn: empty problem");
+
+  const int BN = (p->N % 256 == 0) ? 256 : (p->N % 128 == 0 ? 128 : 64);
+  const int K = p->taps * p->k_per_tap;
+  TnArgs a;
+  a.m_tiles_per_batch = ceil_div(p->rows_per_batch, BM);
+  a.n_tiles = p->N / BN;
+  a.total_tiles = a.m_tiles_per_batch * p->batches * a.n_tiles;
+  a.kb_per_tap = ceil_div(p->k_per_tap, BK);
+  a.k_blocks = a.kb_per_tap * p->taps;
+  a.rows_per_batch = (int)p->rows_per_batch;
+  a.batches = p->batches;
+  a.N = p->N;
+  a.tap_row_stride = p->tap_row_stride;
+  a.tap_pad = p->tap_pad;
+  a.C = p->C; a.C2 = p->C2; a.ldc = p->ldc; a.out_dtype = p->out_dtype; a.act = p->act; a.alpha = p->alpha;
+  a.bias = p->bias; a.pos = p->pos; a.pos_rows = p->pos_rows > 0 ? p->pos_rows : 1;
+  a.aux = p->aux; a.aux_dtype = p->aux_dtype; a.ldaux = p->ldaux;
+  a.residual = p->residual; a.res_dtype = p->res_dtype; a.ldres = p->ldres;
+  a.row_scale = p->row_scale; a.row_scale_div = p->row_scale_div > 0 ? p->row_scale_div : 1;
+  AFB_REQUIRE(p->act != AFB_ACT_GELU_BWD || p->aux != nullptr, "gemm_tn: GELU_BWD needs aux");
+
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, p->A, (uint64_t)p->k_per_tap, (uint64_t)p->rows_per_batch, (uint64_t)p->batches, (uint64_t)p->lda,
+                    (uint64_t)p->rows_per_batch * p->lda, BK, BM, 3);
+  if (rc) return rc;
+  if (!p->b_mn_major)
+    rc = make_map(&tmB, p->B, (uint64_t)K, (uint64_t)p->N, 1, (uint64_t)p->ldb, 0, BK, (uint32_t)BN, 2);
+  else
+    rc = make_map(&tmB, p->B, (uint64_t)p->N, (uint64_t)K, 1, (uint64_t)p->ldb, 0, 64, 64, 2);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(s);
+  if (!p->b_mn_major) {
+    if (BN == 256) return launch_tn<256, false>(tmA, tmB, a, st);
+    if (BN == 128) return launch_tn<128, false>(tmA, tmB, a, st);
+    return launch_tn<64, false>(tmA, tmB, a, st);
+  }
+  if (BN == 256) return launch_tn<256, true>(tmA, tmB, a, st);
+  if (BN == 128) return launch_tn<128, true>(tmA, tmB, a, st);
+  return launch_tn<64, true>(tmA, tmB, a, st);
+}
+
+extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
+  AFB_REQUIRE(p && p->G && p->X && p->dW, "gemm_dw: null operand");
+  AFB_REQUIRE(p->N2 % 64 == 0, "gemm_dw: N2=%d must be a multiple of 64", p->N2);
+  AFB_REQUIRE(p->N1 % 8 == 0, "gemm_dw: N1=%d must be a multiple of 8", p->N1);
+  AFB_REQUIRE(p->ldg % 8 == 0 && p->ldx % 8 == 0, "gemm_dw: leading dims must be 16-byte aligned");
+  AFB_REQUIRE(((uintptr_t)p->G & 15) == 0 && ((uintptr_t)p->X & 15) == 0, "gemm_dw: operands must be 16-byte aligned");
+  const int BN2 = (p->N2 % 256 == 0) ? 256 : (p->N2 % 128 == 0 ? 128 : 64);
+  DwArgs a;
+  a.n1_tiles = ceil_div(p->N1, 128);
+  a.n2_tiles = p->N2 / BN2;
+  a.row_blocks_per_batch = ceil_div(p->rows_per_batch, 64);
+  a.total_row_blocks = a.row_blocks_per_batch * p->batches;
+  const int tiles = a.n1_tiles * a.n2_tiles;
+  int splits = (2 * num_sms()) / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > a.total_row_blocks) splits = a.total_row_blocks;
+  // keep at least 8 row blocks per split so the atomic epilogue is amortised
+  const int max_splits = a.total_row_blocks / 8 > 0 ? a.total_row_blocks / 8 : 1;
+  if (splits > max_splits) splits = max_splits;
+  a.splits = splits;
+  a.N1 = p->N1; a.N2 = p->N2; a.x_row_shift = p->x_row_shift;
+  a.dW = p->dW; a.ld1 = p->ld1; a.ld2 = p->ld2; a.alpha = p->alpha;
+  CUtensorMap tmG, tmX;
+  int rc = make_map(&tmG, p->G, (uint64_t)p->N1, (uint64_t)p->rows_per_batch, (uint64_t)p->batches, (uint64_t)p->ldg,
+                    (uint64_t)p->rows_per_batch * p->ldg, 64, 64, 3);
+  if (rc) return rc;
+  rc = make_map(&tmX, p->X, (uint64_t)p->N2, (uint64_t)p->rows_per_batch, (uint64_t)p->batches, (uint64_t)p->ldx,
+                (uint64_t)p->rows_per_batch * p->ldx, 64, 64, 3);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(s);
+  if (BN2 == 256) return launch_dw<256>(tmG, tmX, a, st);
+  if (BN2 == 128) return launch_dw<128>(tmG, tmX, a, st);
+  return launch_dw<64>(tmG, tmX, a, st);
+}
