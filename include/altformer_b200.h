@@ -122,13 +122,17 @@ int afb_gemm_simt(const afb_gemm_simt_t* p, afb_stream s);
  * Parameter preparation
  * ------------------------------------------------------------------------------------------ */
 int afb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, afb_stream s);
+/* strided 2-D cast-copy: dst[r*ldd + c] = (dst_dtype) src[r*lds + c]  (weight stacking) */
+int afb_copy2d(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd, int64_t rows,
+               int cols, afb_stream s);
 /* dst[c*rows + r] = bf16(src[r*cols + c]) */
 int afb_cast_transpose(const float* src, void* dst_bf16, int rows, int cols, afb_stream s);
 /* Conv2d weight (co, ci, k, 1) fp32 -> fwd bf16 [co][k][ci] and bwd bf16 [ci][k'][co] with k' = k-1-tap
  * (the flipped kernel of the transposed conv that yields dX).  Either output may be NULL. */
 int afb_conv_weight_pack(const float* w, void* fwd_bf16, void* bwd_bf16, int co, int ci, int k, afb_stream s);
 /* hi/lo bf16 split of an fp32 matrix for the 3-pass fp32-parity GEMM: dst is [rows][3*cols] holding
- * (hi | lo | hi) when which == 0 (A side) or (hi | hi | lo) when which == 1 (B side). */
+ * (hi | lo | hi) when which == 0 (A side) or (hi | hi | lo) when which == 1 (B side); which == 2 stacks
+ * (hi ; hi ; lo) along rows instead ([3*rows][cols], the MN-major B operand of dX = dY * W). */
 int afb_split3(const float* src, void* dst_bf16, int64_t rows, int cols, int which, afb_stream s);
 
 /* ------------------------------------------------------------------------------------------ *

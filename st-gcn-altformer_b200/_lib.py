@@ -75,6 +75,7 @@ def _declare(L):
         "afb_gemm_dw": [P(GemmDw), vp],
         "afb_gemm_simt": [P(GemmSimt), vp],
         "afb_cast": [vp, i32, vp, i32, i64, vp],
+        "afb_copy2d": [vp, i32, i64, vp, i32, i64, i64, i32, vp],
         "afb_cast_transpose": [vp, vp, i32, i32, vp],
         "afb_conv_weight_pack": [vp, vp, vp, i32, i32, i32, vp],
         "afb_split3": [vp, vp, i64, i32, i32, vp],

@@ -54,6 +54,16 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, bf16* __restrict__
   }
 }
 
+template <typename S, typename D>
+__global__ void copy2d_kernel(const S* __restrict__ src, int64_t lds, D* __restrict__ dst, int64_t ldd, int64_t rows, int cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i % cols);
+    stf<D>(dst + r * ldd + c, ldf<S>(src + r * lds + c));
+  }
+}
+
 __global__ void split3_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t rows, int cols, int which) {
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -62,10 +72,16 @@ __global__ void split3_kernel(const float* __restrict__ src, bf16* __restrict__ 
     const float v = src[i];
     const bf16 hi = __float2bfloat16_rn(v);
     const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    bf16* o = dst + r * 3 * cols;
-    o[c] = hi;
-    o[cols + c] = which == 0 ? lo : hi;
-    o[2 * cols + c] = which == 0 ? hi : lo;
+    if (which == 2) {  // row-stacked (hi ; hi ; lo): the MN-major B operand of dX = dY * W
+      dst[i] = hi;
+      dst[total + i] = hi;
+      dst[2 * total + i] = lo;
+    } else {
+      bf16* o = dst + r * 3 * cols;
+      o[c] = hi;
+      o[cols + c] = which == 0 ? lo : hi;
+      o[2 * cols + c] = which == 0 ? hi : lo;
+    }
   }
 }
 
@@ -192,60 +208,77 @@ __device__ __forceinline__ int64_t perm_row(int64_t m, int T, int V) {  // (n,t,
   return (n * V + v) * T + t;
 }
 
+// Column tiling shared by the three reductions: a block covers 128 columns (32 float4 lanes) x 8 row
+// lanes and a contiguous slab of rows; grid = (row slabs, ceil(C/128)).
+constexpr int kColTile = 128;
+constexpr int kRowLanes = kBlock / (kColTile / 4);
+
+struct ColTile {
+  int c4, rl;
+  bool active;
+  int64_t r_begin, r_end;
+};
+__device__ __forceinline__ ColTile col_tile(int64_t M, int C) {
+  ColTile t;
+  t.c4 = blockIdx.y * kColTile + (threadIdx.x & 31) * 4;
+  t.rl = threadIdx.x >> 5;
+  t.active = t.c4 < C;
+  const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  t.r_begin = blockIdx.x * rows_per_block;
+  t.r_end = t.r_begin + rows_per_block < M ? t.r_begin + rows_per_block : M;
+  return t;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock) colstats_kernel(const T* __restrict__ x, int64_t M, int C, int ldx, double* __restrict__ sum,
                                                           double* __restrict__ sumsq) {
-  extern __shared__ float sred[];  // [2][row_lanes][C]
-  const int cg = C >> 2, row_lanes = blockDim.x / cg;
-  const int c4 = (threadIdx.x % cg) * 4, rl = threadIdx.x / cg;
-  const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
-  const int64_t r_begin = blockIdx.x * rows_per_block;
-  const int64_t r_end = r_begin + rows_per_block < M ? r_begin + rows_per_block : M;
+  __shared__ float sred[2][kRowLanes][kColTile];
+  const ColTile t = col_tile(M, C);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-  if (rl < row_lanes) {
-    for (int64_t r = r_begin + rl; r < r_end; r += row_lanes) {
-      const float4 v = ld4<T>(x + r * ldx + c4);
+  if (t.active)
+    for (int64_t r = t.r_begin + t.rl; r < t.r_end; r += kRowLanes) {
+      const float4 v = ld4<T>(x + r * ldx + t.c4);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
     }
-    *reinterpret_cast<float4*>(sred + (0 * row_lanes + rl) * C + c4) = s;
-    *reinterpret_cast<float4*>(sred + (1 * row_lanes + rl) * C + c4) = q;
-  }
+  *reinterpret_cast<float4*>(&sred[0][t.rl][(threadIdx.x & 31) * 4]) = s;
+  *reinterpret_cast<float4*>(&sred[1][t.rl][(threadIdx.x & 31) * 4]) = q;
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double a = 0.0, b = 0.0;
-    for (int l = 0; l < row_lanes; ++l) { a += sred[l * C + c]; b += sred[(row_lanes + l) * C + c]; }
-    atomicAdd(sum + c, a);
-    atomicAdd(sumsq + c, b);
+  if (threadIdx.x < kColTile) {
+    const int c = blockIdx.y * kColTile + threadIdx.x;
+    if (c < C) {
+      double a = 0.0, b = 0.0;
+      for (int l = 0; l < kRowLanes; ++l) { a += sred[0][l][threadIdx.x]; b += sred[1][l][threadIdx.x]; }
+      atomicAdd(sum + c, a);
+      atomicAdd(sumsq + c, b);
+    }
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kBlock) colsum_kernel(const T* __restrict__ x, int64_t M, int C, int ldx,
                                                         const float* __restrict__ row_scale, int div, float* __restrict__ out) {
-  extern __shared__ float sred[];
-  const int cg = C >> 2, row_lanes = blockDim.x / cg;
-  const int c4 = (threadIdx.x % cg) * 4, rl = threadIdx.x / cg;
-  const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
-  const int64_t r_begin = blockIdx.x * rows_per_block;
-  const int64_t r_end = r_begin + rows_per_block < M ? r_begin + rows_per_block : M;
+  __shared__ float sred[kRowLanes][kColTile];
+  const ColTile t = col_tile(M, C);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (rl < row_lanes) {
-    for (int64_t r = r_begin + rl; r < r_end; r += row_lanes) {
-      float4 v = ld4<T>(x + r * ldx + c4);
+  if (t.active)
+    for (int64_t r = t.r_begin + t.rl; r < t.r_end; r += kRowLanes) {
+      float4 v = ld4<T>(x + r * ldx + t.c4);
       if (row_scale != nullptr) {
         const float sc = row_scale[r / div];
         v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
       }
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    *reinterpret_cast<float4*>(sred + rl * C + c4) = s;
-  }
+  *reinterpret_cast<float4*>(&sred[t.rl][(threadIdx.x & 31) * 4]) = s;
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f;
-    for (int l = 0; l < row_lanes; ++l) a += sred[l * C + c];
-    atomicAdd(out + c, a);
+  if (threadIdx.x < kColTile) {
+    const int c = blockIdx.y * kColTile + threadIdx.x;
+    if (c < C) {
+      float a = 0.f;
+      for (int l = 0; l < kRowLanes; ++l) a += sred[l][threadIdx.x];
+      atomicAdd(out + c, a);
+    }
   }
 }
 
@@ -340,31 +373,31 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const TG* __restr
                                                                const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int C,
                                                                int T, int V) {
-  extern __shared__ float sred[];
-  const int cg = C >> 2, row_lanes = blockDim.x / cg;
-  const int c4 = (threadIdx.x % cg) * 4, rl = threadIdx.x / cg;
-  const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
-  const int64_t r_begin = blockIdx.x * rows_per_block;
-  const int64_t r_end = r_begin + rows_per_block < M ? r_begin + rows_per_block : M;
+  __shared__ float sred[2][kRowLanes][kColTile];
+  const ColTile t = col_tile(M, C);
   float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sb = sg;
-  if (rl < row_lanes) {
+  if (t.active) {
+    const int c4 = t.c4;
     const float4 mu = *reinterpret_cast<const float4*>(mean + c4), rs = *reinterpret_cast<const float4*>(rstd + c4);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c4), be = *reinterpret_cast<const float4*>(beta + c4);
-    for (int64_t r = r_begin + rl; r < r_end; r += row_lanes) {
+    for (int64_t r = t.r_begin + t.rl; r < t.r_end; r += kRowLanes) {
       float4 xh;
       const float4 g = bn_masked_grad<TG, TX, TR>(dy, dy2, x, res_pre, mu, rs, ga, be, relu, r, c4, C, T, V, xh);
       sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
       sg.x += g.x * xh.x; sg.y += g.y * xh.y; sg.z += g.z * xh.z; sg.w += g.w * xh.w;
     }
-    *reinterpret_cast<float4*>(sred + (0 * row_lanes + rl) * C + c4) = sg;
-    *reinterpret_cast<float4*>(sred + (1 * row_lanes + rl) * C + c4) = sb;
   }
+  *reinterpret_cast<float4*>(&sred[0][t.rl][(threadIdx.x & 31) * 4]) = sg;
+  *reinterpret_cast<float4*>(&sred[1][t.rl][(threadIdx.x & 31) * 4]) = sb;
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int l = 0; l < row_lanes; ++l) { a += sred[l * C + c]; b += sred[(row_lanes + l) * C + c]; }
-    atomicAdd(dgamma + c, a);
-    atomicAdd(dbeta + c, b);
+  if (threadIdx.x < kColTile) {
+    const int c = blockIdx.y * kColTile + threadIdx.x;
+    if (c < C) {
+      float a = 0.f, b = 0.f;
+      for (int l = 0; l < kRowLanes; ++l) { a += sred[0][l][threadIdx.x]; b += sred[1][l][threadIdx.x]; }
+      atomicAdd(dgamma + c, a);
+      atomicAdd(dbeta + c, b);
+    }
   }
 }
 
@@ -523,6 +556,13 @@ __global__ void scale_rows_kernel(const T* __restrict__ x, T* __restrict__ y, in
   }
 }
 
+template <typename T>
+__global__ void scale_rows_any_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t M, int C, const float* __restrict__ rs, int div) {
+  const int64_t total = M * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    stf<T>(y + i, ldf<T>(x + i) * rs[(i / C) / div]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // input streams / ensemble
 // ---------------------------------------------------------------------------------------------
@@ -580,6 +620,13 @@ extern "C" int afb_conv_weight_pack(const float* w, void* fwd, void* bwd, int co
   return check_launch("conv_weight_pack");
 }
 
+extern "C" int afb_copy2d(const void* src, int sd, int64_t lds, void* dst, int dd, int64_t ldd, int64_t rows, int cols, afb_stream s) {
+  AFB_REQUIRE(src && dst && rows > 0 && cols > 0, "copy2d: bad args");
+  const int g = grid_for(rows * cols, kBlock);
+  DISPATCH_DT(sd, S, DISPATCH_DT(dd, D, (copy2d_kernel<S, D><<<g, kBlock, 0, as_stream(s)>>>((const S*)src, lds, (D*)dst, ldd, rows, cols))));
+  return check_launch("copy2d");
+}
+
 extern "C" int afb_split3(const float* src, void* dst, int64_t rows, int cols, int which, afb_stream s) {
   AFB_REQUIRE(src && dst, "split3: bad args");
   split3_kernel<<<grid_for(rows * cols, kBlock), kBlock, 0, as_stream(s)>>>(src, (bf16*)dst, rows, cols, which);
@@ -633,15 +680,17 @@ extern "C" int afb_layernorm_bwd(const void* dy, int dyd, const void* x, int xd,
   return ln_bwd_dispatch<float>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D, as_stream(s));
 }
 
-static bool col_shape_ok(int C) { return C % 4 == 0 && C >= 4 && (C / 4) <= kBlock && kBlock % (C / 4) == 0; }
+static bool col_shape_ok(int C) { return C % 4 == 0 && C >= 4; }
+static dim3 col_grid(int64_t M, int C) {
+  const int col_tiles = ceil_div(C, kColTile);
+  int row_blocks = grid_for(M, kRowLanes * 16, (148 * 8) / col_tiles > 0 ? (148 * 8) / col_tiles : 1);
+  return dim3(row_blocks, col_tiles);
+}
 
 extern "C" int afb_colstats(const void* x, int dt, int64_t M, int C, int ldx, double* sum, double* sumsq, afb_stream s) {
   AFB_REQUIRE(x && sum && sumsq && M > 0, "colstats: bad args");
   AFB_REQUIRE(col_shape_ok(C) && ldx % 4 == 0, "colstats: C=%d unsupported", C);
-  const int row_lanes = kBlock / (C / 4);
-  const int grid = grid_for(M, row_lanes * 16, 148 * 4);
-  const size_t smem = 2 * (size_t)row_lanes * C * sizeof(float);
-  DISPATCH_DT(dt, T, (colstats_kernel<T><<<grid, kBlock, smem, as_stream(s)>>>((const T*)x, M, C, ldx, sum, sumsq)));
+  DISPATCH_DT(dt, T, (colstats_kernel<T><<<col_grid(M, C), kBlock, 0, as_stream(s)>>>((const T*)x, M, C, ldx, sum, sumsq)));
   return check_launch("colstats");
 }
 
@@ -649,10 +698,7 @@ extern "C" int afb_colsum(const void* x, int dt, int64_t M, int C, int ldx, cons
                           afb_stream s) {
   AFB_REQUIRE(x && out && M > 0, "colsum: bad args");
   AFB_REQUIRE(col_shape_ok(C) && ldx % 4 == 0, "colsum: C=%d unsupported", C);
-  const int row_lanes = kBlock / (C / 4);
-  const int grid = grid_for(M, row_lanes * 16, 148 * 4);
-  const size_t smem = (size_t)row_lanes * C * sizeof(float);
-  DISPATCH_DT(dt, T, (colsum_kernel<T><<<grid, kBlock, smem, as_stream(s)>>>((const T*)x, M, C, ldx, row_scale, div > 0 ? div : 1, out)));
+  DISPATCH_DT(dt, T, (colsum_kernel<T><<<col_grid(M, C), kBlock, 0, as_stream(s)>>>((const T*)x, M, C, ldx, row_scale, div > 0 ? div : 1, out)));
   return check_launch("colsum");
 }
 
@@ -685,10 +731,7 @@ extern "C" int afb_bn_bwd_reduce(const void* dy, const void* dy2, int gd, const 
   AFB_REQUIRE(col_shape_ok(C), "bn_bwd_reduce: C=%d unsupported", C);
   AFB_REQUIRE(gd == xd && (res_pre == nullptr || rd == xd), "bn_bwd_reduce: activations must share one dtype");
   AFB_REQUIRE(dy2 == nullptr || (T > 0 && V > 0 && M % ((int64_t)T * V) == 0), "bn_bwd_reduce: permuted grad needs T,V");
-  const int row_lanes = kBlock / (C / 4);
-  const int grid = grid_for(M, row_lanes * 16, 148 * 4);
-  const size_t smem = 2 * (size_t)row_lanes * C * sizeof(float);
-  DISPATCH_DT(xd, T_, (bn_bwd_reduce_kernel<T_, T_, T_><<<grid, kBlock, smem, as_stream(s)>>>(
+  DISPATCH_DT(xd, T_, (bn_bwd_reduce_kernel<T_, T_, T_><<<col_grid(M, C), kBlock, 0, as_stream(s)>>>(
                           (const T_*)dy, (const T_*)dy2, (const T_*)x, (const T_*)res_pre, mean, rstd, gamma, beta, relu, dgamma, dbeta,
                           M, C, T, V)));
   return check_launch("bn_bwd_reduce");
@@ -748,8 +791,12 @@ extern "C" int afb_step_inc(int32_t* step, afb_stream s) {
 }
 
 extern "C" int afb_scale_rows(const void* x, void* y, int dt, int64_t M, int C, const float* rs, int div, afb_stream s) {
-  AFB_REQUIRE(x && y && rs && M > 0 && C % 4 == 0 && div > 0, "scale_rows: bad args");
-  DISPATCH_DT(dt, T, (scale_rows_kernel<T><<<grid_for(M * C / 4, kBlock), kBlock, 0, as_stream(s)>>>((const T*)x, (T*)y, M, C, rs, div)));
+  AFB_REQUIRE(x && y && rs && M > 0 && C > 0 && div > 0, "scale_rows: bad args");
+  if (C % 4 == 0) {
+    DISPATCH_DT(dt, T, (scale_rows_kernel<T><<<grid_for(M * C / 4, kBlock), kBlock, 0, as_stream(s)>>>((const T*)x, (T*)y, M, C, rs, div)));
+  } else {
+    DISPATCH_DT(dt, T, (scale_rows_any_kernel<T><<<grid_for(M * C, kBlock), kBlock, 0, as_stream(s)>>>((const T*)x, (T*)y, M, C, rs, div)));
+  }
   return check_launch("scale_rows");
 }
 

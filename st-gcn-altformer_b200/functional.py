@@ -1,0 +1,780 @@
+"""autograd.Function layer: each Function strings C-ABI kernel launches together for forward and
+backward.  No torch arithmetic happens here; torch provides memory, streams and the autograd graph.
+
+Precision modes (set_precision):
+  'bf16' (default, performance): activations bf16, GEMM operands bf16, fp32 accumulate / statistics.
+  'fp32' (parity): activations fp32; every GEMM runs on the same tcgen05 kernel as three bf16 passes
+         over hi/lo-split operands (hi*hi + lo*hi + hi*lo, K-concatenated), good to ~1e-5 relative.
+"""
+import ctypes as C
+import weakref
+
+import torch
+
+from . import _lib, ops
+from .ops import ACT_GELU, ACT_GELU_BWD, ACT_NONE
+
+_PRECISION = ["bf16"]
+_EPOCH = [0]  # bumped by the trainer after an optimizer step that bypasses tensor version counters
+
+
+def set_precision(mode):
+    if mode not in ("bf16", "fp32"):
+        raise ValueError(mode)
+    _PRECISION[0] = mode
+
+
+def get_precision():
+    return _PRECISION[0]
+
+
+def act_dtype():
+    return torch.bfloat16 if _PRECISION[0] == "bf16" else torch.float32
+
+
+def bump_weights_epoch():
+    _EPOCH[0] += 1
+
+
+# ------------------------------------------------------------------------------------------------
+# derived (low-precision / packed) weights, cached per parameter version
+# ------------------------------------------------------------------------------------------------
+_cache = {}
+
+
+def _slot(p):
+    """Per-parameter dict of derived tensors (id-keyed: tensors cannot be WeakKeyDictionary keys)."""
+    key = id(p)
+    ent = _cache.get(key)
+    if ent is None or ent[0]() is not p:
+        ent = (weakref.ref(p, lambda _r, k=key: _cache.pop(k, None)), {})
+        _cache[key] = ent
+    return ent[1]
+
+
+def _derived(p, kind, make):
+    ver = (p._version, p.data_ptr(), _EPOCH[0])
+    slot = _slot(p)
+    ent = slot.get(kind)
+    if ent is None or ent[0] != ver:
+        with torch.no_grad():
+            ent = (ver, make(p.detach()))
+        slot[kind] = ent
+    return ent[1]
+
+
+def lowp(p):
+    """bf16 copy of a parameter (the trainer installs a persistent shadow as p._afb_shadow)."""
+    sh = getattr(p, "_afb_shadow", None)
+    if sh is not None:
+        return sh
+    return _derived(p, "bf16", lambda w: ops.cast(w.contiguous(), torch.bfloat16))
+
+
+def _w2d(p):
+    return p.detach().reshape(p.shape[0], -1)
+
+
+def w_fwd(p):
+    """B operand of y = x W^T: [N, K] bf16, or the (hi|hi|lo) split [N, 3K] in fp32 mode."""
+    if _PRECISION[0] == "bf16":
+        return lowp(p).reshape(p.shape[0], -1)
+    return _derived(p, "split_b", lambda w: ops.split3(w.reshape(w.shape[0], -1).contiguous(), 1))
+
+
+def w_dx(p):
+    """MN-major B operand of dx = dy W: W itself [N, K] (bf16), or row-stacked (hi;hi;lo) [3N, K]."""
+    if _PRECISION[0] == "bf16":
+        return lowp(p).reshape(p.shape[0], -1)
+    return _derived(p, "split_rows", lambda w: ops.split3(w.reshape(w.shape[0], -1).contiguous(), 2).view(3 * w.shape[0], -1))
+
+
+def conv_packs(p):
+    """(fwd [co, k*ci], bwd [ci, k*co]) operands of the temporal conv; fp32 mode: split per tap."""
+    if _PRECISION[0] == "bf16":
+        return _derived(p, "conv_bf16", lambda w: ops.conv_weight_pack(w.contiguous()))
+
+    def make(w):
+        co, ci, k = w.shape[:3]
+        w3 = w.reshape(co, ci, k)
+        f32_fwd = w3.permute(0, 2, 1).contiguous().view(co * k, ci)             # layout plumbing on a tiny tensor
+        f32_bwd = w3.flip(2).permute(1, 2, 0).contiguous().view(ci * k, co)
+        return ops.split3(f32_fwd, 1).view(co, k * 3 * ci), ops.split3(f32_bwd, 1).view(ci, k * 3 * co)
+
+    return _derived(p, "conv_split", make)
+
+
+def _grad_sink(p):
+    """(fp32 accumulation buffer, direct?).  direct: the trainer's flat gradient view (already zeroed)."""
+    gb = getattr(p, "_afb_grad", None)
+    if gb is not None:
+        return gb, True
+    return torch.zeros(p.shape, device=p.device, dtype=torch.float32), False
+
+
+def _ret(sink):
+    return None if sink[1] else sink[0]
+
+
+def _as_act(x):
+    """Cast an activation to the current activation dtype (kernel launch; no-op if it already matches)."""
+    want = act_dtype()
+    if x.dtype == want:
+        return x
+    return ops.cast(x.contiguous(), want)
+
+
+# ------------------------------------------------------------------------------------------------
+# mode-aware GEMM helpers
+# ------------------------------------------------------------------------------------------------
+def mm_fwd(x, w_param, **epi):
+    """x [M, K] (activation dtype) times w_param [N, K...]^T with the fused epilogue."""
+    N = w_param.shape[0]
+    if _PRECISION[0] == "bf16":
+        return ops.gemm_tn(x, w_fwd(w_param), N, out_dtype=torch.bfloat16, **epi)
+    return ops.gemm_tn(ops.split3(x, 0), w_fwd(w_param), N, out_dtype=torch.float32, **epi)
+
+
+def mm_dx(g, w_param, **epi):
+    """dx [M, K] = g [M, N] @ W [N, K]."""
+    K = w_param[0].numel()
+    if _PRECISION[0] == "bf16":
+        return ops.gemm_tn(g, w_dx(w_param), K, b_mn_major=True, out_dtype=torch.bfloat16, **epi)
+    return ops.gemm_tn(ops.split3(g, 0), w_dx(w_param), K, b_mn_major=True, out_dtype=torch.float32, **epi)
+
+
+def mm_dw(g, x, dW, **kw):
+    """dW [N, K] += g [M, N]^T @ x [M, K]."""
+    if _PRECISION[0] == "bf16":
+        return ops.gemm_dw(g, x, dW, **kw)
+    N1, N2 = g.shape[1], x.shape[1]
+    gs, xs = ops.split3(g, 0), ops.split3(x, 1)     # (hi|lo|hi) x (hi|hi|lo)
+    kw.setdefault("ld1", N2)
+    kw.pop("N1", None), kw.pop("N2", None)
+    for j in range(3):
+        ops.gemm_dw(gs, xs, dW, N1=N1, N2=N2, g_col0=j * N1, x_col0=j * N2, **kw)
+    return dW
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear (+bias, +pos-embed, +residual, +DropPath row scale)
+# ------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = row_scale * (x W^T + b + pos) + residual.   x [M, K]; pos [L, N] indexed by m % L."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pos, residual, row_scale, row_scale_div):
+        x = _as_act(x)
+        y = mm_fwd(x, weight, bias=bias, pos=None if pos is None else pos.detach().reshape(-1, pos.shape[-1]),
+                   residual=residual, row_scale=row_scale, row_scale_div=row_scale_div)
+        ctx.save_for_backward(x, weight, bias, pos, row_scale)
+        ctx.div = row_scale_div
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, pos, row_scale = ctx.saved_tensors
+        dy = _as_act(dy.contiguous())
+        g = dy if row_scale is None else ops.scale_rows(dy, row_scale, ctx.div)
+        dx = mm_dx(g, weight) if ctx.needs_input_grad[0] else None
+        sw = _grad_sink(weight)
+        mm_dw(g, x, sw[0].view(weight.shape[0], -1))
+        db = None
+        if bias is not None:
+            sb = _grad_sink(bias)
+            ops.colsum(g, sb[0])
+            db = _ret(sb)
+        dpos = None
+        if pos is not None:
+            sp = _grad_sink(pos)
+            L, N = pos.shape[-2], pos.shape[-1]
+            ops.colsum(g.view(-1, L * N), sp[0].view(-1))
+            dpos = _ret(sp)
+        return dx, _ret(sw), db, dpos, (dy if ctx.has_res else None), None, None
+
+
+def linear(x, weight, bias=None, pos=None, residual=None, row_scale=None, row_scale_div=1):
+    return LinearFn.apply(x, weight, bias, pos, residual, row_scale, row_scale_div)
+
+
+class SmallLinearFn(torch.autograd.Function):
+    """Classifier head (N = num_class, not a multiple of 64): strided CUDA-core GEMM, fp32 logits."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        M, K = x.shape
+        N = weight.shape[0]
+        y = ops.gemm_simt(x, weight.detach(), M, N, K, (K, 1), (K, 1), bias=bias, out_dtype=torch.float32)
+        ctx.save_for_backward(x, weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias = ctx.saved_tensors
+        dy = dy.contiguous()
+        if dy.dtype != torch.float32:
+            dy = ops.cast(dy, torch.float32)
+        M, K = x.shape
+        N = weight.shape[0]
+        dx = ops.gemm_simt(dy, weight.detach(), M, K, N, (N, 1), (1, K), out_dtype=x.dtype) if ctx.needs_input_grad[0] else None
+        sw = _grad_sink(weight)
+        ops.gemm_simt(dy, x, N, K, M, (1, N), (1, K), out=sw[0], beta=1.0)
+        db = None
+        if bias is not None:
+            sb = _grad_sink(bias)
+            one = torch.ones(1, device=dy.device, dtype=torch.float32)
+            ops.gemm_simt(dy, one, N, 1, M, (1, N), (0, 0), out=sb[0].view(N, 1), sc=(1, 1), beta=1.0)
+            db = _ret(sb)
+        return dx, _ret(sw), db
+
+
+def small_linear(x, weight, bias):
+    return SmallLinearFn.apply(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x = _as_act(x)
+        y, mean, rstd = ops.layernorm_fwd(x, weight.detach(), bias.detach(), eps)
+        ctx.save_for_backward(x, weight, bias, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, mean, rstd = ctx.saved_tensors
+        sg, sb = _grad_sink(weight), _grad_sink(bias)
+        dx = ops.layernorm_bwd(_as_act(dy.contiguous()), x, weight.detach(), mean, rstd, sg[0], sb[0])
+        return dx, _ret(sg), _ret(sb), None
+
+
+def layer_norm(x, weight, bias, eps):
+    return LayerNormFn.apply(x, weight, bias, eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# attention core, MLP, Block
+# ------------------------------------------------------------------------------------------------
+class AttentionCoreFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, B, L, heads):
+        o = ops.attention_fwd(qkv, B, L, heads)
+        ctx.save_for_backward(qkv)
+        ctx.cfg = (B, L, heads)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        (qkv,) = ctx.saved_tensors
+        return ops.attention_bwd(qkv, _as_act(do.contiguous()), *ctx.cfg), None, None, None
+
+
+def attention_core(qkv, B, L, heads):
+    return AttentionCoreFn.apply(qkv, B, L, heads)
+
+
+def _mlp_fwd(x, w1, b1, w2, b2, residual, keep, div):
+    h_act, h_pre = mm_fwd(x, w1, bias=b1, act=ACT_GELU, want_preact=True)
+    y = mm_fwd(h_act, w2, bias=b2, residual=residual, row_scale=keep, row_scale_div=div)
+    return y, h_act, h_pre
+
+
+def _mlp_bwd(g, x, h_act, h_pre, w1, b1, w2, b2, need_dx=True):
+    """g: gradient w.r.t. the (already DropPath-scaled) fc2 output."""
+    s2, sb2 = _grad_sink(w2), _grad_sink(b2)
+    mm_dw(g, h_act, s2[0])
+    ops.colsum(g, sb2[0])
+    dpre = mm_dx(g, w2, act=ACT_GELU_BWD, aux=h_pre)
+    s1, sb1 = _grad_sink(w1), _grad_sink(b1)
+    mm_dw(dpre, x, s1[0])
+    ops.colsum(dpre, sb1[0])
+    dx = mm_dx(dpre, w1) if need_dx else None
+    return dx, (_ret(s1), _ret(sb1), _ret(s2), _ret(sb2))
+
+
+class MlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x = _as_act(x)
+        y, h_act, h_pre = _mlp_fwd(x, w1, b1.detach(), w2, b2.detach(), None, None, 1)
+        ctx.save_for_backward(x, h_act, h_pre, w1, b1, w2, b2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, h_act, h_pre, w1, b1, w2, b2 = ctx.saved_tensors
+        dx, grads = _mlp_bwd(_as_act(dy.contiguous()), x, h_act, h_pre, w1, b1, w2, b2, ctx.needs_input_grad[0])
+        return (dx,) + grads
+
+
+def mlp(x, w1, b1, w2, b2):
+    return MlpFn.apply(x, w1, b1, w2, b2)
+
+
+class BlockFn(torch.autograd.Function):
+    """Pre-LN transformer block (model_ST.py:84-87) as one node: 4 GEMMs with fused bias / GELU /
+    DropPath / residual epilogues, 2 LayerNorms, attention; backward fuses the residual-gradient adds
+    into the LayerNorm backward kernels."""
+
+    @staticmethod
+    def forward(ctx, x, B, L, heads, eps, keep1, keep2, n1w, n1b, qkvw, qkvb, pw, pb, n2w, n2b, w1, b1, w2, b2):
+        x = _as_act(x)
+        d = lambda t: None if t is None else t.detach()  # noqa: E731
+        ln1, mean1, rstd1 = ops.layernorm_fwd(x, d(n1w), d(n1b), eps)
+        qkv = mm_fwd(ln1, qkvw, bias=d(qkvb))
+        ao = ops.attention_fwd(qkv, B, L, heads)
+        x1 = mm_fwd(ao, pw, bias=d(pb), residual=x, row_scale=keep1, row_scale_div=L)
+        ln2, mean2, rstd2 = ops.layernorm_fwd(x1, d(n2w), d(n2b), eps)
+        x2, h_act, h_pre = _mlp_fwd(ln2, w1, d(b1), w2, d(b2), x1, keep2, L)
+        ctx.save_for_backward(x, mean1, rstd1, ln1, qkv, ao, x1, mean2, rstd2, ln2, h_act, h_pre, keep1, keep2,
+                              n1w, n1b, qkvw, qkvb, pw, pb, n2w, n2b, w1, b1, w2, b2)
+        ctx.cfg = (B, L, heads)
+        return x2
+
+    @staticmethod
+    def backward(ctx, g2):
+        (x, mean1, rstd1, ln1, qkv, ao, x1, mean2, rstd2, ln2, h_act, h_pre, keep1, keep2,
+         n1w, n1b, qkvw, qkvb, pw, pb, n2w, n2b, w1, b1, w2, b2) = ctx.saved_tensors
+        B, L, heads = ctx.cfg
+        g2 = _as_act(g2.contiguous())
+        gs = g2 if keep2 is None else ops.scale_rows(g2, keep2, L)
+        dln2, (gw1, gb1, gw2, gb2) = _mlp_bwd(gs, ln2, h_act, h_pre, w1, b1, w2, b2)
+        sg2, sb2 = _grad_sink(n2w), _grad_sink(n2b)
+        g1 = ops.layernorm_bwd(dln2, x1, n2w.detach(), mean2, rstd2, sg2[0], sb2[0], dres=g2)
+        gs1 = g1 if keep1 is None else ops.scale_rows(g1, keep1, L)
+        sp, spb = _grad_sink(pw), _grad_sink(pb)
+        mm_dw(gs1, ao, sp[0])
+        ops.colsum(gs1, spb[0])
+        dao = mm_dx(gs1, pw)
+        dqkv = ops.attention_bwd(qkv, dao, B, L, heads)
+        sq = _grad_sink(qkvw)
+        mm_dw(dqkv, ln1, sq[0])
+        gqb = None
+        if qkvb is not None:
+            sqb = _grad_sink(qkvb)
+            ops.colsum(dqkv, sqb[0])
+            gqb = _ret(sqb)
+        dln1 = mm_dx(dqkv, qkvw)
+        sg1, sb1 = _grad_sink(n1w), _grad_sink(n1b)
+        g0 = ops.layernorm_bwd(dln1, x, n1w.detach(), mean1, rstd1, sg1[0], sb1[0], dres=g1)
+        return (g0, None, None, None, None, None, None, _ret(sg1), _ret(sb1), _ret(sq), gqb, _ret(sp), _ret(spb),
+                _ret(sg2), _ret(sb2), gw1, gb1, gw2, gb2)
+
+
+def block(x, B, L, heads, eps, keep1, keep2, *params):
+    return BlockFn.apply(x, B, L, heads, eps, keep1, keep2, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling / loss
+# ------------------------------------------------------------------------------------------------
+class PoolMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, B, L):
+        ctx.cfg = (B, L)
+        return ops.pool_mean_fwd(x, B, L)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.pool_mean_bwd(_as_act(dy.contiguous()), *ctx.cfg), None, None
+
+
+class PoolMaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, B, L):
+        y, arg = ops.pool_max_fwd(x, B, L)
+        ctx.save_for_backward(arg)
+        ctx.cfg = (B, L)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (arg,) = ctx.saved_tensors
+        return ops.pool_max_bwd(_as_act(dy.contiguous()), arg, *ctx.cfg), None, None
+
+
+def pool_mean(x, B, L):
+    return PoolMeanFn.apply(x, B, L)
+
+
+def pool_max(x, B, L):
+    return PoolMaxFn.apply(x, B, L)
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """mean softmax cross-entropy (torch.nn.CrossEntropyLoss, train_sttran.py:161)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        loss, dlogits = ops.softmax_ce(logits.contiguous(), labels.contiguous())
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        # g is the scalar upstream gradient (1.0 for loss.backward()); scaled on device, no host sync
+        return ops.scale_rows(dlogits, g.reshape(1), dlogits.shape[0]), None
+
+
+def cross_entropy(logits, labels):
+    return CrossEntropyFn.apply(logits, labels)
+
+
+# ------------------------------------------------------------------------------------------------
+# Unit2D: temporal conv (implicit GEMM) + BatchNorm + ReLU (+ residual after, + permuted copy)
+# ------------------------------------------------------------------------------------------------
+def _bn_forward(raw, bn_w, bn_b, rm, rv, training, momentum, eps):
+    M = raw.shape[0]
+    acc = ops.colstats(raw) if training else None
+    return ops.bn_finalize(acc, M, bn_w.detach(), bn_b.detach(), rm, rv, momentum, eps, training)
+
+
+class Unit2DFn(torch.autograd.Function):
+    """x tokens [N*T*V, Cin] -> relu(bn(conv_kx1(x))) (+ res_post); optionally also the (n,v,t)-ordered
+    copy the TS stage consumes.  model/net.py:47-57."""
+
+    @staticmethod
+    def forward(ctx, x, dims, conv_w, conv_b, bn_w, bn_b, rm, rv, training, momentum, eps, res_post, want_perm):
+        N, T, V = dims
+        x = _as_act(x)
+        co, ci, k = conv_w.shape[:3]
+        fwd_w, _ = conv_packs(conv_w)
+        three = 1 if get_precision() == "bf16" else 3
+        a = x if three == 1 else ops.split3(x, 0)
+        raw = ops.gemm_tn(a, fwd_w, co, k_per_tap=three * ci, taps=k, tap_row_stride=V, tap_pad=(k - 1) // 2,
+                          rows_per_batch=T * V, batches=N, bias=None if conv_b is None else conv_b.detach(),
+                          out_dtype=act_dtype())
+        stats = _bn_forward(raw, bn_w, bn_b, rm, rv, training, momentum, eps)
+        y, y2 = ops.bn_act_fwd(raw, stats[2], stats[3], True, res_post=res_post, T=T, V=V, want_perm=want_perm)
+        ctx.save_for_backward(x, raw, stats, conv_w, conv_b, bn_w, bn_b)
+        ctx.cfg = (N, T, V, training, res_post is not None, want_perm)
+        if want_perm:
+            return y, y2
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, dy2=None):
+        x, raw, stats, conv_w, conv_b, bn_w, bn_b = ctx.saved_tensors
+        N, T, V, training, has_res, want_perm = ctx.cfg
+        co, ci, k = conv_w.shape[:3]
+        dy = None if dy is None else _as_act(dy.contiguous())
+        dy2 = None if dy2 is None else _as_act(dy2.contiguous())
+        sg, sb = _grad_sink(bn_w), _grad_sink(bn_b)
+        draw, _ = ops.bn_bwd(dy, dy2, raw, stats, bn_w.detach(), bn_b.detach(), True, training, sg[0], sb[0], T=T, V=V)
+        gcb = None
+        if conv_b is not None:
+            scb = _grad_sink(conv_b)
+            ops.colsum(draw, scb[0])
+            gcb = _ret(scb)
+        sw = _grad_sink(conv_w)
+        flat = sw[0].view(-1)
+        pad = (k - 1) // 2
+        for tap in range(k):  # dW[co, ci, tap] = sum_rows draw[row, co] * x[row + (tap - pad) V, ci]
+            mm_dw(draw, x, flat[tap:], N1=co, N2=ci, rows_per_batch=T * V, batches=N, ld1=ci * k, ld2=k,
+                  x_row_shift=(tap - pad) * V)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, bwd_w = conv_packs(conv_w)
+            three = 1 if get_precision() == "bf16" else 3
+            g = draw if three == 1 else ops.split3(draw, 0)
+            dx = ops.gemm_tn(g, bwd_w, ci, k_per_tap=three * co, taps=k, tap_row_stride=V, tap_pad=pad,
+                             rows_per_batch=T * V, batches=N, out_dtype=act_dtype())
+        return dx, None, _ret(sw), gcb, _ret(sg), _ret(sb), None, None, None, None, None, (dy if has_res else None), None
+
+
+def unit2d(x, dims, conv_w, conv_b, bn_w, bn_b, rm, rv, training, momentum, eps, res_post=None, want_perm=False):
+    return Unit2DFn.apply(x, dims, conv_w, conv_b, bn_w, bn_b, rm, rv, training, momentum, eps, res_post, want_perm)
+
+
+# ------------------------------------------------------------------------------------------------
+# gcn0: unit_agcn(3 -> Cout)
+# ------------------------------------------------------------------------------------------------
+def _p3(ts):
+    return (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
+
+
+def _gcn0_struct(x, A, PA, mods, bufs, training, momentum, eps, Mmat, moments, stats, wfold, y):
+    N, T, V, _ = x.shape
+    wa, ba, wb, bb, wd, bd, wdn, bdn, dng, dnb, bng, bnb = mods
+    dn_rm, dn_rv, bn_rm, bn_rv = bufs
+    Cout, IC = wd[0].shape[0], wa[0].shape[0]
+    return _lib.Gcn0Fwd(x=x.data_ptr(), A=A.data_ptr(), PA=PA.data_ptr(), Wa=_p3(wa), ba=_p3(ba), Wb=_p3(wb), bb=_p3(bb),
+                        Wd=_p3(wd), bd=_p3(bd), Wdn=wdn.data_ptr(), bdn=bdn.data_ptr(), bn_g=bng.data_ptr(),
+                        bn_b=bnb.data_ptr(), dn_g=dng.data_ptr(), dn_b=dnb.data_ptr(), bn_rm=bn_rm.data_ptr(),
+                        bn_rv=bn_rv.data_ptr(), dn_rm=dn_rm.data_ptr(), dn_rv=dn_rv.data_ptr(), N=N, T=T, V=V, Cout=Cout,
+                        IC=IC, training=int(training), momentum=momentum, eps=eps, Mmat=Mmat.data_ptr(),
+                        moments=moments.data_ptr(), stats=stats.data_ptr(), Wfold=wfold.data_ptr(), y=y.data_ptr(),
+                        y_dtype=ops.dt(y), precise=int(get_precision() == "fp32"))
+
+
+class Gcn0Fn(torch.autograd.Function):
+    """unit_agcn with 3 input channels on the raw (N,T,V,3) skeleton batch (model/unit_agcn.py:73-93).
+    Inputs after x/A: PA, 3x(conv_a w,b), 3x(conv_b w,b), 3x(conv_d w,b), down conv w,b, down bn w,b, bn w,b,
+    then the four running-stat buffers."""
+
+    @staticmethod
+    def forward(ctx, x, A, training, momentum, eps, PA, *rest):
+        params, bufs = rest[:24], rest[24:]
+        ops.need_cuda(x, A, PA, *params, *bufs)
+        ops.ensure_device(x)
+        if x.dtype != torch.float32:
+            raise RuntimeError("gcn0 expects the float32 skeleton batch (N,T,V,3)")
+        wa, ba = params[0:6:2], params[1:6:2]
+        wb, bb = params[6:12:2], params[7:12:2]
+        wd, bd = params[12:18:2], params[13:18:2]
+        wdn, bdn, dng, dnb, bng, bnb = params[18:24]
+        N, T, V, cin = x.shape
+        if cin != 3:
+            raise RuntimeError("gcn0 kernel is specialised for 3 input channels")
+        Cout = wd[0].shape[0]
+        dev = x.device
+        Mmat = torch.empty((N, 3, V, V), device=dev, dtype=torch.float32)
+        moments = torch.empty((N, _lib.GCN0_NMOM), device=dev, dtype=torch.float32)
+        stats = torch.empty(_lib.GCN0_NSTAT_BASE + 4 * Cout, device=dev, dtype=torch.float32)
+        wfold = torch.empty((Cout, 16), device=dev, dtype=torch.float32)
+        y = torch.empty((N * T * V, Cout), device=dev, dtype=act_dtype())
+        det = lambda ts: [t.detach() for t in ts]  # noqa: E731
+        mods = (det(wa), det(ba), det(wb), det(bb), det(wd), det(bd), wdn.detach(), bdn.detach(), dng.detach(),
+                dnb.detach(), bng.detach(), bnb.detach())
+        st = _gcn0_struct(x, A, PA.detach(), mods, bufs, training, momentum, eps, Mmat, moments, stats, wfold, y)
+        _lib.check(_lib.lib().afb_gcn0_fwd(C.byref(st), ops.stream()), "afb_gcn0_fwd")
+        ctx.save_for_backward(x, A, PA, Mmat, stats, wfold, y, *params, *bufs)
+        ctx.cfg = (training, momentum, eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        saved = ctx.saved_tensors
+        x, A, PA, Mmat, stats, wfold, y = saved[:7]
+        params, bufs = saved[7:31], saved[31:]
+        training, momentum, eps = ctx.cfg
+        wa, ba = params[0:6:2], params[1:6:2]
+        wb, bb = params[6:12:2], params[7:12:2]
+        wd, bd = params[12:18:2], params[13:18:2]
+        wdn, bdn, dng, dnb, bng, bnb = params[18:24]
+        det = lambda ts: [t.detach() for t in ts]  # noqa: E731
+        mods = (det(wa), det(ba), det(wb), det(bb), det(wd), det(bd), wdn.detach(), bdn.detach(), dng.detach(),
+                dnb.detach(), bng.detach(), bnb.detach())
+        Cout = wd[0].shape[0]
+        moments = torch.empty(1, device=x.device, dtype=torch.float32)  # unused by backward
+        f = _gcn0_struct(x, A, PA.detach(), mods, bufs, training, momentum, eps, Mmat, moments, stats, wfold, y)
+        dy = _as_act(dy.contiguous())
+        ws = torch.empty(32 * Cout + 256, device=x.device, dtype=torch.float32)
+        sinks = [_grad_sink(p) for p in (PA, *params)]
+        gp = lambda i: sinks[i][0].data_ptr()  # noqa: E731
+        b = _lib.Gcn0Bwd(f=f, dy=dy.data_ptr(), ws=ws.data_ptr(), dPA=gp(0),
+                         dWa=(C.c_void_p * 3)(gp(1), gp(3), gp(5)), dba=(C.c_void_p * 3)(gp(2), gp(4), gp(6)),
+                         dWb=(C.c_void_p * 3)(gp(7), gp(9), gp(11)), dbb=(C.c_void_p * 3)(gp(8), gp(10), gp(12)),
+                         dWd=(C.c_void_p * 3)(gp(13), gp(15), gp(17)), dbd=(C.c_void_p * 3)(gp(14), gp(16), gp(18)),
+                         dWdn=gp(19), dbdn=gp(20), ddn_g=gp(21), ddn_b=gp(22), dbn_g=gp(23), dbn_b=gp(24))
+        _lib.check(_lib.lib().afb_gcn0_bwd(C.byref(b), ops.stream()), "afb_gcn0_bwd")
+        return (None, None, None, None, None) + tuple(_ret(s) for s in sinks) + (None,) * len(bufs)
+
+
+def gcn0(x, A, training, momentum, eps, PA, params, bufs):
+    return Gcn0Fn.apply(x, A, training, momentum, eps, PA, *params, *bufs)
+
+
+# ------------------------------------------------------------------------------------------------
+# general unit_agcn(C -> Cout), C % 8 == 0  (TCN_GCN_unit stack, ST_TR_new.py:355-385)
+# ------------------------------------------------------------------------------------------------
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+def _agcn_stacked(wa, ba, wb, bb, wd, bd):
+    """Stacked operands, rebuilt when any member changes:
+       Wab  fp32 [ldt, C]  rows (a0,a1,a2,b0,b1,b2, zero pad), bab fp32 [ldt]
+       Wdc  fp32 [Cout, 3C] (Wd_0 | Wd_1 | Wd_2),             bdc fp32 [Cout] = sum_i bd_i."""
+    members = (*wa, *ba, *wb, *bb, *wd, *bd)
+    ver = tuple((m._version, m.data_ptr()) for m in members) + (_EPOCH[0],)
+    slot = _slot(wa[0])
+    ent = slot.get("agcn_stack")
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    with torch.no_grad():
+        IC, Cin = wa[0].shape[0], wa[0].shape[1]
+        Cout = wd[0].shape[0]
+        ldt = _round_up(6 * IC, 64)
+        dev = wa[0].device
+        Wab = torch.zeros((ldt, Cin), device=dev, dtype=torch.float32)
+        bab = torch.zeros(ldt, device=dev, dtype=torch.float32)
+        Wdc = torch.empty((Cout, 3 * Cin), device=dev, dtype=torch.float32)
+        for i in range(3):
+            ops.copy2d(wa[i].detach(), Wab, IC, Cin, Cin, Cin, dst_off=i * IC * Cin)
+            ops.copy2d(wb[i].detach(), Wab, IC, Cin, Cin, Cin, dst_off=(3 + i) * IC * Cin)
+            ops.copy2d(ba[i].detach(), bab, 1, IC, IC, IC, dst_off=i * IC)
+            ops.copy2d(bb[i].detach(), bab, 1, IC, IC, IC, dst_off=(3 + i) * IC)
+            ops.copy2d(wd[i].detach(), Wdc, Cout, Cin, Cin, 3 * Cin, dst_off=i * Cin)
+        bdc = ops.axpby(ops.axpby(bd[0].detach(), 1.0, bd[1].detach(), 1.0), 1.0, bd[2].detach(), 1.0)
+        if _PRECISION[0] == "bf16":
+            ab_f, dc_f = ops.cast(Wab, torch.bfloat16), ops.cast(Wdc, torch.bfloat16)
+            ab_x, dc_x = ab_f, dc_f
+        else:
+            ab_f, dc_f = ops.split3(Wab, 1), ops.split3(Wdc, 1)
+            ab_x = ops.split3(Wab, 2).view(3 * ldt, Cin)
+            dc_x = ops.split3(Wdc, 2).view(3 * Cout, 3 * Cin)
+        out = dict(ldt=ldt, bab=bab, bdc=bdc, ab_f=ab_f, dc_f=dc_f, ab_x=ab_x, dc_x=dc_x)
+    slot["agcn_stack"] = (ver, out)
+    return out
+
+
+def _gemm_raw(x, w_f, N, **epi):
+    """x (activation dtype) @ pre-packed operand w_f."""
+    if _PRECISION[0] == "bf16":
+        return ops.gemm_tn(x, w_f, N, out_dtype=torch.bfloat16, **epi)
+    return ops.gemm_tn(ops.split3(x, 0), w_f, N, out_dtype=torch.float32, **epi)
+
+
+def _gemm_raw_dx(g, w_x, K, **epi):
+    if _PRECISION[0] == "bf16":
+        return ops.gemm_tn(g, w_x, K, b_mn_major=True, out_dtype=torch.bfloat16, **epi)
+    return ops.gemm_tn(ops.split3(g, 0), w_x, K, b_mn_major=True, out_dtype=torch.float32, **epi)
+
+
+def _dw_cols(g, x, dW, N1, N2, g_col0=0, x_col0=0):
+    """dW [N1, N2] += g[:, g_col0:g_col0+N1]^T x[:, x_col0:x_col0+N2] (mode aware)."""
+    if _PRECISION[0] == "bf16":
+        return ops.gemm_dw(g, x, dW, N1=N1, N2=N2, ld1=N2, g_col0=g_col0, x_col0=x_col0)
+    gs, xs = ops.split3(g, 0), ops.split3(x, 1)
+    wg, wx = g.shape[1], x.shape[1]
+    for j in range(3):
+        ops.gemm_dw(gs, xs, dW, N1=N1, N2=N2, ld1=N2, g_col0=j * wg + g_col0, x_col0=j * wx + x_col0)
+    return dW
+
+
+class AgcnFn(torch.autograd.Function):
+    """x tokens [N*T*V, C] -> relu(bn(sum_i conv_d_i(x M_i)) + down(x)).  Inputs after the scalars:
+    PA, 3x(conv_a w,b), 3x(conv_b w,b), 3x(conv_d w,b), bn w,b, [down conv w,b, down bn w,b], then running
+    stats bn_rm, bn_rv, [dn_rm, dn_rv]."""
+
+    @staticmethod
+    def forward(ctx, x, dims, A, training, momentum, eps, has_down, PA, *rest):
+        N, T, V = dims
+        npar = 24 if has_down else 20
+        params, bufs = rest[:npar], rest[npar:]
+        x = _as_act(x)
+        wa, ba = params[0:6:2], params[1:6:2]
+        wb, bb = params[6:12:2], params[7:12:2]
+        wd, bd = params[12:18:2], params[13:18:2]
+        bng, bnb = params[18:20]
+        M, Cin = x.shape
+        Cout, IC = wd[0].shape[0], wa[0].shape[0]
+        st = _agcn_stacked(wa, ba, wb, bb, wd, bd)
+        ldt = st["ldt"]
+        thph = _gemm_raw(x, st["ab_f"], ldt, bias=st["bab"])
+        P = torch.empty((N, 3, V, V), device=x.device, dtype=torch.float32)
+        Mmat = torch.empty_like(P)
+        ops._call("afb_agcn_scores_fwd", ops.ptr(thph), ops.dt(thph), ldt, ops.ptr(A), ops.ptr(PA.detach()), ops.ptr(P),
+                  ops.ptr(Mmat), N, T, V, IC, ops.stream())
+        z = torch.empty((M, 3 * Cin), device=x.device, dtype=x.dtype)
+        ops._call("afb_agcn_aggregate_fwd", ops.ptr(x), ops.ptr(Mmat), ops.ptr(z), ops.dt(x), N, T, V, Cin, ops.stream())
+        h_raw = _gemm_raw(z, st["dc_f"], Cout, bias=st["bdc"])
+        stats_h = _bn_forward(h_raw, bng, bnb, bufs[0], bufs[1], training, momentum, eps)
+        if has_down:
+            wdn, bdn, dng, dnb = params[20:24]
+            d_raw = mm_fwd(x, wdn, bias=bdn.detach())
+            stats_d = _bn_forward(d_raw, dng, dnb, bufs[2], bufs[3], training, momentum, eps)
+            res, _ = ops.bn_act_fwd(d_raw, stats_d[2], stats_d[3], False)
+        else:
+            if Cin != Cout:
+                raise RuntimeError("unit_agcn without `down` needs in_channels == out_channels")
+            d_raw = stats_d = None
+            res = x
+        y, _ = ops.bn_act_fwd(h_raw, stats_h[2], stats_h[3], True, res_pre=res)
+        ctx.save_for_backward(x, A, thph, P, Mmat, z, h_raw, stats_h, d_raw, stats_d, res if has_down else None, PA, *params)
+        ctx.cfg = (N, T, V, training, has_down, len(bufs))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        saved = ctx.saved_tensors
+        x, A, thph, P, Mmat, z, h_raw, stats_h, d_raw, stats_d, res, PA = saved[:12]
+        params = saved[12:]
+        N, T, V, training, has_down, nbufs = ctx.cfg
+        wa, ba = params[0:6:2], params[1:6:2]
+        wb, bb = params[6:12:2], params[7:12:2]
+        wd, bd = params[12:18:2], params[13:18:2]
+        bng, bnb = params[18:20]
+        M, Cin = x.shape
+        Cout, IC = wd[0].shape[0], wa[0].shape[0]
+        st = _agcn_stacked(wa, ba, wb, bb, wd, bd)
+        ldt = st["ldt"]
+        sinks = [_grad_sink(p) for p in (PA, *params)]
+        sk = lambda i: sinks[i][0]  # noqa: E731   (index 0 = PA, 1.. = params in order)
+        dy = _as_act(dy.contiguous())
+        dh, dres = ops.bn_bwd(dy, None, h_raw, stats_h, bng.detach(), bnb.detach(), True, training, sk(19), sk(20),
+                              res_pre=res if has_down else x, want_dres=True)
+        if has_down:
+            wdn, bdn, dng, dnb = params[20:24]
+            dd, _ = ops.bn_bwd(dres, None, d_raw, stats_d, dng.detach(), dnb.detach(), False, training, sk(23), sk(24))
+            mm_dw(dd, x, sk(21).view(Cout, Cin))
+            ops.colsum(dd, sk(22))
+            dx = mm_dx(dd, wdn)
+        else:
+            dx = dres
+        for i in range(3):
+            _dw_cols(dh, z, sk(13 + 2 * i).view(Cout, Cin), Cout, Cin, x_col0=i * Cin)
+            ops.colsum(dh, sk(14 + 2 * i))
+        dz = _gemm_raw_dx(dh, st["dc_x"], 3 * Cin)
+        dM = torch.empty_like(P)
+        ops._call("afb_agcn_aggregate_bwd", ops.ptr(x), ops.ptr(dz), ops.ptr(Mmat), ops.ptr(dx), 1, ops.ptr(dM), ops.dt(x),
+                  N, T, V, Cin, ops.stream())
+        dthph = torch.zeros_like(thph) if ldt != 6 * IC else torch.empty_like(thph)
+        ops._call("afb_agcn_scores_bwd", ops.ptr(thph), ldt, ops.ptr(P), ops.ptr(dM), ops.ptr(sk(0)), ops.ptr(dthph),
+                  ops.dt(thph), N, T, V, IC, ops.stream())
+        for i in range(3):
+            _dw_cols(dthph, x, sk(1 + 2 * i).view(IC, Cin), IC, Cin, g_col0=i * IC)
+            ops.colsum(dthph, sk(2 + 2 * i), col0=i * IC, ncols=IC)
+            _dw_cols(dthph, x, sk(7 + 2 * i).view(IC, Cin), IC, Cin, g_col0=(3 + i) * IC)
+            ops.colsum(dthph, sk(8 + 2 * i), col0=(3 + i) * IC, ncols=IC)
+        dx = _gemm_raw_dx(dthph, st["ab_x"], Cin, residual=dx, out=dx)
+        grads = tuple(_ret(s) for s in sinks)
+        return (dx, None, None, None, None, None, None) + grads + (None,) * nbufs
+
+
+def agcn(x, dims, A, training, momentum, eps, PA, params, bufs, has_down):
+    return AgcnFn.apply(x, dims, A, training, momentum, eps, has_down, PA, *params, *bufs)
+
+
+class CastFn(torch.autograd.Function):
+    """Differentiable dtype change at module boundaries (afb_cast both ways)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src = x.dtype
+        return ops.cast(x.contiguous(), dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.cast(g.contiguous(), ctx.src), None
+
+
+def to_act(x):
+    """Bring a tensor to the activation dtype of the current precision mode (tracked by autograd)."""
+    want = act_dtype()
+    return x if x.dtype == want else CastFn.apply(x, want)
+
+
+class ScaleRowsFn(torch.autograd.Function):
+    """y[m, :] = s[m // div] * x[m, :]   (stand-alone DropPath)."""
+
+    @staticmethod
+    def forward(ctx, x, s, div):
+        ctx.save_for_backward(s)
+        ctx.div = div
+        return ops.scale_rows(x.contiguous(), s, div)
+
+    @staticmethod
+    def backward(ctx, g):
+        (s,) = ctx.saved_tensors
+        return ops.scale_rows(g.contiguous(), s, ctx.div), None, None
+
+
+def scale_rows_fn(x, s, div=1):
+    return ScaleRowsFn.apply(x, s, div)

@@ -1,0 +1,150 @@
+"""Batch data-parallel training: one process per GPU, replaces the reference's single-process
+nn.DataParallel (SHREC/ST_TS/train_sttran.py:84) and its train step (:89-102,185-191):
+
+    zero_grad -> forward -> CrossEntropyLoss -> backward -> [all-reduce mean over ranks] -> AdamW
+
+All live parameters are re-homed into ONE flat fp32 buffer (with flat gradient / Adam-moment / bf16
+shadow twins), so the gradient exchange is a single NCCL all-reduce over NVLink/NVSwitch and the
+optimizer is a single fused kernel that also refreshes the bf16 GEMM operands.  Weight-gradient
+kernels accumulate straight into the flat gradient buffer.  BatchNorm statistics stay per-rank, which
+is what DataParallel does.  The forward+backward of a fixed shape can be captured in a
+CUDA graph (`use_graph=True`) so the ~300 launches of a step cost one host call.
+"""
+import torch
+import torch.distributed as dist
+
+from . import functional as AF
+from . import ops
+
+
+def shard_range(n, rank, world):
+    """Contiguous [lo, hi) slice of a global batch of n samples owned by `rank` (n % world may be != 0)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+class FlatBuffers:
+    """Layout of the flat parameter space: name -> (offset, numel, shape); offsets 8-element aligned so every
+    bf16 view is 16-byte aligned (TMA requirement).  Pure host logic (testable on CPU)."""
+
+    ALIGN = 8
+
+    def __init__(self, named_shapes):
+        self.index = {}
+        off = 0
+        for name, shape in named_shapes:
+            n = 1
+            for s in shape:
+                n *= s
+            self.index[name] = (off, n, tuple(shape))
+            off += _round_up(max(n, 1), self.ALIGN)
+        self.total = _round_up(off, self.ALIGN)
+
+    def view(self, flat, name):
+        off, n, shape = self.index[name]
+        return flat[off:off + n].view(shape)
+
+
+class GradReducer:
+    """Mean all-reduce of the flat gradient buffer.  With backend nccl this is one collective over
+    NVLink/NVSwitch; the division by world size is folded into the optimizer kernel (grad_scale)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    @property
+    def grad_scale(self):
+        return 1.0 / self.world
+
+    def reduce(self, flat_grad):
+        if self.world > 1:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        return flat_grad
+
+
+class DataParallelTrainer:
+    def __init__(self, model, lr=2e-4, weight_decay=0.1, betas=(0.9, 0.999), eps=1e-8, use_graph=False, group=None):
+        dev = next(model.parameters()).device
+        if not next(model.parameters()).is_cuda:
+            raise RuntimeError("DataParallelTrainer needs the model on a CUDA device (there is no CPU fallback)")
+        self.model, self.device = model, dev
+        self.hp = dict(lr=lr, wd=weight_decay, b1=betas[0], b2=betas[1], eps=eps)
+        live = model.live_parameters() if hasattr(model, "live_parameters") else list(model.named_parameters())
+        self.layout = FlatBuffers([(n, p.shape) for n, p in live])
+        T = self.layout.total
+        z = lambda dt: torch.zeros(T, device=dev, dtype=dt)  # noqa: E731
+        self.flat_p, self.flat_g, self.flat_m, self.flat_v = z(torch.float32), z(torch.float32), z(torch.float32), z(torch.float32)
+        self.flat_lowp = z(torch.bfloat16)
+        self.step_count = torch.ones((), device=dev, dtype=torch.int32)
+        self.params = []
+        with torch.no_grad():
+            for name, p in live:
+                dst = self.layout.view(self.flat_p, name)
+                ops.cast(p.detach().contiguous(), torch.float32, out=dst)
+                p.data = dst
+                p._afb_grad = self.layout.view(self.flat_g, name)
+                p._afb_shadow = self.layout.view(self.flat_lowp, name)
+                p.grad = p._afb_grad
+                self.params.append(p)
+            ops.cast(self.flat_p, torch.bfloat16, out=self.flat_lowp)
+        self.reducer = GradReducer(group)
+        self.use_graph = use_graph
+        self._graph = None
+        self._static = None
+
+    # -- one training step -------------------------------------------------------------------
+    def _fwd_bwd(self, x, labels):
+        self.flat_g.zero_()                      # model.zero_grad() (train_sttran.py:187); memset plumbing
+        logits = self.model(x)
+        loss = AF.cross_entropy(logits, labels)
+        loss.backward()
+        return loss.detach(), logits.detach()
+
+    def _optimize(self):
+        self.reducer.reduce(self.flat_g)
+        h = self.hp
+        ops.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_lowp, self.step_count, h["lr"], h["b1"],
+                  h["b2"], h["eps"], h["wd"], self.reducer.grad_scale)
+        AF.bump_weights_epoch()
+
+    def step(self, x, labels):
+        """x (n, T, V, 3) float32 and labels (n,) int64 of THIS rank's shard, on the trainer's device.
+        Returns (loss, logits) as device tensors (no host sync)."""
+        self.model.train()
+        if not self.use_graph:
+            out = self._fwd_bwd(x, labels)
+            self._optimize()
+            return out
+        if self._graph is None:
+            self._capture(x, labels)
+        sx, sy, sloss, slogits = self._static
+        sx.copy_(x, non_blocking=True)
+        sy.copy_(labels, non_blocking=True)
+        self._graph.replay()
+        self._optimize()
+        return sloss, slogits
+
+    def _capture(self, x, labels):
+        sx, sy = x.clone(), labels.clone()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):            # warm-up outside capture (lazy inits, smem attributes, caches)
+            for _ in range(2):
+                self._fwd_bwd(sx, sy)
+        torch.cuda.current_stream().wait_stream(side)
+        AF.bump_weights_epoch()                   # force derived-weight kernels to be part of the graph
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            loss, logits = self._fwd_bwd(sx, sy)
+        self._static = (sx, sy, loss, logits)
+
+    @torch.no_grad()
+    def evaluate(self, x):
+        self.model.eval()
+        return self.model(x)
