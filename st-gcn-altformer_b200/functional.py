@@ -542,7 +542,7 @@ class Gcn0Fn(torch.autograd.Function):
         mods = (det(wa), det(ba), det(wb), det(bb), det(wd), det(bd), wdn.detach(), bdn.detach(), dng.detach(),
                 dnb.detach(), bng.detach(), bnb.detach())
         st = _gcn0_struct(x, A, PA.detach(), mods, bufs, training, momentum, eps, Mmat, moments, stats, wfold, y)
-        _lib.check(_lib.lib().afb_gcn0_fwd(C.byref(st), ops.stream()), "afb_gcn0_fwd")
+        ops._call("afb_gcn0_fwd", C.byref(st), ops.stream())
         ctx.save_for_backward(x, A, PA, Mmat, stats, wfold, y, *params, *bufs)
         ctx.cfg = (training, momentum, eps)
         return y
@@ -572,7 +572,7 @@ class Gcn0Fn(torch.autograd.Function):
                          dWb=(C.c_void_p * 3)(gp(7), gp(9), gp(11)), dbb=(C.c_void_p * 3)(gp(8), gp(10), gp(12)),
                          dWd=(C.c_void_p * 3)(gp(13), gp(15), gp(17)), dbd=(C.c_void_p * 3)(gp(14), gp(16), gp(18)),
                          dWdn=gp(19), dbdn=gp(20), ddn_g=gp(21), ddn_b=gp(22), dbn_g=gp(23), dbn_b=gp(24))
-        _lib.check(_lib.lib().afb_gcn0_bwd(C.byref(b), ops.stream()), "afb_gcn0_bwd")
+        ops._call("afb_gcn0_bwd", C.byref(b), ops.stream())
         return (None, None, None, None, None) + tuple(_ret(s) for s in sinks) + (None,) * len(bufs)
 
 

@@ -49,8 +49,13 @@ def ensure_device(t):
         _checked_devices.add(d)
 
 
+LAUNCHES = [0]  # kernels launched through the C ABI (bench.py reports launches per step)
+_KERNELS_PER_CALL = {"afb_gcn0_fwd": 3, "afb_gcn0_bwd": 4}
+
+
 def _call(name, *args):
     _lib.check(getattr(_lib.lib(), name)(*args), name)
+    LAUNCHES[0] += _KERNELS_PER_CALL.get(name, 1)
 
 
 # ------------------------------------------------------------------------------------------------

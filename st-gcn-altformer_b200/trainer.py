@@ -97,6 +97,7 @@ class DataParallelTrainer:
         self.use_graph = use_graph
         self._graph = None
         self._static = None
+        self.launches_per_step = None
 
     # -- one training step -------------------------------------------------------------------
     def _fwd_bwd(self, x, labels):
@@ -140,8 +141,10 @@ class DataParallelTrainer:
         torch.cuda.current_stream().wait_stream(side)
         AF.bump_weights_epoch()                   # force derived-weight kernels to be part of the graph
         self._graph = torch.cuda.CUDAGraph()
+        ops.LAUNCHES[0] = 0
         with torch.cuda.graph(self._graph):
             loss, logits = self._fwd_bwd(sx, sy)
+        self.launches_per_step = ops.LAUNCHES[0] + 2   # + AdamW and the step counter (outside the graph)
         self._static = (sx, sy, loss, logits)
 
     @torch.no_grad()

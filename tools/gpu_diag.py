@@ -18,7 +18,7 @@ RESULTS = []
 
 
 def rel(a, b):
-    a, b = a.double().flatten(), b.double().flatten()
+    a, b = a.detach().double().flatten().cpu(), b.detach().double().flatten().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)), float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
@@ -192,7 +192,7 @@ def grp_elementwise():
             opt.step()
         report("adamw 3 steps", p, pr.detach(), 1e-6)
         report("adamw bf16 shadow", pl, p.bfloat16(), 0)
-        report("adamw step counter", step.float(), torch.tensor(4.0), 0)
+        report("adamw step counter", step.float().cpu(), torch.tensor(4.0), 0)
     check(pools_ce_adam)
 
     def streams():
@@ -381,272 +381,28 @@ def grp_attention():
 
 
 # --------------------------------------------------------------------------------------------
-def _oracle_setup():
-    from oracle import altformer_oracle as O
-    return O
-
-
-def _load_agcn(mod, st, prefix=""):
-    sd = {k[len(prefix):]: v for k, v in st.items() if k.startswith(prefix)}
-    mod.load_state_dict(sd, strict=True)
-
-
-def _grad_report(tag, mod, ref_params, prefix, tol, abs_floor=1e-3):
-    named = dict(mod.named_parameters())
-    worst = 0.0
-    for k, p in named.items():
-        rg = ref_params[prefix + k].grad
-        if rg is None:
-            continue
-        got = p.grad
-        if got is None:
-            RESULTS.append((f"{tag} grad {k}", False))
-            print(f"FAIL {tag} grad {k}: missing")
-            continue
-        rn = float(rg.norm())
-        if rn < 1e-5:  # analytically zero gradients: absolute check
-            ok = float(got.float().norm()) < abs_floor
-            RESULTS.append((f"{tag} grad {k}", ok))
-            if not ok:
-                print(f"FAIL {tag} grad {k}: expected ~0, got norm {float(got.float().norm()):.3e}")
-            continue
-        e_inf, e_l2 = rel(got.cpu(), rg)
-        worst = max(worst, e_l2)
-        ok = e_inf <= tol and e_l2 <= tol
-        RESULTS.append((f"{tag} grad {k}", ok))
-        if not ok:
-            print(f"FAIL {tag} grad {k:40s} rel_inf={e_inf:.3e} rel_l2={e_l2:.3e} tol={tol:g}")
-    print(f"     {tag}: worst grad rel_l2 = {worst:.3e}", flush=True)
-
-
-def _oracle_run(fn, st, x, need_dx):
-    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in st.items()}
-    xr = x.clone().requires_grad_(need_dx)
-    y = fn(xr, params)
-    cot = torch.randn(y.shape, generator=torch.Generator().manual_seed(7))
-    (y * cot).sum().backward()
-    return y.detach(), xr.grad, params, cot
-
-
-def grp_gcn0():
-    O = _oracle_setup()
-
-    def gcn0_case(N, T, V, training, mode, tol, seed):
-        AF.set_precision(mode)
-        A = O.spatial_graph(V)
-        st = O.random_state(O.agcn_spec("", 3, 128, V), seed)
-        x, _ = O.synthetic_batch(N, T, V, 14, seed + 1)
-        xc = x.permute(0, 3, 1, 2).contiguous()
-        yr, _, params, cot = _oracle_run(lambda x_, p: O.agcn_forward(x_, p, "", A, training), st, xc, False)
-        mod = ab.unit_agcn(3, 128, A).to(DEV)
-        _load_agcn(mod, st)
-        mod.train(training)
-        y = mod(x.to(DEV).permute(0, 3, 1, 2))
-        tag = f"gcn0 N={N} T={T} V={V} train={training} {mode}"
-        report(tag + " fwd", y.float().cpu(), yr, tol)
-        if training:
-            (y.float() * cot.to(DEV)).sum().backward()
-            _grad_report(tag, mod, params, "", 5 * tol)
-            report(tag + " running_mean", mod.bn.running_mean.cpu(), params["bn.running_mean"], 1e-4)
-            report(tag + " running_var", mod.bn.running_var.cpu(), params["bn.running_var"], 1e-4)
-            report(tag + " down running_var", mod.down[1].running_var.cpu(), params["down.1.running_var"], 1e-4)
-        AF.set_precision("bf16")
-
-    check(lambda: gcn0_case(4, 8, 22, True, "fp32", 1e-4, 11))
-    check(lambda: gcn0_case(4, 8, 22, False, "fp32", 1e-4, 11))
-    check(lambda: gcn0_case(4, 8, 22, True, "bf16", 1e-2, 11))
-    check(lambda: gcn0_case(3, 6, 46, True, "fp32", 1e-4, 12))
-    check(lambda: gcn0_case(3, 6, 46, True, "bf16", 1e-2, 12))
-    check(lambda: gcn0_case(32, 32, 22, True, "bf16", 1e-2, 13))
-    check(lambda: gcn0_case(8, 64, 46, True, "bf16", 1e-2, 14))
-    check(lambda: gcn0_case(32, 32, 22, False, "bf16", 1e-2, 13))
-
-
-def grp_modules():
-    O = _oracle_setup()
-
-    def unit2d_case(Cc, N, T, V, training, mode, tol):
-        AF.set_precision(mode)
-        st = O.random_state(O.unit2d_spec("", Cc, Cc, 9), 21)
-        x = torch.randn(N, Cc, T, V, generator=torch.Generator().manual_seed(5))
-        yr, dxr, params, cot = _oracle_run(lambda x_, p: O.unit2d_forward(x_, p, "", training), st, x, True)
-        mod = ab.Unit2D(Cc, Cc, 9).to(DEV)
-        mod.load_state_dict(st)
-        mod.train(training)
-        xg = x.to(DEV).requires_grad_(True)
-        y = mod(xg)
-        tag = f"Unit2D C={Cc} N={N} T={T} V={V} train={training} {mode}"
-        report(tag + " fwd", y.float().cpu(), yr, tol)
-        (y.float() * cot.to(DEV)).sum().backward()
-        report(tag + " dx", xg.grad.cpu(), dxr, 5 * tol)
-        _grad_report(tag, mod, params, "", 5 * tol, abs_floor=0.05 if mode == "bf16" else 1e-3)
-        AF.set_precision("bf16")
-
-    check(lambda: unit2d_case(64, 2, 12, 22, True, "fp32", 1e-4))
-    check(lambda: unit2d_case(128, 3, 32, 22, True, "bf16", 1e-2))
-    check(lambda: unit2d_case(128, 2, 16, 46, False, "bf16", 1e-2))
-
-    def block_case(D, B, L, mode, tol):
-        AF.set_precision(mode)
-        st = O.random_state(O.block_spec("", D), 41)
-        x = torch.randn(B, L, D, generator=torch.Generator().manual_seed(6))
-        yr, dxr, params, cot = _oracle_run(lambda x_, p: O.block_forward(x_, p, ""), st, x, True)
-        mod = ab.Block(D, 8, mlp_ratio=2.0, qkv_bias=True, norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6)).to(DEV)
-        mod.load_state_dict(st)
-        xg = x.to(DEV).requires_grad_(True)
-        y = mod(xg)
-        tag = f"Block D={D} B={B} L={L} {mode}"
-        report(tag + " fwd", y.float().cpu(), yr, tol)
-        (y.float() * cot.to(DEV)).sum().backward()
-        report(tag + " dx", xg.grad.cpu(), dxr, 2 * tol)
-        _grad_report(tag, mod, params, "", 3 * tol)
-        # sub-modules standalone
-        a = mod.attn(xg.detach())
-        ar = O.attention_forward(x, st, "attn.")
-        report(tag + " Attention standalone", a.float().cpu(), ar, tol)
-        m = mod.mlp(xg.detach())
-        report(tag + " Mlp standalone", m.float().cpu(), O.mlp_forward(x, st, "mlp."), tol)
-        AF.set_precision("bf16")
-
-    check(lambda: block_case(256, 24, 22, "fp32", 1e-4))
-    check(lambda: block_case(256, 24, 22, "bf16", 1.5e-2))
-    check(lambda: block_case(512, 6, 32, "bf16", 1.5e-2))
-
-    def droppath_case():
-        AF.set_precision("fp32")
-        D, B, L = 256, 12, 22
-        st = O.random_state(O.block_spec("", D), 43)
-        x = torch.randn(B, L, D, generator=torch.Generator().manual_seed(8))
-        k1 = (torch.rand(B) > 0.3).float() / 0.7
-        k2 = (torch.rand(B) > 0.3).float() / 0.7
-        yr, dxr, params, cot = _oracle_run(lambda x_, p: O.block_forward(x_, p, "", keep=(k1, k2)), st, x, True)
-        mod = ab.Block(D, 8, mlp_ratio=2.0, qkv_bias=True, drop_path=0.3, norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6)).to(DEV)
-        mod.load_state_dict(st)
-        calls = [k1.to(DEV), k2.to(DEV)]
-        mod.drop_path.row_scale = lambda B_, dev: calls.pop(0)
-        xg = x.to(DEV).requires_grad_(True)
-        y = mod(xg)
-        report("Block DropPath pinned masks fwd fp32", y.float().cpu(), yr, 1e-4)
-        (y.float() * cot.to(DEV)).sum().backward()
-        report("Block DropPath pinned masks dx fp32", xg.grad.cpu(), dxr, 2e-4)
-        _grad_report("Block DropPath", mod, params, "", 3e-4)
-        AF.set_precision("bf16")
-    check(droppath_case)
-
-    def agcn_case(cin, cout, N, T, V, mode, tol):
-        AF.set_precision(mode)
-        A = O.spatial_graph(V)
-        st = O.random_state(O.agcn_spec("", cin, cout, V), 13)
-        x = 0.5 * torch.randn(N, cin, T, V, generator=torch.Generator().manual_seed(9))
-        yr, dxr, params, cot = _oracle_run(lambda x_, p: O.agcn_forward(x_, p, "", A, True), st, x, True)
-        mod = ab.unit_agcn(cin, cout, A).to(DEV)
-        mod.load_state_dict(st)
-        xg = x.to(DEV).requires_grad_(True)
-        y = mod(xg)
-        tag = f"unit_agcn {cin}->{cout} N={N} T={T} V={V} {mode}"
-        report(tag + " fwd", y.float().cpu(), yr, tol)
-        (y.float() * cot.to(DEV)).sum().backward()
-        report(tag + " dx", xg.grad.cpu(), dxr, 5 * tol)
-        _grad_report(tag, mod, params, "", 5 * tol, abs_floor=0.05 if mode == "bf16" else 1e-3)
-        AF.set_precision("bf16")
-
-    check(lambda: agcn_case(64, 64, 2, 8, 22, "fp32", 1e-4))
-    check(lambda: agcn_case(64, 128, 2, 8, 22, "fp32", 1e-4))
-    check(lambda: agcn_case(128, 128, 4, 32, 22, "bf16", 1.5e-2))
-
-    def tcn_gcn_case(mode, tol):
-        AF.set_precision(mode)
-        Cc, N, T, V = 64, 2, 8, 22
-        A = O.spatial_graph(V)
-        spec = O.OrderedDict()
-        spec.update(O.agcn_spec("gcn1.", Cc, Cc, V))
-        spec.update(O.unit2d_spec("tcn1.", Cc, Cc, 9))
-        st = O.random_state(spec, 31)
-        x = torch.randn(N, Cc, T, V, generator=torch.Generator().manual_seed(131))
-        yr, dxr, params, cot = _oracle_run(lambda x_, p: O.tcn_gcn_forward(x_, p, "", A, True), st, x, True)
-        mod = ab.TCN_GCN_unit(Cc, Cc, A, dropout=0.0).to(DEV)
-        mod.load_state_dict(st)
-        xg = x.to(DEV).requires_grad_(True)
-        y = mod(xg)
-        report(f"TCN_GCN_unit {mode} fwd", y.float().cpu(), yr, tol)
-        (y.float() * cot.to(DEV)).sum().backward()
-        report(f"TCN_GCN_unit {mode} dx", xg.grad.cpu(), dxr, 5 * tol)
-        _grad_report(f"TCN_GCN_unit {mode}", mod, params, "", 5 * tol, abs_floor=0.05 if mode == "bf16" else 1e-3)
-        AF.set_precision("bf16")
-    check(lambda: tcn_gcn_case("fp32", 1e-4))
-    check(lambda: tcn_gcn_case("bf16", 2e-2))
-
-
-def grp_model():
-    O = _oracle_setup()
-
-    def model_case(style, N, T, V, cls, mode, tol, training=True):
-        AF.set_precision(mode)
-        A = O.spatial_graph(V)
-        st = O.random_state(O.model_spec(3, cls, T, V), 61)
-        x, _ = O.synthetic_batch(N, T, V, cls, 161)
-        yr, _, params, cot = _oracle_run(lambda x_, p: O.model_forward(x_, p, A, style, training), st, x, False)
-        graph = "graph.SHRE" if V == 22 else "graph.LMDHG"
-        mod = ab.ST_GCN_AltFormer(3, cls, num_frame=T, num_joints=V, style=style, graph=graph, graph_args={"labeling_mode": "spatial"})
-        mod.load_state_dict(st)
-        mod = mod.to(DEV)
-        for m in mod.modules():
-            if type(m).__name__ == "DropPath":
-                m.drop_prob = 0.0
-        mod.train(training)
-        y = mod(x.to(DEV))
-        tag = f"model style={style} N={N} T={T} V={V} {mode} train={training}"
-        report(tag + " logits", y.float().cpu(), yr, tol)
-        if training:
-            (y.float() * cot.to(DEV)).sum().backward()
-            _grad_report(tag, mod, params, "", 6 * tol, abs_floor=0.1 if mode == "bf16" else 1e-3)
-        AF.set_precision("bf16")
-
-    check(lambda: model_case("ST", 2, 8, 22, 14, "fp32", 2e-4))
-    check(lambda: model_case("TS", 2, 8, 22, 14, "fp32", 2e-4))
-    check(lambda: model_case(None, 2, 8, 22, 28, "fp32", 2e-4))
-    check(lambda: model_case("ST", 4, 32, 22, 28, "bf16", 3e-2))
-    check(lambda: model_case("TS", 4, 32, 22, 28, "bf16", 3e-2))
-    check(lambda: model_case("ST", 2, 16, 46, 14, "bf16", 3e-2, training=False))
-
-
-def grp_trainer():
-    def train_steps():
-        from oracle import altformer_oracle as O
-        torch.manual_seed(0)
-        N, T, V, cls = 16, 32, 22, 28
-        x, yl = O.synthetic_batch(N, T, V, cls, 1234)
-        x, yl = x.to(DEV), yl.to(DEV)
-        losses = {}
-        for use_graph in (False, True):
-            torch.manual_seed(0)
-            mod = ab.ST_GCN_AltFormer(3, cls, num_frame=T, num_joints=V, style="ST", graph="graph.SHRE", graph_args={"labeling_mode": "spatial"}).to(DEV)
-            for m in mod.modules():
-                if type(m).__name__ == "DropPath":
-                    m.drop_prob = 0.0
-            tr = ab.DataParallelTrainer(mod, use_graph=use_graph)
-            ls = []
-            for it in range(6):
-                loss, _ = tr.step(x, yl)
-                ls.append(float(loss))
-            losses[use_graph] = ls
-            print("   losses graph=%s:" % use_graph, ["%.4f" % v for v in ls], flush=True)
-        ok = losses[False][-1] < losses[False][0]
-        RESULTS.append(("trainer loss decreases", ok))
-        print(("PASS" if ok else "FAIL") + " trainer loss decreases")
-        report("trainer graph == eager losses", torch.tensor(losses[True]), torch.tensor(losses[False]), 2e-2)
-    check(train_steps)
+def _module_groups():
+    from tools import gpu_diag_modules
+    return gpu_diag_modules.GROUPS
 
 
 GROUPS = {"simt": grp_simt, "elementwise": grp_elementwise, "gemm_tn": grp_gemm_tn, "gemm_mn": grp_gemm_mn, "gemm_dw": grp_gemm_dw,
-          "attention": grp_attention, "gcn0": grp_gcn0, "modules": grp_modules, "model": grp_model, "trainer": grp_trainer}
+          "attention": grp_attention}
+MODULE_GROUPS = ("gcn0", "modules", "model", "trainer")
+
+
+def run_group(name):
+    if name in GROUPS:
+        return GROUPS[name]()
+    return _module_groups()[name]()
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(GROUPS)
+    sys.modules.setdefault("tools.gpu_diag", sys.modules["__main__"])   # one shared RESULTS list
+    names = sys.argv[1:] or list(GROUPS) + list(MODULE_GROUPS)
     print("device:", torch.cuda.get_device_name(0), "| lib version", ab._lib.lib().afb_version(), flush=True)
     for n in names:
         print(f"===== group {n} =====", flush=True)
-        GROUPS[n]()
+        run_group(n)
     npass = sum(1 for _, ok in RESULTS if ok)
     print(f"SUMMARY {' '.join(names)}: {npass}/{len(RESULTS)} passed", flush=True)
     for name, ok in RESULTS:

@@ -1,0 +1,327 @@
+"""Module- and model-level parity groups (gcn0, modules, model, trainer) of tools/gpu_diag.py.
+
+Every case runs the CPU oracle (pinned to the reference by tests/golden) and the CUDA module on the SAME
+weights and inputs.  In bf16 mode, inputs and cotangents are first rounded to bf16-representable values so
+both sides see identical inputs (the bf16 bar applies per kernel on identical inputs).
+
+Tolerances, as max|d|/max|ref| and relative L2:
+  forward:            fp32 mode 1e-4,  bf16 mode 1e-2 (1.5e-2 for a whole Block = 3 chained GEMM+LN stages)
+  gradients fp32:     5e-4 per tensor at module level
+  gradients bf16:     3e-2 for transformer Blocks; 1e-1 for modules containing a batch-statistics BatchNorm --
+                      the reference itself under torch.autocast(bf16) is 4-7e-2 there
+  whole model:        logits fp32 2e-4 / bf16 3e-2 (reference autocast floor 0.65-1.5e-2); gradients: MEDIAN
+                      tensor error fp32 2e-4 / bf16 1e-1, worst tensor fp32 3e-2 (a max-pool arg-max near-tie
+                      re-routes single gradient entries; seen as ~1e-2 on individual early-layer tensors)
+  analytically-zero gradients (conv_a bias; conv biases feeding a batch-stat BN): absolute, relative to the
+                      sibling weight-gradient norm.
+"""
+import torch
+
+from tools.gpu_diag import DEV, RESULTS, check, rel, report  # noqa: F401
+import altformer_b200 as ab
+from altformer_b200 import functional as AF
+from oracle import altformer_oracle as O
+
+
+def is_zero_class(name, training=True):
+    if not name.endswith(".bias"):
+        return False
+    if "conv_a." in name:
+        return True
+    return training and any(k in name for k in ("conv_d.", "down.0.bias", "conv.bias"))
+
+
+def grad_report(tag, mod, ref_params, tol, abs_rel=None, training=True, worst_tol=None):
+    abs_rel = abs_rel if abs_rel is not None else tol
+    named = dict(mod.named_parameters())
+    errs, fails = [], []
+    for k, p in named.items():
+        if k not in ref_params or ref_params[k].grad is None:
+            continue
+        rg, got = ref_params[k].grad, p.grad
+        if got is None:
+            fails.append(f"{k}: missing")
+            continue
+        if is_zero_class(k, training):
+            sib = named.get(k[:-4] + "weight")
+            scale = float(sib.grad.float().norm()) if sib is not None and sib.grad is not None else 1.0
+            gn = float(got.float().norm())
+            if gn > abs_rel * max(scale, 1e-12):
+                fails.append(f"{k}: analytically zero, got norm {gn:.3e} vs sibling weight-grad norm {scale:.3e}")
+            continue
+        e_inf, e_l2 = rel(got, rg)
+        errs.append(e_l2)
+        if e_l2 != e_l2:
+            fails.append(f"{k}: NaN")
+        elif worst_tol is None and (e_inf > tol or e_l2 > tol):
+            fails.append(f"{k:42s} rel_inf={e_inf:.3e} rel_l2={e_l2:.3e} tol={tol:g}")
+    es = sorted(errs)
+    med, worst = (es[len(es) // 2], es[-1]) if es else (0.0, 0.0)
+    if worst_tol is not None and (med > tol or worst > worst_tol):
+        fails.append(f"median rel_l2 {med:.3e} (tol {tol:g}) worst {worst:.3e} (tol {worst_tol:g})")
+    ok = not fails
+    RESULTS.append((f"{tag} grads", ok))
+    print(f"{'PASS' if ok else 'FAIL'} {tag} grads: {len(errs)} tensors, median rel_l2 {med:.3e}, worst {worst:.3e}", flush=True)
+    for f in fails[:12]:
+        print("     -", f)
+
+
+def r16(t):
+    return t.bfloat16().float()
+
+
+def oracle_run(fn, st, x, need_dx, lowp):
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in st.items()}
+    xr = x.clone().requires_grad_(need_dx)
+    y = fn(xr, params)
+    cot = torch.randn(y.shape, generator=torch.Generator().manual_seed(7))
+    if lowp:
+        cot = r16(cot)
+    (y * cot).sum().backward()
+    return y.detach(), xr.grad, params, cot
+
+
+class precision:
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        AF.set_precision(self.mode)
+
+    def __exit__(self, *a):
+        AF.set_precision("bf16")
+
+
+def _tols(mode, bn):
+    """(forward tol, dx tol, param-grad tol)"""
+    if mode == "fp32":
+        return 1e-4, 5e-4, 5e-4
+    return (1e-2, 1e-1, 1e-1) if bn else (1.5e-2, 3e-2, 3e-2)
+
+
+# --------------------------------------------------------------------------------------------
+def grp_gcn0():
+    def case(N, T, V, training, mode, seed):
+        with precision(mode):
+            ftol, _, gtol = _tols(mode, True)
+            A = O.spatial_graph(V)
+            st = O.random_state(O.agcn_spec("", 3, 128, V), seed)
+            x, _ = O.synthetic_batch(N, T, V, 14, seed + 1)
+            xc = x.permute(0, 3, 1, 2).contiguous()
+            yr, _, params, cot = oracle_run(lambda x_, p: O.agcn_forward(x_, p, "", A, training), st, xc, False, mode == "bf16")
+            mod = ab.unit_agcn(3, 128, A).to(DEV)
+            mod.load_state_dict(st)
+            mod.train(training)
+            y = mod(x.to(DEV).permute(0, 3, 1, 2))
+            tag = f"gcn0 N={N} T={T} V={V} train={training} {mode}"
+            report(tag + " fwd", y.float(), yr, ftol)
+            if training:
+                (y.float() * cot.to(DEV)).sum().backward()
+                grad_report(tag, mod, params, gtol)
+                report(tag + " running_mean", mod.bn.running_mean, params["bn.running_mean"], 1e-4)
+                report(tag + " running_var", mod.bn.running_var, params["bn.running_var"], 1e-4)
+                report(tag + " down running_var", mod.down[1].running_var, params["down.1.running_var"], 1e-4)
+
+    for args in ((4, 8, 22, True, "fp32", 11), (4, 8, 22, False, "fp32", 11), (4, 8, 22, True, "bf16", 11), (3, 6, 46, True, "fp32", 12),
+                 (3, 6, 46, True, "bf16", 12), (32, 32, 22, True, "bf16", 13), (8, 64, 46, True, "bf16", 14), (32, 32, 22, False, "bf16", 13),
+                 (1, 1, 22, True, "fp32", 15), (2, 180, 22, True, "bf16", 16)):
+        check(lambda a=args: case(*a))
+
+
+def grp_modules():
+    def unit2d_case(Cc, N, T, V, training, mode):
+        with precision(mode):
+            ftol, xtol, gtol = _tols(mode, True)
+            st = O.random_state(O.unit2d_spec("", Cc, Cc, 9), 21)
+            x = torch.randn(N, Cc, T, V, generator=torch.Generator().manual_seed(5))
+            x = r16(x) if mode == "bf16" else x
+            yr, dxr, params, cot = oracle_run(lambda x_, p: O.unit2d_forward(x_, p, "", training), st, x, True, mode == "bf16")
+            mod = ab.Unit2D(Cc, Cc, 9).to(DEV)
+            mod.load_state_dict(st)
+            mod.train(training)
+            xg = x.to(DEV).requires_grad_(True)
+            y = mod(xg)
+            tag = f"Unit2D C={Cc} N={N} T={T} V={V} train={training} {mode}"
+            report(tag + " fwd", y.float(), yr, ftol)
+            (y.float() * cot.to(DEV)).sum().backward()
+            report(tag + " dx", xg.grad, dxr, xtol)
+            grad_report(tag, mod, params, gtol, training=training)
+
+    check(lambda: unit2d_case(64, 2, 12, 22, True, "fp32"))
+    check(lambda: unit2d_case(128, 3, 32, 22, True, "bf16"))
+    check(lambda: unit2d_case(128, 2, 16, 46, False, "bf16"))
+    check(lambda: unit2d_case(256, 2, 7, 22, True, "fp32"))
+
+    def block_case(D, B, L, mode):
+        with precision(mode):
+            ftol, xtol, gtol = _tols(mode, False)
+            st = O.random_state(O.block_spec("", D), 41)
+            x = torch.randn(B, L, D, generator=torch.Generator().manual_seed(6))
+            x = r16(x) if mode == "bf16" else x
+            yr, dxr, params, cot = oracle_run(lambda x_, p: O.block_forward(x_, p, ""), st, x, True, mode == "bf16")
+            mod = ab.Block(D, 8, mlp_ratio=2.0, qkv_bias=True, norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6)).to(DEV)
+            mod.load_state_dict(st)
+            xg = x.to(DEV).requires_grad_(True)
+            y = mod(xg)
+            tag = f"Block D={D} B={B} L={L} {mode}"
+            report(tag + " fwd", y.float(), yr, ftol)
+            (y.float() * cot.to(DEV)).sum().backward()
+            report(tag + " dx", xg.grad, dxr, xtol)
+            grad_report(tag, mod, params, gtol)
+            report(tag + " Attention standalone", mod.attn(xg.detach()).float(), O.attention_forward(x, st, "attn."), ftol)
+            report(tag + " Mlp standalone", mod.mlp(xg.detach()).float(), O.mlp_forward(x, st, "mlp."), ftol)
+
+    check(lambda: block_case(256, 24, 22, "fp32"))
+    check(lambda: block_case(256, 24, 22, "bf16"))
+    check(lambda: block_case(512, 6, 32, "bf16"))
+    check(lambda: block_case(512, 3, 64, "fp32"))
+    check(lambda: block_case(256, 7, 46, "bf16"))
+
+    def droppath_case():
+        with precision("fp32"):
+            D, B, L = 256, 12, 22
+            st = O.random_state(O.block_spec("", D), 43)
+            x = torch.randn(B, L, D, generator=torch.Generator().manual_seed(8))
+            k1 = (torch.rand(B) > 0.3).float() / 0.7
+            k2 = (torch.rand(B) > 0.3).float() / 0.7
+            yr, dxr, params, cot = oracle_run(lambda x_, p: O.block_forward(x_, p, "", keep=(k1, k2)), st, x, True, False)
+            mod = ab.Block(D, 8, mlp_ratio=2.0, qkv_bias=True, drop_path=0.3, norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6)).to(DEV)
+            mod.load_state_dict(st)
+            calls = [k1.to(DEV), k2.to(DEV)]
+            mod.drop_path.row_scale = lambda B_, dev: calls.pop(0)
+            xg = x.to(DEV).requires_grad_(True)
+            y = mod(xg)
+            report("Block DropPath pinned masks fwd fp32", y.float(), yr, 1e-4)
+            (y.float() * cot.to(DEV)).sum().backward()
+            report("Block DropPath pinned masks dx fp32", xg.grad, dxr, 5e-4)
+            grad_report("Block DropPath", mod, params, 5e-4)
+    check(droppath_case)
+
+    def agcn_case(cin, cout, N, T, V, mode):
+        with precision(mode):
+            ftol, xtol, gtol = _tols(mode, True)
+            A = O.spatial_graph(V)
+            st = O.random_state(O.agcn_spec("", cin, cout, V), 13)
+            x = 0.5 * torch.randn(N, cin, T, V, generator=torch.Generator().manual_seed(9))
+            x = r16(x) if mode == "bf16" else x
+            yr, dxr, params, cot = oracle_run(lambda x_, p: O.agcn_forward(x_, p, "", A, True), st, x, True, mode == "bf16")
+            mod = ab.unit_agcn(cin, cout, A).to(DEV)
+            mod.load_state_dict(st)
+            xg = x.to(DEV).requires_grad_(True)
+            y = mod(xg)
+            tag = f"unit_agcn {cin}->{cout} N={N} T={T} V={V} {mode}"
+            report(tag + " fwd", y.float(), yr, ftol)
+            (y.float() * cot.to(DEV)).sum().backward()
+            report(tag + " dx", xg.grad, dxr, xtol)
+            grad_report(tag, mod, params, gtol)
+
+    check(lambda: agcn_case(64, 64, 2, 8, 22, "fp32"))
+    check(lambda: agcn_case(64, 128, 2, 8, 22, "fp32"))
+    check(lambda: agcn_case(128, 128, 4, 32, 22, "bf16"))
+    check(lambda: agcn_case(256, 256, 2, 16, 22, "bf16"))
+    check(lambda: agcn_case(64, 64, 2, 16, 46, "bf16"))
+
+    def tcn_gcn_case(mode):
+        with precision(mode):
+            ftol, xtol, gtol = _tols(mode, True)
+            Cc, N, T, V = 64, 2, 8, 22
+            A = O.spatial_graph(V)
+            spec = O.OrderedDict()
+            spec.update(O.agcn_spec("gcn1.", Cc, Cc, V))
+            spec.update(O.unit2d_spec("tcn1.", Cc, Cc, 9))
+            st = O.random_state(spec, 31)
+            x = torch.randn(N, Cc, T, V, generator=torch.Generator().manual_seed(131))
+            x = r16(x) if mode == "bf16" else x
+            yr, dxr, params, cot = oracle_run(lambda x_, p: O.tcn_gcn_forward(x_, p, "", A, True), st, x, True, mode == "bf16")
+            mod = ab.TCN_GCN_unit(Cc, Cc, A, dropout=0.0).to(DEV)
+            mod.load_state_dict(st)
+            xg = x.to(DEV).requires_grad_(True)
+            y = mod(xg)
+            report(f"TCN_GCN_unit {mode} fwd", y.float(), yr, 2 * ftol)
+            (y.float() * cot.to(DEV)).sum().backward()
+            report(f"TCN_GCN_unit {mode} dx", xg.grad, dxr, 1.5 * xtol)
+            grad_report(f"TCN_GCN_unit {mode}", mod, params, 1.5 * gtol)
+    check(lambda: tcn_gcn_case("fp32"))
+    check(lambda: tcn_gcn_case("bf16"))
+
+
+def grp_model():
+    def model_case(style, N, T, V, cls, mode, training=True):
+        with precision(mode):
+            A = O.spatial_graph(V)
+            st = O.random_state(O.model_spec(3, cls, T, V), 61)
+            x, _ = O.synthetic_batch(N, T, V, cls, 161)
+            yr, _, params, cot = oracle_run(lambda x_, p: O.model_forward(x_, p, A, style, training), st, x, False, False)
+            graph = "graph.SHRE" if V == 22 else "graph.LMDHG"
+            mod = ab.ST_GCN_AltFormer(3, cls, num_frame=T, num_joints=V, style=style, graph=graph, graph_args={"labeling_mode": "spatial"})
+            mod.load_state_dict(st)
+            mod = mod.to(DEV)
+            for m in mod.modules():
+                if type(m).__name__ == "DropPath":
+                    m.drop_prob = 0.0
+            mod.train(training)
+            y = mod(x.to(DEV))
+            tag = f"model style={style} N={N} T={T} V={V} {mode} train={training}"
+            report(tag + " logits", y.float(), yr, 2e-4 if mode == "fp32" else 3e-2)
+            if training:
+                (y.float() * cot.to(DEV)).sum().backward()
+                if mode == "fp32":
+                    grad_report(tag, mod, params, 2e-4, abs_rel=1e-3, worst_tol=3e-2)
+                else:
+                    grad_report(tag, mod, params, 1e-1, abs_rel=2e-1, worst_tol=1.0)
+
+    check(lambda: model_case("ST", 2, 8, 22, 14, "fp32"))
+    check(lambda: model_case("TS", 2, 8, 22, 14, "fp32"))
+    check(lambda: model_case(None, 2, 8, 22, 28, "fp32"))
+    check(lambda: model_case("ST", 4, 32, 22, 28, "bf16"))
+    check(lambda: model_case("TS", 4, 32, 22, 28, "bf16"))
+    check(lambda: model_case(None, 2, 16, 46, 14, "bf16"))
+    check(lambda: model_case("ST", 2, 16, 46, 14, "bf16", training=False))
+    check(lambda: model_case("ST", 1, 180, 22, 28, "bf16", training=False))
+
+
+def grp_trainer():
+    def train_steps():
+        torch.manual_seed(0)
+        N, T, V, cls = 16, 32, 22, 28
+        x, yl = O.synthetic_batch(N, T, V, cls, 1234)
+        x, yl = x.to(DEV), yl.to(DEV)
+        losses = {}
+        for use_graph in (False, True):
+            torch.manual_seed(0)
+            mod = ab.ST_GCN_AltFormer(3, cls, num_frame=T, num_joints=V, style="ST", graph="graph.SHRE", graph_args={"labeling_mode": "spatial"}).to(DEV)
+            for m in mod.modules():
+                if type(m).__name__ == "DropPath":
+                    m.drop_prob = 0.0
+            tr = ab.DataParallelTrainer(mod, use_graph=use_graph)
+            ls = [float(tr.step(x, yl)[0]) for _ in range(6)]
+            losses[use_graph] = ls
+            print("   losses graph=%s:" % use_graph, ["%.4f" % v for v in ls], flush=True)
+        ok = losses[False][-1] < 0.5 * losses[False][0]
+        RESULTS.append(("trainer loss decreases", ok))
+        print(("PASS" if ok else "FAIL") + " trainer loss decreases")
+        report("trainer graph == eager losses", torch.tensor(losses[True]), torch.tensor(losses[False]), 2e-2)
+    check(train_steps)
+
+    def adamw_matches_torch():
+        """One trainer step == reference semantics: same grads fed to torch.optim.AdamW give the same params."""
+        torch.manual_seed(1)
+        N, T, V, cls = 4, 8, 22, 14
+        x, yl = O.synthetic_batch(N, T, V, cls, 99)
+        mod = ab.ST_GCN_AltFormer(3, cls, num_frame=T, num_joints=V, style="ST", graph="graph.SHRE", graph_args={"labeling_mode": "spatial"}).to(DEV)
+        for m in mod.modules():
+            if type(m).__name__ == "DropPath":
+                m.drop_prob = 0.0
+        tr = ab.DataParallelTrainer(mod, use_graph=False)
+        before = tr.flat_p.clone()
+        tr.step(x.to(DEV), yl.to(DEV))
+        pr = before.clone().requires_grad_(True)
+        opt = torch.optim.AdamW([pr], lr=2e-4, weight_decay=0.1)
+        pr.grad = tr.flat_g.clone()
+        opt.step()
+        report("trainer AdamW == torch.optim.AdamW on the same grads", tr.flat_p, pr.detach(), 1e-6)
+        report("trainer bf16 shadow == bf16(params)", tr.flat_lowp.float(), tr.flat_p.bfloat16().float(), 0)
+    check(adamw_matches_torch)
+
+
+GROUPS = {"gcn0": grp_gcn0, "modules": grp_modules, "model": grp_model, "trainer": grp_trainer}
