@@ -1,0 +1,56 @@
+"""Time the tcgen05 GEMMs on the cfg2 shapes (M = 256*32*22 tokens) with CUDA events, and serve as the
+target of `ncu --set full` captures.  Usage: python tools/prof_gemm.py [iters]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import altformer_b200 as ab  # noqa: E402,F401
+from altformer_b200 import ops  # noqa: E402
+
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+M = int(os.environ.get("M", 256 * 32 * 22))
+dev = "cuda"
+torch.manual_seed(0)
+
+
+def bench(name, fn, flops, bytes_):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / iters
+    print(f"{name:44s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s  {bytes_ / us / 1e3:8.1f} GB/s", flush=True)
+
+
+def mk(r, c, dt=torch.bfloat16, s=1.0):
+    return (s * torch.randn(r, c, device=dev)).to(dt)
+
+
+x256, x512 = mk(M, 256), mk(M, 512)
+wqkv, wproj, wfc1, wfc2 = mk(768, 256, s=0.05), mk(256, 256, s=0.05), mk(512, 256, s=0.05), mk(256, 512, s=0.05)
+bq, b256, b512 = torch.zeros(768, device=dev), torch.zeros(256, device=dev), torch.zeros(512, device=dev)
+res = mk(M, 256)
+g768, g512 = mk(M, 768), mk(M, 512)
+dW = torch.zeros(768, 256, device=dev)
+
+bench("qkv   tn 768x256 +bias", lambda: ops.gemm_tn(x256, wqkv, 768, bias=bq), 2 * M * 768 * 256, M * (256 + 768) * 2)
+bench("proj  tn 256x256 +bias+residual", lambda: ops.gemm_tn(x256, wproj, 256, bias=b256, residual=res), 2 * M * 256 * 256, M * 768 * 2)
+bench("fc1   tn 512x256 +bias+gelu+preact", lambda: ops.gemm_tn(x256, wfc1, 512, bias=b512, act=ops.ACT_GELU, want_preact=True),
+      2 * M * 512 * 256, M * (256 + 1024) * 2)
+bench("fc2   tn 256x512 +bias+residual", lambda: ops.gemm_tn(x512, wfc2, 256, bias=b256, residual=res), 2 * M * 256 * 512, M * (512 + 512) * 2)
+bench("dX    mn 768->256", lambda: ops.gemm_tn(g768, wqkv, 256, b_mn_major=True), 2 * M * 768 * 256, M * (768 + 256) * 2)
+bench("dpre  mn 256->512 gelu_bwd", lambda: ops.gemm_tn(x256, wfc2, 512, b_mn_major=True, act=ops.ACT_GELU_BWD, aux=x512),
+      2 * M * 256 * 512, M * (256 + 1024) * 2)
+bench("dW    768x256", lambda: ops.gemm_dw(g768, x256, dW), 2 * M * 768 * 256, M * 1024 * 2)
+x128 = mk(M, 128)
+wconv = mk(128, 9 * 128, s=0.03)
+bench("conv  9x1 128->128", lambda: ops.gemm_tn(x128, wconv, 128, k_per_tap=128, taps=9, tap_row_stride=22, tap_pad=4, rows_per_batch=704,
+                                                batches=M // 704, bias=torch.zeros(128, device=dev)), 2 * M * 128 * 1152, M * 256 * 2)
+print("done")
