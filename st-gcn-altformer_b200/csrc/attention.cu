@@ -5,10 +5,24 @@
 // one nn.Linear(dim, 3*dim) + reshape(B, L, 3, heads, dh) implies: feature = s*D + h*dh + d.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace afb {
+// tensor-core path (attention_mma.cu)
+bool attention_mma_supported(int L, int heads, int dh);
+int attention_fwd_mma(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st);
+int attention_bwd_mma(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st);
+
 namespace {
 
 constexpr int kSmemBudget = 200 * 1024;
+
+// bf16 goes to the mma.sync kernels; fp32 (parity mode), odd head sizes, or AFB_ATTN_SIMT=1 (cross-check)
+// use the fp32 CUDA-core kernels below.
+bool use_mma(int dt, int L, int heads, int dh) {
+  static const bool force_simt = getenv("AFB_ATTN_SIMT") != nullptr;
+  return dt == AFB_BF16 && !force_simt && attention_mma_supported(L, heads, dh);
+}
 
 template <typename T>
 __device__ __forceinline__ void load_slice(float* dst, const T* src, int L, int dh, int ld, int lane) {
@@ -143,6 +157,7 @@ using namespace afb;
 extern "C" int afb_attention_fwd(const void* qkv, void* o, int dt, int64_t B, int L, int heads, int dh, float scale, afb_stream s) {
   AFB_REQUIRE(qkv && o && B > 0, "attention_fwd: bad args");
   AFB_REQUIRE(L >= 1 && L <= 64 && dh >= 1 && dh <= 64, "attention: L=%d dh=%d unsupported (L<=64, dh<=64)", L, dh);
+  if (use_mma(dt, L, heads, dh)) return attention_fwd_mma(qkv, o, B, L, heads, dh, scale, as_stream(s));
   const int per_warp = 3 * L * (dh + 1) + L + 3;
   int warps = kSmemBudget / (per_warp * 4);
   if (warps > 8) warps = 8;
@@ -165,6 +180,7 @@ extern "C" int afb_attention_bwd(const void* qkv, const void* dO, void* dqkv, in
                                  float scale, afb_stream s) {
   AFB_REQUIRE(qkv && dO && dqkv && B > 0, "attention_bwd: bad args");
   AFB_REQUIRE(L >= 1 && L <= 64 && dh >= 1 && dh <= 64, "attention: L=%d dh=%d unsupported (L<=64, dh<=64)", L, dh);
+  if (use_mma(dt, L, heads, dh)) return attention_bwd_mma(qkv, dO, dqkv, B, L, heads, dh, scale, as_stream(s));
   const int per_warp = 4 * L * (dh + 1) + 2 * L * (L + 1) + 2;
   int warps = kSmemBudget / (per_warp * 4);
   if (warps > 4) warps = 4;

@@ -1,0 +1,383 @@
+// Tensor-core small-sequence attention (bf16, mma.sync.m16n8k16 + ldmatrix), forward and backward.
+// Reference: model/AltFormer/model_ST.py:49-67.  Sequences are 22..64 tokens long, so one warp owns one
+// (sequence, head): S = QK^T, softmax, PV -- and in backward dP, dS, dQ, dK, dV -- all stay in registers
+// and shared memory; a CTA owns HG heads of one sequence so that global traffic is whole 256/512-byte row
+// segments (coalesced 16-byte accesses), read once and written once.
+//
+// Fragment conventions (PTX ISA, m16n8k16, g = lane / 4, t = lane % 4):
+//   A (16x16 row):  a0 (g, 2t..2t+1)  a1 (g+8, 2t..)  a2 (g, 2t+8..)  a3 (g+8, 2t+8..)
+//   B (16x8  col):  b0 (k = 2t..2t+1, n = g)          b1 (k = 2t+8.., n = g)
+//   C (16x8):       c0,c1 (g, 2t..2t+1)               c2,c3 (g+8, 2t..2t+1)
+// ldmatrix (non-transposed) of an 8x8 b16 tile gives thread (row g, cols 2t..2t+1); .trans gives
+// (rows 2t..2t+1, col g).  An accumulator tile pair (two n8 tiles) is therefore already an A fragment.
+#include "common.cuh"
+
+namespace afb {
+namespace attn_mma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+
+// Geometry of one CTA's shared memory (all pitches are an odd number of 16-byte chunks => conflict-free
+// ldmatrix and 16-byte row copies).
+template <int DH, int LP, int HG> struct Geo {
+  static constexpr int W = HG * DH;             // columns per q / k / v part handled by this CTA
+  static constexpr int QKV_PITCH = 3 * W + 8;   // elements
+  static constexpr int O_PITCH = W + 8;
+  static constexpr int S_PITCH = LP + 8;
+  static constexpr int kThreads = HG * 32;
+  static constexpr size_t fwd_bytes = ((size_t)LP * QKV_PITCH + (size_t)LP * O_PITCH) * 2;
+  static constexpr size_t bwd_bytes = ((size_t)LP * QKV_PITCH + (size_t)LP * O_PITCH + (size_t)HG * 2 * LP * S_PITCH) * 2;
+};
+
+// rows [0, L) of three W-wide column windows of a [.., ld] matrix -> smem tile; rows [L, LP) zeroed.
+template <int W, int PITCH, int PARTS>
+__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t ld, int64_t part_stride, int L, int LP, int nthreads) {
+  constexpr int C16 = W / 8;  // 16-byte chunks per part row
+  const int total = LP * PARTS * C16;
+  for (int idx = threadIdx.x; idx < total; idx += nthreads) {
+    const int row = idx / (PARTS * C16), rem = idx % (PARTS * C16);
+    const int part = rem / C16, c = rem % C16;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < L) v = *reinterpret_cast<const uint4*>(src + row * ld + part * part_stride + c * 8);
+    *reinterpret_cast<uint4*>(dst + row * PITCH + part * W + c * 8) = v;
+  }
+}
+template <int W, int PITCH>
+__device__ __forceinline__ void store_tile(bf16* dst, int64_t ld, const bf16* src, int L, int nthreads) {
+  constexpr int C16 = W / 8;
+  for (int idx = threadIdx.x; idx < L * C16; idx += nthreads) {
+    const int row = idx / C16, c = idx % C16;
+    *reinterpret_cast<uint4*>(dst + row * ld + c * 8) = *reinterpret_cast<const uint4*>(src + row * PITCH + c * 8);
+  }
+}
+
+// S tile for query rows [mi*16, mi*16+16): s[nj][0..3] = (Q K^T) for key tile nj, then masked softmax.
+// Returns the normalised probabilities in s (fp32), columns >= L are exactly 0.
+template <int DH, int LP, int PITCH>
+__device__ __forceinline__ void scores_softmax(const bf16* sq, int qcol, int kcol, int mi, int L, float scale_log2, float (&s)[LP / 8][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  uint32_t qa[DH / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < DH / 16; ++kk)
+    ldsm_x4(smem_u32(sq + (mi * 16 + (lane & 15)) * PITCH + qcol + kk * 16 + (lane >> 4) * 8), qa[kk]);
+#pragma unroll
+  for (int nj = 0; nj < LP / 8; ++nj)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[nj][e] = 0.f;
+#pragma unroll
+  for (int n2 = 0; n2 < LP / 16; ++n2)
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+      uint32_t kb[4];
+      const int id = lane >> 3;
+      ldsm_x4(smem_u32(sq + (n2 * 16 + (lane & 7) + (id >> 1) * 8) * PITCH + kcol + kk * 16 + (id & 1) * 8), kb);
+      mma(s[2 * n2], qa[kk], kb[0], kb[1]);
+      mma(s[2 * n2 + 1], qa[kk], kb[2], kb[3]);
+    }
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nj = 0; nj < LP / 8; ++nj) {
+    const int c = nj * 8 + 2 * t;
+    if (c >= L) { s[nj][0] = -INFINITY; s[nj][2] = -INFINITY; }
+    if (c + 1 >= L) { s[nj][1] = -INFINITY; s[nj][3] = -INFINITY; }
+    mx0 = fmaxf(mx0, fmaxf(s[nj][0], s[nj][1]));
+    mx1 = fmaxf(mx1, fmaxf(s[nj][2], s[nj][3]));
+  }
+  mx0 = quad_max(mx0);
+  mx1 = quad_max(mx1);
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nj = 0; nj < LP / 8; ++nj) {
+    s[nj][0] = exp2f((s[nj][0] - mx0) * scale_log2);
+    s[nj][1] = exp2f((s[nj][1] - mx0) * scale_log2);
+    s[nj][2] = exp2f((s[nj][2] - mx1) * scale_log2);
+    s[nj][3] = exp2f((s[nj][3] - mx1) * scale_log2);
+    sum0 += s[nj][0] + s[nj][1];
+    sum1 += s[nj][2] + s[nj][3];
+  }
+  const float inv0 = 1.0f / quad_sum(sum0), inv1 = 1.0f / quad_sum(sum1);
+#pragma unroll
+  for (int nj = 0; nj < LP / 8; ++nj) {
+    s[nj][0] *= inv0; s[nj][1] *= inv0;
+    s[nj][2] *= inv1; s[nj][3] *= inv1;
+  }
+}
+
+// acc[nd][..] += A(16 x LPk) * Bt, where B[k][n] = src[krow0 + k][col + n] (row-major source, transposed load)
+template <int NK16, int ND8, int PITCH>
+__device__ __forceinline__ void mma_a_regs_bt(const uint32_t (&a)[NK16][4], const bf16* src, int col, float (&acc)[ND8][4]) {
+  const int lane = threadIdx.x & 31, id = lane >> 3;
+#pragma unroll
+  for (int kk = 0; kk < NK16; ++kk)
+#pragma unroll
+    for (int n2 = 0; n2 < ND8 / 2; ++n2) {
+      uint32_t b[4];
+      ldsm_x4_t(smem_u32(src + (kk * 16 + (lane & 7) + (id & 1) * 8) * PITCH + col + n2 * 16 + (id >> 1) * 8), b);
+      mma(acc[2 * n2], a[kk], b[0], b[1]);
+      mma(acc[2 * n2 + 1], a[kk], b[2], b[3]);
+    }
+}
+
+template <int ND8, int PITCH>
+__device__ __forceinline__ void store_acc(bf16* dst, int row0, int col, const float (&acc)[ND8][4], float m0, float m1) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nd = 0; nd < ND8; ++nd) {
+    *reinterpret_cast<uint32_t*>(dst + (row0 + g) * PITCH + col + nd * 8 + 2 * t) = pack2(acc[nd][0] * m0, acc[nd][1] * m0);
+    *reinterpret_cast<uint32_t*>(dst + (row0 + g + 8) * PITCH + col + nd * 8 + 2 * t) = pack2(acc[nd][2] * m1, acc[nd][3] * m1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int DH, int LP, int HG>
+__global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int L, int heads, float scale) {
+  using G = Geo<DH, LP, HG>;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* sq = reinterpret_cast<bf16*>(smraw);
+  bf16* so = sq + LP * G::QKV_PITCH;
+  const int groups = heads / HG;
+  const int64_t b = blockIdx.x / groups;
+  const int h0 = (blockIdx.x % groups) * HG;
+  const int D = heads * DH;
+  load_tile<G::W, G::QKV_PITCH, 3>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L, LP, G::kThreads);
+  __syncthreads();
+  const int hw = threadIdx.x >> 5;
+  const int qcol = hw * DH, kcol = G::W + hw * DH, vcol = 2 * G::W + hw * DH;
+  const float scale_log2 = scale * 1.4426950408889634f;
+#pragma unroll 1
+  for (int mi = 0; mi < LP / 16; ++mi) {
+    if (mi * 16 >= L) break;
+    float s[LP / 8][4];
+    scores_softmax<DH, LP, G::QKV_PITCH>(sq, qcol, kcol, mi, L, scale_log2, s);
+    uint32_t pa[LP / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < LP / 16; ++kk) {
+      pa[kk][0] = pack2(s[2 * kk][0], s[2 * kk][1]);
+      pa[kk][1] = pack2(s[2 * kk][2], s[2 * kk][3]);
+      pa[kk][2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[kk][3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    }
+    float acc[DH / 8][4];
+#pragma unroll
+    for (int nd = 0; nd < DH / 8; ++nd)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
+    mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(pa, sq, vcol, acc);
+    store_acc<DH / 8, G::O_PITCH>(so, mi * 16, hw * DH, acc, 1.f, 1.f);
+  }
+  __syncthreads();
+  store_tile<G::W, G::O_PITCH>(o + b * L * D + h0 * DH, D, so, L, G::kThreads);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int DH, int LP, int HG>
+__global__ void __launch_bounds__(HG * 32) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, bf16* __restrict__ dqkv,
+                                                               int L, int heads, float scale) {
+  using G = Geo<DH, LP, HG>;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* sq = reinterpret_cast<bf16*>(smraw);           // q | k | v   ->  q | dK | dV
+  bf16* sdo = sq + LP * G::QKV_PITCH;                  // dO          ->  dQ
+  const int hw = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, id = lane >> 3;
+  bf16* sP = sdo + LP * G::O_PITCH + hw * 2 * LP * G::S_PITCH;   // per-warp staging of P and dS (bf16)
+  bf16* sdS = sP + LP * G::S_PITCH;
+  const int groups = heads / HG;
+  const int64_t b = blockIdx.x / groups;
+  const int h0 = (blockIdx.x % groups) * HG;
+  const int D = heads * DH;
+  load_tile<G::W, G::QKV_PITCH, 3>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L, LP, G::kThreads);
+  load_tile<G::W, G::O_PITCH, 1>(sdo, dO + b * L * D + h0 * DH, D, 0, L, LP, G::kThreads);
+  __syncthreads();
+  const int qcol = hw * DH, kcol = G::W + hw * DH, vcol = 2 * G::W + hw * DH, ocol = hw * DH;
+  const float scale_log2 = scale * 1.4426950408889634f;
+
+  // ---- phase A: P and dS = P * (dP - delta) * scale for every query tile -> staging ----
+#pragma unroll 1
+  for (int mi = 0; mi < LP / 16; ++mi) {
+    float s[LP / 8][4];
+    scores_softmax<DH, LP, G::QKV_PITCH>(sq, qcol, kcol, mi, L, scale_log2, s);
+    uint32_t da[DH / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk)
+      ldsm_x4(smem_u32(sdo + (mi * 16 + (lane & 15)) * G::O_PITCH + ocol + kk * 16 + (lane >> 4) * 8), da[kk]);
+    float dp[LP / 8][4];
+#pragma unroll
+    for (int nj = 0; nj < LP / 8; ++nj)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dp[nj][e] = 0.f;
+#pragma unroll
+    for (int n2 = 0; n2 < LP / 16; ++n2)
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {  // dP = dO V^T : B[k = d][n = key] = V[key][d] (non-transposed load)
+        uint32_t vb[4];
+        ldsm_x4(smem_u32(sq + (n2 * 16 + (lane & 7) + (id >> 1) * 8) * G::QKV_PITCH + vcol + kk * 16 + (id & 1) * 8), vb);
+        mma(dp[2 * n2], da[kk], vb[0], vb[1]);
+        mma(dp[2 * n2 + 1], da[kk], vb[2], vb[3]);
+      }
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int nj = 0; nj < LP / 8; ++nj) {
+      d0 += s[nj][0] * dp[nj][0] + s[nj][1] * dp[nj][1];
+      d1 += s[nj][2] * dp[nj][2] + s[nj][3] * dp[nj][3];
+    }
+    d0 = quad_sum(d0);
+    d1 = quad_sum(d1);
+#pragma unroll
+    for (int nj = 0; nj < LP / 8; ++nj) {
+      const int c = nj * 8 + 2 * t;
+      bf16* p0 = sP + (mi * 16 + g) * G::S_PITCH + c;
+      bf16* p1 = sP + (mi * 16 + g + 8) * G::S_PITCH + c;
+      *reinterpret_cast<uint32_t*>(p0) = pack2(s[nj][0], s[nj][1]);
+      *reinterpret_cast<uint32_t*>(p1) = pack2(s[nj][2], s[nj][3]);
+      bf16* q0 = sdS + (mi * 16 + g) * G::S_PITCH + c;
+      bf16* q1 = sdS + (mi * 16 + g + 8) * G::S_PITCH + c;
+      *reinterpret_cast<uint32_t*>(q0) = pack2(s[nj][0] * (dp[nj][0] - d0) * scale, s[nj][1] * (dp[nj][1] - d0) * scale);
+      *reinterpret_cast<uint32_t*>(q1) = pack2(s[nj][2] * (dp[nj][2] - d1) * scale, s[nj][3] * (dp[nj][3] - d1) * scale);
+    }
+  }
+  __syncwarp();
+
+  // ---- phase B1: dV = P^T dO  (A = P^T via transposed loads of the staged P) -> v columns ----
+#pragma unroll 1
+  for (int mj = 0; mj < LP / 16; ++mj) {
+    uint32_t a[LP / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < LP / 16; ++kk)  // a0:(key 0-7, q 0-7) a1:(key 8-15, q 0-7) a2:(key 0-7, q 8-15) a3:(key 8-15, q 8-15)
+      ldsm_x4_t(smem_u32(sP + (kk * 16 + (lane & 7) + (id >> 1) * 8) * G::S_PITCH + mj * 16 + (id & 1) * 8), a[kk]);
+    float acc[DH / 8][4];
+#pragma unroll
+    for (int nd = 0; nd < DH / 8; ++nd)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
+    mma_a_regs_bt<LP / 16, DH / 8, G::O_PITCH>(a, sdo, ocol, acc);
+    store_acc<DH / 8, G::QKV_PITCH>(sq, mj * 16, vcol, acc, 1.f, 1.f);
+  }
+  __syncwarp();
+  // ---- phase B2: dQ = dS K  -> the (now free) dO columns of this head ----
+#pragma unroll 1
+  for (int mi = 0; mi < LP / 16; ++mi) {
+    uint32_t a[LP / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < LP / 16; ++kk)
+      ldsm_x4(smem_u32(sdS + (mi * 16 + (lane & 15)) * G::S_PITCH + kk * 16 + (lane >> 4) * 8), a[kk]);
+    float acc[DH / 8][4];
+#pragma unroll
+    for (int nd = 0; nd < DH / 8; ++nd)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
+    mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(a, sq, kcol, acc);
+    store_acc<DH / 8, G::O_PITCH>(sdo, mi * 16, ocol, acc, 1.f, 1.f);
+  }
+  __syncwarp();
+  // ---- phase B3: dK = dS^T Q  -> k columns (K is no longer needed by this warp) ----
+#pragma unroll 1
+  for (int mj = 0; mj < LP / 16; ++mj) {
+    uint32_t a[LP / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < LP / 16; ++kk)
+      ldsm_x4_t(smem_u32(sdS + (kk * 16 + (lane & 7) + (id >> 1) * 8) * G::S_PITCH + mj * 16 + (id & 1) * 8), a[kk]);
+    float acc[DH / 8][4];
+#pragma unroll
+    for (int nd = 0; nd < DH / 8; ++nd)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
+    mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(a, sq, qcol, acc);
+    store_acc<DH / 8, G::QKV_PITCH>(sq, mj * 16, kcol, acc, 1.f, 1.f);
+  }
+  __syncthreads();
+  bf16* out = dqkv + b * L * 3 * D + h0 * DH;
+  store_tile<G::W, G::O_PITCH>(out, 3 * D, sdo, L, G::kThreads);                      // dQ
+  store_tile<G::W, G::QKV_PITCH>(out + D, 3 * D, sq + G::W, L, G::kThreads);          // dK
+  store_tile<G::W, G::QKV_PITCH>(out + 2 * D, 3 * D, sq + 2 * G::W, L, G::kThreads);  // dV
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("attention_mma: cudaFuncSetAttribute(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+template <int DH, int LP, int HG>
+int launch_fwd(const void* qkv, void* o, int64_t B, int L, int heads, float scale, cudaStream_t st) {
+  using G = Geo<DH, LP, HG>;
+  int rc = set_smem(attn_fwd_mma_kernel<DH, LP, HG>, G::fwd_bytes);
+  if (rc) return rc;
+  attn_fwd_mma_kernel<DH, LP, HG><<<(unsigned)(B * (heads / HG)), G::kThreads, G::fwd_bytes, st>>>((const bf16*)qkv, (bf16*)o, L, heads, scale);
+  return check_launch("attention_fwd_mma");
+}
+template <int DH, int LP, int HG>
+int launch_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int heads, float scale, cudaStream_t st) {
+  using G = Geo<DH, LP, HG>;
+  int rc = set_smem(attn_bwd_mma_kernel<DH, LP, HG>, G::bwd_bytes);
+  if (rc) return rc;
+  attn_bwd_mma_kernel<DH, LP, HG><<<(unsigned)(B * (heads / HG)), G::kThreads, G::bwd_bytes, st>>>((const bf16*)qkv, (const bf16*)dO, (bf16*)dqkv, L, heads,
+                                                                                                    scale);
+  return check_launch("attention_bwd_mma");
+}
+
+}  // namespace attn_mma
+
+// true if the tensor-core path covers this shape
+bool attention_mma_supported(int L, int heads, int dh) {
+  return (dh == 32 || dh == 64) && L >= 1 && L <= 64 && heads % 4 == 0;
+}
+
+#define AFB_ATTN_DISPATCH(FN, ...)                                                              \
+  do {                                                                                          \
+    const int LP = L <= 16 ? 16 : (L <= 32 ? 32 : (L <= 48 ? 48 : 64));                         \
+    const bool hg8 = heads % 8 == 0 && (bwd ? (dh == 32 && LP <= 48) : (dh == 32 || LP <= 32)); \
+    if (dh == 32) {                                                                             \
+      if (hg8) {                                                                                \
+        if (LP == 16) return attn_mma::FN<32, 16, 8>(__VA_ARGS__);                              \
+        if (LP == 32) return attn_mma::FN<32, 32, 8>(__VA_ARGS__);                              \
+        if (LP == 48) return attn_mma::FN<32, 48, 8>(__VA_ARGS__);                              \
+        return attn_mma::FN<32, 64, 8>(__VA_ARGS__);                                            \
+      }                                                                                         \
+      if (LP == 16) return attn_mma::FN<32, 16, 4>(__VA_ARGS__);                                \
+      if (LP == 32) return attn_mma::FN<32, 32, 4>(__VA_ARGS__);                                \
+      if (LP == 48) return attn_mma::FN<32, 48, 4>(__VA_ARGS__);                                \
+      return attn_mma::FN<32, 64, 4>(__VA_ARGS__);                                              \
+    }                                                                                           \
+    if (LP == 16) return attn_mma::FN<64, 16, 4>(__VA_ARGS__);                                  \
+    if (LP == 32) return attn_mma::FN<64, 32, 4>(__VA_ARGS__);                                  \
+    if (LP == 48) return attn_mma::FN<64, 48, 4>(__VA_ARGS__);                                  \
+    return attn_mma::FN<64, 64, 4>(__VA_ARGS__);                                                \
+  } while (0)
+
+int attention_fwd_mma(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st) {
+  const bool bwd = false;
+  AFB_ATTN_DISPATCH(launch_fwd, qkv, o, B, L, heads, scale, st);
+}
+int attention_bwd_mma(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st) {
+  const bool bwd = true;
+  AFB_ATTN_DISPATCH(launch_bwd, qkv, dO, dqkv, B, L, heads, scale, st);
+}
+
+}  // namespace afb

@@ -20,8 +20,10 @@ namespace {
 
 constexpr int BM = 128;       // rows per tile == TMEM lanes
 constexpr int BK = 64;        // bf16 elements per k-block row == 128 bytes == swizzle span
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;      // dW kernel: producer + MMA + 4 epilogue warps
 constexpr int kEpiWarps = 4;
+constexpr int kTnEpiWarps = 8;     // TN kernel: two epilogue warps per TMEM lane quarter
+constexpr int kTnThreads = 64 + 32 * kTnEpiWarps;
 constexpr int kScratchStride = 36;  // floats; 144 B rows keep float4 writes conflict-free
 constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;  // 4 s: a protocol bug traps instead of hanging
 
@@ -59,8 +61,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const unsigned long long t0 = global_ns();
-  while (!mbar_try_wait(bar, parity)) {
-    if (global_ns() - t0 > kWaitTimeoutNs) __trap();
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 1023u) == 0 && global_ns() - t0 > kWaitTimeoutNs) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -134,6 +137,56 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// 32 consecutive elements of one row <-> registers, 16-byte vector accesses (row start 16-byte aligned)
+__device__ __forceinline__ void load32_dyn(const void* base, int64_t idx, int dt, float (&o)[32]) {
+  if (dt == AFB_BF16) {
+    const uint4* ptr = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + idx);
+    uint4 raw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) raw[q] = ptr[q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t w[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[8 * q + 2 * j] = __uint_as_float(w[j] << 16);
+        o[8 * q + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+      }
+    }
+  } else {
+    const float4* ptr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 f = ptr[q];
+      o[4 * q] = f.x; o[4 * q + 1] = f.y; o[4 * q + 2] = f.z; o[4 * q + 3] = f.w;
+    }
+  }
+}
+__device__ __forceinline__ void store32_dyn(void* base, int64_t idx, int dt, const float (&v)[32]) {
+  if (dt == AFB_BF16) {
+    uint4* ptr = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + idx);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      ptr[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+    float4* ptr = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ptr[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+__device__ __forceinline__ void prefetch_row(const void* base, int64_t idx, int dt, int ncols) {
+  const int esz = dt == AFB_BF16 ? 2 : 4;
+  const char* ptr = reinterpret_cast<const char*>(base) + idx * esz;
+  for (int off = 0; off < ncols * esz; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + off));
+}
+
 template <int BN> struct TnCfg {
   static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int kABytes = BM * BK * 2;
@@ -164,7 +217,7 @@ struct TnArgs {
 };
 
 template <int BN, bool B_MN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kTnThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnArgs p) {
   using Cfg = TnCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -196,7 +249,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiWarps);
+      mbar_init(tempty_bar(a), kTnEpiWarps);
     }
     fence_barrier_init();
   }
@@ -265,69 +318,88 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------ epilogue warps ----------------------------------------
-    const int ew = warp - 2;        // scratch slot
-    const int lane_grp = warp & 3;  // TMEM lane quarter this warp may access
-    float* my = scratch + ew * 32 * kScratchStride;
+    // 8 warps: warp w reads TMEM lane quarter (w & 3); the two warps of a quarter split the 32-column
+    // chunks (even / odd).  Thread = one output row: tcgen05.ld hands it 32 consecutive columns, so every
+    // global access is a 16-byte vector on that row (residual / aux / pos in, C / C2 out) and the fused
+    // epilogue costs ~2 instructions per element.  Operand rows are prefetched to L2 while the MMA runs.
+    const int ew = warp - 2;
+    const int lane_grp = warp & 3;
+    const int half = ew >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int sub_row = lane >> 4;        // 0/1: which of the two rows handled per iteration
-    const int cpair = (lane & 15) * 2;    // column pair inside the 32-column chunk
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles;
       const int mt = tile / p.n_tiles;
       const int batch = mt / p.m_tiles_per_batch;
       const int m0 = (mt % p.m_tiles_per_batch) * BM;
+      const int row_local = m0 + lane_grp * 32 + lane;
+      const bool valid = row_local < p.rows_per_batch;
+      const int64_t row = (int64_t)batch * p.rows_per_batch + row_local;
+      const int ncol0 = n_blk * BN;
+      if (valid) {  // warm L2 with this row's epilogue operands while the accumulator is being produced
+        if (p.residual != nullptr) prefetch_row(p.residual, row * p.ldres + ncol0, p.res_dtype, BN);
+        if (p.aux != nullptr) prefetch_row(p.aux, row * p.ldaux + ncol0, p.aux_dtype, BN);
+      }
+      float rscale = 1.f;
+      if (p.row_scale != nullptr && valid) rscale = p.row_scale[row / p.row_scale_div];
+      const float* pos_row = p.pos != nullptr ? p.pos + (int64_t)(row % p.pos_rows) * p.N : nullptr;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row_base_local = m0 + lane_grp * 32;  // row inside the batch
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        float v[32];
+      constexpr int kChunks = BN / 32;
+#pragma unroll 1
+      for (int ch = half; ch < kChunks; ch += 2) {
+        const int n0 = ncol0 + ch * 32;
+        float v[32], t[32];
+        const bool has_res = p.residual != nullptr && valid;
+        if (has_res) load32_dyn(p.residual, row * p.ldres + n0, p.res_dtype, t);  // issued before the TMEM wait
         tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
-        if (ch == BN / 32 - 1) {  // all TMEM reads of this accumulator are done
+        if (ch + 2 >= kChunks) {  // this warp's last TMEM read of the accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
+        if (valid) {
+          if (p.bias != nullptr) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(my + lane * kScratchStride + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        __syncwarp();
-        const int n = n_blk * BN + ch * 32 + cpair;
-        float b0 = 0.f, b1 = 0.f;
-        if (p.bias != nullptr) { b0 = p.bias[n]; b1 = p.bias[n + 1]; }
-#pragma unroll 4
-        for (int it = 0; it < 16; ++it) {
-          const int r = it * 2 + sub_row;
-          const int row_local = row_base_local + r;
-          if (row_local < p.rows_per_batch) {
-            const int64_t row = (int64_t)batch * p.rows_per_batch + row_local;
-            const float2 a = *reinterpret_cast<const float2*>(my + r * kScratchStride + cpair);
-            float v0 = a.x * p.alpha + b0, v1 = a.y * p.alpha + b1;
-            if (p.pos != nullptr) {
-              const float2 pe = *reinterpret_cast<const float2*>(p.pos + (int64_t)(row % p.pos_rows) * p.N + n);
-              v0 += pe.x; v1 += pe.y;
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + q);
+              v[4 * q] = v[4 * q] * p.alpha + b4.x; v[4 * q + 1] = v[4 * q + 1] * p.alpha + b4.y;
+              v[4 * q + 2] = v[4 * q + 2] * p.alpha + b4.z; v[4 * q + 3] = v[4 * q + 3] * p.alpha + b4.w;
             }
-            if (p.act == AFB_ACT_GELU) {
-              if (p.C2 != nullptr) st2_dyn(p.C2, row * p.ldc + n, p.out_dtype, v0, v1);
-              v0 = gelu_f(v0); v1 = gelu_f(v1);
-            } else if (p.act == AFB_ACT_GELU_BWD) {
-              const float2 h = ld2_dyn(p.aux, row * p.ldaux + n, p.aux_dtype);
-              v0 *= gelu_grad_f(h.x); v1 *= gelu_grad_f(h.y);
-            } else if (p.act == AFB_ACT_RELU) {
-              v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);
-            }
-            if (p.row_scale != nullptr) {
-              const float sc = p.row_scale[row / p.row_scale_div];
-              v0 *= sc; v1 *= sc;
-            }
-            if (p.residual != nullptr) {
-              const float2 rr = ld2_dyn(p.residual, row * p.ldres + n, p.res_dtype);
-              v0 += rr.x; v1 += rr.y;
-            }
-            st2_dyn(p.C, row * p.ldc + n, p.out_dtype, v0, v1);
+          } else if (p.alpha != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
           }
+          if (pos_row != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 e4 = __ldg(reinterpret_cast<const float4*>(pos_row + n0) + q);
+              v[4 * q] += e4.x; v[4 * q + 1] += e4.y; v[4 * q + 2] += e4.z; v[4 * q + 3] += e4.w;
+            }
+          }
+          if (p.act == AFB_ACT_GELU) {
+            if (p.C2 != nullptr) store32_dyn(p.C2, row * p.ldc + n0, p.out_dtype, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+          } else if (p.act == AFB_ACT_GELU_BWD) {
+            float h[32];
+            load32_dyn(p.aux, row * p.ldaux + n0, p.aux_dtype, h);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(h[i]);
+          } else if (p.act == AFB_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.row_scale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= rscale;
+          }
+          if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += t[i];
+          }
+          store32_dyn(p.C, row * p.ldc + n0, p.out_dtype, v);
         }
-        __syncwarp();
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -546,7 +618,7 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const TnArgs& a, c
     configured = true;
   }
   const int grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
-  gemm_tn_kernel<BN, B_MN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  gemm_tn_kernel<BN, B_MN><<<grid, kTnThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
   return check_launch("gemm_tn");
 }
 
@@ -576,7 +648,12 @@ extern "C" int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s) {
   AFB_REQUIRE(p && p->A && p->B && p->C, "gemm_tn: null operand");
   AFB_REQUIRE(p->taps >= 1 && p->k_per_tap > 0, "gemm_tn: bad taps/k");
   AFB_REQUIRE(p->N % 64 == 0, "gemm_tn: N=%d must be a multiple of 64", p->N);
-  AFB_REQUIRE(p->lda % 8 == 0 && p->ldb % 8 == 0 && p->ldc % 2 == 0, "gemm_tn: leading dims must be 16-byte aligned");
+  AFB_REQUIRE(p->lda % 8 == 0 && p->ldb % 8 == 0 && p->ldc % 8 == 0, "gemm_tn: leading dims must be 16-byte aligned");
+  AFB_REQUIRE((p->residual == nullptr || p->ldres % 8 == 0) && (p->aux == nullptr || p->ldaux % 8 == 0),
+              "gemm_tn: residual / aux leading dims must be multiples of 8");
+  AFB_REQUIRE(((uintptr_t)p->C & 15) == 0 && ((uintptr_t)p->C2 & 15) == 0 && ((uintptr_t)p->residual & 15) == 0 &&
+                  ((uintptr_t)p->aux & 15) == 0 && ((uintptr_t)p->bias & 15) == 0 && ((uintptr_t)p->pos & 15) == 0,
+              "gemm_tn: epilogue operands must be 16-byte aligned");
   AFB_REQUIRE(p->taps == 1 || p->k_per_tap % BK == 0, "gemm_tn: k_per_tap %% 64 != 0 with taps > 1");
   AFB_REQUIRE(p->k_per_tap % 8 == 0, "gemm_tn: k_per_tap %% 8 != 0");
   AFB_REQUIRE(((uintptr_t)p->A & 15) == 0 && ((uintptr_t)p->B & 15) == 0, "gemm_tn: operands must be 16-byte aligned");

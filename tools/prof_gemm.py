@@ -54,3 +54,20 @@ wconv = mk(128, 9 * 128, s=0.03)
 bench("conv  9x1 128->128", lambda: ops.gemm_tn(x128, wconv, 128, k_per_tap=128, taps=9, tap_row_stride=22, tap_pad=4, rows_per_batch=704,
                                                 batches=M // 704, bias=torch.zeros(128, device=dev)), 2 * M * 128 * 1152, M * 256 * 2)
 print("done")
+
+# attention (cfg2 spatial stage: 8192 sequences of 22 tokens, 8 heads x 32; temporal: 256 x 32 tokens, 8 x 64)
+for (B, L, H, dh) in ((256 * 32, 22, 8, 32), (256, 32, 8, 64)):
+    D = H * dh
+    qkv = mk(B * L, 3 * D)
+    do = mk(B * L, D)
+    fl = 4 * B * H * L * L * dh
+    bench(f"attention fwd B={B} L={L} dh={dh}", lambda: ops.attention_fwd(qkv, B, L, H), fl, B * L * 4 * D * 2)
+    bench(f"attention bwd B={B} L={L} dh={dh}", lambda: ops.attention_bwd(qkv, do, B, L, H), 2.5 * fl, B * L * 7 * D * 2)
+x = mk(M, 256)
+gam, bet = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+bench("layernorm fwd D=256", lambda: ops.layernorm_fwd(x, gam, bet, 1e-6), 0, M * 256 * 4)
+y, mean, rstd = ops.layernorm_fwd(x, gam, bet, 1e-6)
+dg, db = torch.zeros(256, device=dev), torch.zeros(256, device=dev)
+bench("layernorm bwd D=256 (+dres)", lambda: ops.layernorm_bwd(x, x, gam, mean, rstd, dg, db, dres=x), 0, M * 256 * 8)
+bench("colsum 768", lambda: ops.colsum(g768, torch.zeros(768, device=dev)), 0, M * 768 * 2)
+print("done2")
