@@ -98,11 +98,28 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // exact (erf) GELU and its derivative -- nn.GELU default (model_ST.py:17)
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Phi(x) = 0.5 (1 + erf(x / sqrt 2)) via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 on erf): one exp, one
+// reciprocal and five FMAs -- the same exp(-x^2/2) also yields the normal pdf needed by the derivative.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& u) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  u = __expf(-z * z);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float h = 0.5f * poly * t * u;  // 0.5 (1 - erf(z))
+  cdf = x >= 0.f ? 1.0f - h : h;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float cdf, u;
+  gelu_parts(x, cdf, u);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, u;
+  gelu_parts(x, cdf, u);
+  return fmaf(x * 0.3989422804014327f, u, cdf);
 }
 
 }  // namespace afb

@@ -12,6 +12,7 @@
 //   warps 2-5 epilogue      : tcgen05.ld 32 lanes x 32 columns -> smem transpose -> coalesced
 //                             fused epilogue (bias, pos-embed, GELU, DropPath scale, residual)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -187,23 +188,37 @@ __device__ __forceinline__ void prefetch_row(const void* base, int64_t idx, int 
   for (int off = 0; off < ncols * esz; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + off));
 }
 
-template <int BN> struct TnCfg {
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+// TMA store of one staged [32 rows x 128 bytes] box (128B-swizzled smem) into a 3-D tensor (cols, rows, batch)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Shared-memory plan of the TN kernel.  STAT ("B-stationary"): the whole [BN x K] weight panel stays resident
+// (<= 128 KB) and only A tiles stream through the ring -- cuts the L2->SM fill per tile by 3x for the
+// K <= 256/512 linears whose weight panel would otherwise be re-fetched for every 128-row tile.
+template <int BN, bool STAT> struct TnCfg {
+  static constexpr int kStages = STAT ? 4 : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8));
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = BN >= 256 ? 512 : (BN >= 128 ? 256 : (BN >= 64 ? 128 : 64));
-  static constexpr int kScratchBytes = kEpiWarps * 32 * kScratchStride * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kBBytes = BN * BK * 2;                       // one k-block of the B panel
+  static constexpr int kResKBlocks = (128 * 1024) / kBBytes;        // resident k-blocks (STAT)
+  static constexpr int kBRegion = STAT ? 128 * 1024 : kStages * kBBytes;
+  static constexpr int kStageTx = STAT ? kABytes : kABytes + kBBytes;
+  static constexpr int kTmemCols = BN >= 256 ? 512 : (BN >= 128 ? 256 : 128);
+  static constexpr int kStagingBytes = kTnEpiWarps * 4096;          // one 32 x 128 B box per epilogue warp
+  static constexpr int kSmemBytes = kStages * kABytes + kBRegion + kStagingBytes + 256 /*barriers*/ + 1024 /*align*/;
 };
 
 struct TnArgs {
-  int m_tiles_per_batch, n_tiles, total_tiles, k_blocks;
+  int m_tiles_per_batch, n_tiles, total_m_tiles, k_blocks;
   int rows_per_batch, batches, N;
   int kb_per_tap, tap_row_stride, tap_pad;
-  void* C;
-  void* C2;
-  int ldc, out_dtype, act;
+  int out_dtype, act, has_c2;
   float alpha;
   const float* bias;
   const float* pos;
@@ -216,10 +231,44 @@ struct TnArgs {
   int row_scale_div;
 };
 
-template <int BN, bool B_MN>
+// Tile walk of one CTA.  Streaming: tiles blockIdx.x, +grid, ... over (m-tile, n-block) with n fastest, so
+// CTAs working on the same A tile run side by side (A is fetched from HBM once, then hits L2).  Stationary:
+// the CTA keeps n-block (blockIdx.x % n_tiles) and walks m-tiles with stride grid / n_tiles.
+template <bool STAT>
+struct TileWalk {
+  int n_blk, mt, mt_stride, mt_end, n_tiles, lin, lin_stride, lin_end;
+  __device__ __forceinline__ TileWalk(const TnArgs& p) {
+    n_tiles = p.n_tiles;
+    if (STAT) {
+      n_blk = blockIdx.x % p.n_tiles;
+      mt = blockIdx.x / p.n_tiles;
+      mt_stride = gridDim.x / p.n_tiles;
+      mt_end = p.total_m_tiles;
+    } else {
+      lin = blockIdx.x;
+      lin_stride = gridDim.x;
+      lin_end = p.total_m_tiles * p.n_tiles;
+      n_blk = lin % n_tiles;
+      mt = lin / n_tiles;
+    }
+  }
+  __device__ __forceinline__ bool valid() const { return STAT ? mt < mt_end : lin < lin_end; }
+  __device__ __forceinline__ void next() {
+    if (STAT) {
+      mt += mt_stride;
+    } else {
+      lin += lin_stride;
+      n_blk = lin % n_tiles;
+      mt = lin / n_tiles;
+    }
+  }
+};
+
+template <int BN, bool B_MN, bool STAT>
 __global__ void __launch_bounds__(kTnThreads, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnArgs p) {
-  using Cfg = TnCfg<BN>;
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmC2, const TnArgs p) {
+  using Cfg = TnCfg<BN, STAT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
@@ -227,15 +276,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const uint32_t sA = base;
   const uint32_t sB = base + Cfg::kStages * Cfg::kABytes;
-  float* scratch = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  const uint32_t bar0 = base + Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes;
+  const uint32_t sStage = sB + Cfg::kBRegion;
+  constexpr uint32_t kBarOff = Cfg::kStages * Cfg::kABytes + Cfg::kBRegion + Cfg::kStagingBytes;
+  const uint32_t bar0 = base + kBarOff;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * Cfg::kStages + 2 + a); };
-  const uint32_t tmem_slot = bar0 + 8u * (2 * Cfg::kStages + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes + 8 * (2 * Cfg::kStages + 4));
+  const uint32_t bres_bar = bar0 + 8u * (2 * Cfg::kStages + 4);
+  const uint32_t tmem_slot = bar0 + 8u * (2 * Cfg::kStages + 5);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + kBarOff + 8 * (2 * Cfg::kStages + 5));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -243,6 +293,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -251,6 +302,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kTnEpiWarps);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -262,25 +314,38 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------------------
     if (lane == 0) {
+      TileWalk<STAT> w(p);
+      if (STAT && w.valid()) {  // the weight panel of this CTA's n-block, once
+        mbar_expect_tx(bres_bar, (uint32_t)p.k_blocks * Cfg::kBBytes);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          if (!B_MN) {
+            tma_load_2d(&tmB, bres_bar, sB + kb * Cfg::kBBytes, kb * BK, w.n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(&tmB, bres_bar, sB + kb * Cfg::kBBytes + j * (64 * 128), w.n_blk * BN + j * 64, kb * BK);
+          }
+        }
+      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_blk = tile % p.n_tiles;
-        const int mt = tile / p.n_tiles;
-        const int batch = mt / p.m_tiles_per_batch;
-        const int m0 = (mt % p.m_tiles_per_batch) * BM;
+      for (; w.valid(); w.next()) {
+        const int batch = w.mt / p.m_tiles_per_batch;
+        const int m0 = (w.mt % p.m_tiles_per_batch) * BM;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          mbar_expect_tx(full_bar(stage), Cfg::kStageTx);
           const int tap = kb / p.kb_per_tap;
           const int kc = (kb - tap * p.kb_per_tap) * BK;
           tma_load_3d(&tmA, full_bar(stage), sA + stage * Cfg::kABytes, kc, m0 + (tap - p.tap_pad) * p.tap_row_stride, batch);
-          if (!B_MN) {
-            tma_load_2d(&tmB, full_bar(stage), sB + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
-          } else {
+          if (!STAT) {
+            if (!B_MN) {
+              tma_load_2d(&tmB, full_bar(stage), sB + stage * Cfg::kBBytes, kb * BK, w.n_blk * BN);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)  // 64(k) x 64(n) boxes, N contiguous
-              tma_load_2d(&tmB, full_bar(stage), sB + stage * Cfg::kBBytes + j * (64 * 128), n_blk * BN + j * 64, kb * BK);
+              for (int j = 0; j < BN / 64; ++j)  // 64(k) x 64(n) boxes, N contiguous
+                tma_load_2d(&tmB, full_bar(stage), sB + stage * Cfg::kBBytes + j * (64 * 128), w.n_blk * BN + j * 64, kb * BK);
+            }
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
@@ -294,7 +359,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      TileWalk<STAT> w(p);
+      if (STAT && w.valid()) mbar_wait(bres_bar, 0);
+      for (; w.valid(); w.next()) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -302,7 +369,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = sA + stage * Cfg::kABytes;
-          const uint32_t b_addr = sB + stage * Cfg::kBBytes;
+          const uint32_t b_addr = sB + (STAT ? kb : stage) * Cfg::kBBytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = make_desc(a_addr + k * 32, 16, 1024);
@@ -318,24 +385,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------ epilogue warps ----------------------------------------
-    // 8 warps: warp w reads TMEM lane quarter (w & 3); the two warps of a quarter split the 32-column
-    // chunks (even / odd).  Thread = one output row: tcgen05.ld hands it 32 consecutive columns, so every
-    // global access is a 16-byte vector on that row (residual / aux / pos in, C / C2 out) and the fused
-    // epilogue costs ~2 instructions per element.  Operand rows are prefetched to L2 while the MMA runs.
+    // 8 warps: warp w reads TMEM lane quarter (w & 3); the two warps of a quarter alternate over 128-byte
+    // output units (64 bf16 / 32 fp32 columns).  Thread = one output row: tcgen05.ld hands it 32 consecutive
+    // columns, residual / aux / pos come in as 16-byte vectors of that row (prefetched to L2 while the MMA
+    // runs), and the finished unit is staged in 128B-swizzled shared memory and written with one TMA store
+    // (full, coalesced lines; rows beyond the batch are clipped by the tensor map).
     const int ew = warp - 2;
     const int lane_grp = warp & 3;
     const int half = ew >> 2;
+    const uint32_t my_stage = sStage + ew * 4096;
+    uint8_t* my_stage_ptr = smem + Cfg::kStages * Cfg::kABytes + Cfg::kBRegion + ew * 4096;
+    const bool out_bf16 = p.out_dtype == AFB_BF16;
+    const int ncl = out_bf16 ? 2 : 1;          // tcgen05.ld chunks per 128-byte staging row
+    const int units = BN / (32 * ncl);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_blk = tile % p.n_tiles;
-      const int mt = tile / p.n_tiles;
-      const int batch = mt / p.m_tiles_per_batch;
-      const int m0 = (mt % p.m_tiles_per_batch) * BM;
-      const int row_local = m0 + lane_grp * 32 + lane;
+    for (TileWalk<STAT> w(p); w.valid(); w.next()) {
+      const int batch = w.mt / p.m_tiles_per_batch;
+      const int m0 = (w.mt % p.m_tiles_per_batch) * BM;
+      const int row_in_batch0 = m0 + lane_grp * 32;
+      const int row_local = row_in_batch0 + lane;
       const bool valid = row_local < p.rows_per_batch;
       const int64_t row = (int64_t)batch * p.rows_per_batch + row_local;
-      const int ncol0 = n_blk * BN;
+      const int ncol0 = w.n_blk * BN;
       if (valid) {  // warm L2 with this row's epilogue operands while the accumulator is being produced
         if (p.residual != nullptr) prefetch_row(p.residual, row * p.ldres + ncol0, p.res_dtype, BN);
         if (p.aux != nullptr) prefetch_row(p.aux, row * p.ldaux + ncol0, p.aux_dtype, BN);
@@ -345,64 +417,114 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float* pos_row = p.pos != nullptr ? p.pos + (int64_t)(row % p.pos_rows) * p.N : nullptr;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      constexpr int kChunks = BN / 32;
+      bool arrived = false;
 #pragma unroll 1
-      for (int ch = half; ch < kChunks; ch += 2) {
-        const int n0 = ncol0 + ch * 32;
-        float v[32], t[32];
-        const bool has_res = p.residual != nullptr && valid;
-        if (has_res) load32_dyn(p.residual, row * p.ldres + n0, p.res_dtype, t);  // issued before the TMEM wait
-        tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
-        if (ch + 2 >= kChunks) {  // this warp's last TMEM read of the accumulator
-          tc_fence_before();
+      for (int u = half; u < units; u += 2) {
+#pragma unroll 1
+        for (int pass = 0; pass < (p.has_c2 ? 2 : 1); ++pass) {   // pass 0 of a GELU+preact GEMM stores the pre-activation
+#pragma unroll 1
+          for (int c = 0; c < ncl; ++c) {
+            const int ch = u * ncl + c;
+            const int n0 = ncol0 + ch * 32;
+            float v[32], t[32];
+            const bool has_res = p.residual != nullptr && valid;
+            if (has_res) load32_dyn(p.residual, row * p.ldres + n0, p.res_dtype, t);  // issued before the TMEM wait
+            float4 bq[8];
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) bq[q] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + q);
+            }
+            tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
+            const bool last_pass = pass == (p.has_c2 ? 1 : 0);
+            if (last_pass && u + 2 >= units && c == ncl - 1) {  // this warp's last TMEM read of the accumulator
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty_bar(acc));
+              arrived = true;
+            }
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 b4 = bq[q];
+                v[4 * q] = v[4 * q] * p.alpha + b4.x; v[4 * q + 1] = v[4 * q + 1] * p.alpha + b4.y;
+                v[4 * q + 2] = v[4 * q + 2] * p.alpha + b4.z; v[4 * q + 3] = v[4 * q + 3] * p.alpha + b4.w;
+              }
+            } else if (p.alpha != 1.f) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+            }
+            if (pos_row != nullptr && valid) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 e4 = __ldg(reinterpret_cast<const float4*>(pos_row + n0) + q);
+                v[4 * q] += e4.x; v[4 * q + 1] += e4.y; v[4 * q + 2] += e4.z; v[4 * q + 3] += e4.w;
+              }
+            }
+            if (last_pass) {
+              if (p.act == AFB_ACT_GELU) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+              } else if (p.act == AFB_ACT_GELU_BWD) {
+                if (valid) {
+                  float h[32];
+                  load32_dyn(p.aux, row * p.ldaux + n0, p.aux_dtype, h);
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(h[i]);
+                }
+              } else if (p.act == AFB_ACT_RELU) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+              }
+              if (p.row_scale != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= rscale;
+              }
+              if (has_res) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += t[i];
+              }
+            }
+            // stage: row = lane, 128-byte rows, 16-byte chunk index XOR (row & 7)  (SWIZZLE_128B)
+            uint8_t* rowp = my_stage_ptr + lane * 128;
+            if (out_bf16) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t wv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]);
+                  wv[j] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                const int chunk = (c * 4 + q) ^ (lane & 7);
+                *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int chunk = q ^ (lane & 7);
+                *reinterpret_cast<float4*>(rowp + chunk * 16) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              }
+            }
+          }
+          fence_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            const int col = ncol0 + u * 32 * ncl;
+            tma_store_3d((p.has_c2 && pass == 0) ? &tmC2 : &tmC, my_stage, col, row_in_batch0, batch);
+            bulk_commit();
+            bulk_wait_read0();
+          }
+          __syncwarp();
         }
-        if (valid) {
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + q);
-              v[4 * q] = v[4 * q] * p.alpha + b4.x; v[4 * q + 1] = v[4 * q + 1] * p.alpha + b4.y;
-              v[4 * q + 2] = v[4 * q + 2] * p.alpha + b4.z; v[4 * q + 3] = v[4 * q + 3] * p.alpha + b4.w;
-            }
-          } else if (p.alpha != 1.f) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
-          }
-          if (pos_row != nullptr) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 e4 = __ldg(reinterpret_cast<const float4*>(pos_row + n0) + q);
-              v[4 * q] += e4.x; v[4 * q + 1] += e4.y; v[4 * q + 2] += e4.z; v[4 * q + 3] += e4.w;
-            }
-          }
-          if (p.act == AFB_ACT_GELU) {
-            if (p.C2 != nullptr) store32_dyn(p.C2, row * p.ldc + n0, p.out_dtype, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
-          } else if (p.act == AFB_ACT_GELU_BWD) {
-            float h[32];
-            load32_dyn(p.aux, row * p.ldaux + n0, p.aux_dtype, h);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(h[i]);
-          } else if (p.act == AFB_ACT_RELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (p.row_scale != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= rscale;
-          }
-          if (has_res) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += t[i];
-          }
-          store32_dyn(p.C, row * p.ldc + n0, p.out_dtype, v);
-        }
+      }
+      if (!arrived) {  // BN == 64 with bf16 output: the odd warps of each quarter have no unit in this tile
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) bulk_wait0();
   }
 
   tc_fence_before();
@@ -570,19 +692,20 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 tensor [d2][d1][d0] (d0 contiguous), strides in elements; 128B swizzle; OOB reads give zero.
+// tensor [d2][d1][d0] (d0 contiguous), strides in elements; 128B swizzle; OOB reads give zero, OOB writes are clipped.
 int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
-             uint32_t box0, uint32_t box1, int rank) {
+             uint32_t box0, uint32_t box1, int rank, int dtype = AFB_BF16) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled unavailable (driver too old?)");
     return AFB_ERR_DRIVER;
   }
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};
+  const uint64_t esz = dtype == AFB_BF16 ? 2 : 4;
+  cuuint64_t strides[2] = {stride1 * esz, stride2 * esz};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, dtype == AFB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -605,21 +728,36 @@ int num_sms() {
   return n;
 }
 
-template <int BN, bool B_MN>
-int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const TnArgs& a, cudaStream_t st) {
-  using Cfg = TnCfg<BN>;
+template <int BN, bool B_MN, bool STAT>
+int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2, const TnArgs& a,
+              cudaStream_t st) {
+  using Cfg = TnCfg<BN, STAT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN, B_MN, STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("gemm_tn: cudaFuncSetAttribute(%d B) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return (int)e;
     }
     configured = true;
   }
-  const int grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
-  gemm_tn_kernel<BN, B_MN><<<grid, kTnThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  int grid;
+  if (STAT) {
+    grid = (num_sms() / a.n_tiles) * a.n_tiles;
+    const int max_useful = a.total_m_tiles * a.n_tiles;
+    if (grid > max_useful) grid = max_useful;
+  } else {
+    const int tiles = a.total_m_tiles * a.n_tiles;
+    grid = tiles < num_sms() ? tiles : num_sms();
+  }
+  gemm_tn_kernel<BN, B_MN, STAT><<<grid, kTnThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmC, tmC2, a);
   return check_launch("gemm_tn");
+}
+
+template <int BN, bool B_MN>
+int launch_tn_stat(bool stat, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+                   const TnArgs& a, cudaStream_t st) {
+  return stat ? launch_tn<BN, B_MN, true>(tmA, tmB, tmC, tmC2, a, st) : launch_tn<BN, B_MN, false>(tmA, tmB, tmC, tmC2, a, st);
 }
 
 template <int BN2>
@@ -659,27 +797,43 @@ extern "C" int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s) {
   AFB_REQUIRE(((uintptr_t)p->A & 15) == 0 && ((uintptr_t)p->B & 15) == 0, "gemm_tn: operands must be 16-byte aligned");
   AFB_REQUIRE(p->rows_per_batch > 0 && p->batches > 0, "gemm_tn: empty problem");
 
-  const int BN = (p->N % 256 == 0) ? 256 : (p->N % 128 == 0 ? 128 : 64);
   const int K = p->taps * p->k_per_tap;
+  const int kb_per_tap = ceil_div(p->k_per_tap, BK);
+  const int k_blocks = kb_per_tap * p->taps;
+  // Tile width and mode.  B-stationary when the whole [BN x K] weight panel fits 128 KB of shared memory
+  // (K <= 256 at BN 256, <= 512 at BN 128, <= 1024 at BN 64) and there are enough CTAs per n-block.
+  int BN = (p->N % 256 == 0) ? 256 : (p->N % 128 == 0 ? 128 : 64);
+  bool stat = false;
+  static const bool no_stat = getenv("AFB_GEMM_NO_STAT") != nullptr;
+  if (!no_stat) {
+    for (int bn = BN; bn >= 64; bn >>= 1) {
+      if (p->N % bn == 0 && k_blocks * bn * 128 <= 128 * 1024 && p->N / bn <= num_sms()) {
+        BN = bn;
+        stat = true;
+        break;
+      }
+    }
+  }
   TnArgs a;
   a.m_tiles_per_batch = ceil_div(p->rows_per_batch, BM);
   a.n_tiles = p->N / BN;
-  a.total_tiles = a.m_tiles_per_batch * p->batches * a.n_tiles;
-  a.kb_per_tap = ceil_div(p->k_per_tap, BK);
-  a.k_blocks = a.kb_per_tap * p->taps;
+  a.total_m_tiles = a.m_tiles_per_batch * p->batches;
+  a.kb_per_tap = kb_per_tap;
+  a.k_blocks = k_blocks;
   a.rows_per_batch = (int)p->rows_per_batch;
   a.batches = p->batches;
   a.N = p->N;
   a.tap_row_stride = p->tap_row_stride;
   a.tap_pad = p->tap_pad;
-  a.C = p->C; a.C2 = p->C2; a.ldc = p->ldc; a.out_dtype = p->out_dtype; a.act = p->act; a.alpha = p->alpha;
+  a.out_dtype = p->out_dtype; a.act = p->act; a.alpha = p->alpha;
+  a.has_c2 = (p->C2 != nullptr && p->act == AFB_ACT_GELU) ? 1 : 0;
   a.bias = p->bias; a.pos = p->pos; a.pos_rows = p->pos_rows > 0 ? p->pos_rows : 1;
   a.aux = p->aux; a.aux_dtype = p->aux_dtype; a.ldaux = p->ldaux;
   a.residual = p->residual; a.res_dtype = p->res_dtype; a.ldres = p->ldres;
   a.row_scale = p->row_scale; a.row_scale_div = p->row_scale_div > 0 ? p->row_scale_div : 1;
   AFB_REQUIRE(p->act != AFB_ACT_GELU_BWD || p->aux != nullptr, "gemm_tn: GELU_BWD needs aux");
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmC2;
   int rc = make_map(&tmA, p->A, (uint64_t)p->k_per_tap, (uint64_t)p->rows_per_batch, (uint64_t)p->batches, (uint64_t)p->lda,
                     (uint64_t)p->rows_per_batch * p->lda, BK, BM, 3);
   if (rc) return rc;
@@ -688,15 +842,22 @@ extern "C" int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s) {
   else
     rc = make_map(&tmB, p->B, (uint64_t)p->N, (uint64_t)K, 1, (uint64_t)p->ldb, 0, 64, 64, 2);
   if (rc) return rc;
+  const uint32_t out_box = p->out_dtype == AFB_BF16 ? 64 : 32;  // 128 bytes of columns x 32 rows per TMA store
+  rc = make_map(&tmC, p->C, (uint64_t)p->N, (uint64_t)p->rows_per_batch, (uint64_t)p->batches, (uint64_t)p->ldc,
+                (uint64_t)p->rows_per_batch * p->ldc, out_box, 32, 3, p->out_dtype);
+  if (rc) return rc;
+  rc = make_map(&tmC2, a.has_c2 ? p->C2 : p->C, (uint64_t)p->N, (uint64_t)p->rows_per_batch, (uint64_t)p->batches, (uint64_t)p->ldc,
+                (uint64_t)p->rows_per_batch * p->ldc, out_box, 32, 3, p->out_dtype);
+  if (rc) return rc;
   cudaStream_t st = as_stream(s);
   if (!p->b_mn_major) {
-    if (BN == 256) return launch_tn<256, false>(tmA, tmB, a, st);
-    if (BN == 128) return launch_tn<128, false>(tmA, tmB, a, st);
-    return launch_tn<64, false>(tmA, tmB, a, st);
+    if (BN == 256) return launch_tn_stat<256, false>(stat, tmA, tmB, tmC, tmC2, a, st);
+    if (BN == 128) return launch_tn_stat<128, false>(stat, tmA, tmB, tmC, tmC2, a, st);
+    return launch_tn_stat<64, false>(stat, tmA, tmB, tmC, tmC2, a, st);
   }
-  if (BN == 256) return launch_tn<256, true>(tmA, tmB, a, st);
-  if (BN == 128) return launch_tn<128, true>(tmA, tmB, a, st);
-  return launch_tn<64, true>(tmA, tmB, a, st);
+  if (BN == 256) return launch_tn_stat<256, true>(stat, tmA, tmB, tmC, tmC2, a, st);
+  if (BN == 128) return launch_tn_stat<128, true>(stat, tmA, tmB, tmC, tmC2, a, st);
+  return launch_tn_stat<64, true>(stat, tmA, tmB, tmC, tmC2, a, st);
 }
 
 extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
