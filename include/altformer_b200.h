@@ -240,7 +240,9 @@ typedef struct {
   int32_t training;
   float momentum, eps;
   float* Mmat;         /* out [N][3][V][V]: softmax_u(S_i) + A_i + PA_i (saved for backward) */
-  float* moments;      /* workspace [N][AFB_GCN0_NMOM] per-sample partial moments of r */
+  double* moments;     /* persistent workspace [AFB_GCN0_SLOTS][AFB_GCN0_NMOM], ZERO before the first call; the
+                          kernel re-zeroes it, so one buffer serves every launch on a stream */
+  int32_t* counter;    /* persistent, zero-initialised CTA ticket (re-armed by the kernel) */
   float* stats;        /* out [AFB_GCN0_NSTAT_BASE + 4*Cout]: E[r] (12), Cov(r) (144), mean_h, rstd_h, mean_d, rstd_d */
   float* Wfold;        /* out [Cout][16]: BN-folded weights of the apply pass */
   void* y;             /* out [N*T*V][Cout] */
@@ -249,6 +251,7 @@ typedef struct {
 } afb_gcn0_fwd_t;
 #define AFB_GCN0_NR 12          /* r = (z_0, z_1, z_2, x): 9 + 3 */
 #define AFB_GCN0_NMOM 96        /* 12 first + 78 second moments (upper triangle), padded */
+#define AFB_GCN0_SLOTS 32       /* fp64 accumulation slots */
 #define AFB_GCN0_NSTAT_BASE 160 /* 12 + 144, padded */
 int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s);
 

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libaltformer_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_RELU = 0, 1, 2, 3
-GCN0_NMOM, GCN0_NSTAT_BASE = 96, 160
+GCN0_NMOM, GCN0_NSTAT_BASE, GCN0_SLOTS = 96, 160, 32
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -40,7 +40,7 @@ class Gcn0Fwd(C.Structure):
                 ("Wd", vp * 3), ("bd", vp * 3), ("Wdn", vp), ("bdn", vp), ("bn_g", vp), ("bn_b", vp), ("dn_g", vp),
                 ("dn_b", vp), ("bn_rm", vp), ("bn_rv", vp), ("dn_rm", vp), ("dn_rv", vp), ("N", i32), ("T", i32),
                 ("V", i32), ("Cout", i32), ("IC", i32), ("training", i32), ("momentum", f32), ("eps", f32),
-                ("Mmat", vp), ("moments", vp), ("stats", vp), ("Wfold", vp), ("y", vp), ("y_dtype", i32),
+                ("Mmat", vp), ("moments", vp), ("counter", vp), ("stats", vp), ("Wfold", vp), ("y", vp), ("y_dtype", i32),
                 ("precise", i32)]
 
 

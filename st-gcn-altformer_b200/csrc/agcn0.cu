@@ -86,15 +86,90 @@ __device__ __forceinline__ void position_r(const float* xs, const float* Ms, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward 1: mixing matrices + per-sample moments
+// forward 1: mixing matrices, moments of r, and (last CTA) statistics + folded weights
 // ---------------------------------------------------------------------------------------------
+constexpr int kSlots = AFB_GCN0_SLOTS;   // fp64 accumulation slots (spreads atomic contention)
+constexpr int kPosChunk = 704;           // positions staged per moment pass (33 KB of r vectors)
+
+// E[r], Cov(r) -> batch statistics of both BatchNorms -> BN-folded weights.  Runs in the last CTA to finish.
+__device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm /* >= 96 + 12 + 144 doubles */) {
+  double* tot = dsm;
+  double* E = dsm + NMOM;
+  double* Cov = E + NR;   // [NR][NR]
+  const int tid = threadIdx.x;
+  for (int j = tid; j < NMOM; j += blockDim.x) {
+    double s = 0.0;
+    for (int l = 0; l < kSlots; ++l) s += __ldcg(p.moments + l * NMOM + j);
+    tot[j] = s;
+  }
+  __syncthreads();
+  const double m = (double)p.N * p.T * p.V;
+  if (tid < NR) E[tid] = tot[tid] / m;
+  __syncthreads();
+  for (int e = tid; e < NR * NR; e += blockDim.x) {
+    const int j = e / NR, k = e % NR;
+    const int a = j < k ? j : k, b = j < k ? k : j;
+    Cov[e] = tot[tri(a, b)] / m - E[j] * E[k];
+  }
+  __syncthreads();
+  if (tid < NR) p.stats[tid] = (float)E[tid];
+  for (int e = tid; e < NR * NR; e += blockDim.x) p.stats[NR + e] = (float)Cov[e];
+  for (int o = tid; o < p.Cout; o += blockDim.x) {
+    double w[NR];
+    double b = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      for (int a = 0; a < 3; ++a) w[i * 3 + a] = p.Wd[i][o * 3 + a];
+      b += p.bd[i][o];
+    }
+    for (int a = 0; a < 3; ++a) w[9 + a] = p.Wdn[o * 3 + a];
+    double mean_h = b, mean_d = p.bdn[o], var_h = 0.0, var_d = 0.0;
+    for (int j = 0; j < 9; ++j) {
+      mean_h += w[j] * E[j];
+      for (int k = 0; k < 9; ++k) var_h += w[j] * Cov[j * NR + k] * w[k];
+    }
+    for (int j = 9; j < 12; ++j) {
+      mean_d += w[j] * E[j];
+      for (int k = 9; k < 12; ++k) var_d += w[j] * Cov[j * NR + k] * w[k];
+    }
+    if (var_h < 0.0) var_h = 0.0;
+    if (var_d < 0.0) var_d = 0.0;
+    const double ctr_h = mean_h, ctr_d = mean_d;  // pre-BN activations at the batch centre E[r]
+    if (p.training) {
+      const double unb = m > 1.0 ? m / (m - 1.0) : 1.0;
+      p.bn_rm[o] = (float)((1.0 - p.momentum) * p.bn_rm[o] + p.momentum * mean_h);
+      p.bn_rv[o] = (float)((1.0 - p.momentum) * p.bn_rv[o] + p.momentum * var_h * unb);
+      p.dn_rm[o] = (float)((1.0 - p.momentum) * p.dn_rm[o] + p.momentum * mean_d);
+      p.dn_rv[o] = (float)((1.0 - p.momentum) * p.dn_rv[o] + p.momentum * var_d * unb);
+    } else {
+      mean_h = p.bn_rm[o]; var_h = p.bn_rv[o];
+      mean_d = p.dn_rm[o]; var_d = p.dn_rv[o];
+    }
+    const double rstd_h = 1.0 / sqrt(var_h + (double)p.eps), rstd_d = 1.0 / sqrt(var_d + (double)p.eps);
+    const double sh = p.bn_g[o] * rstd_h, sd = p.dn_g[o] * rstd_d;
+    float* wf = p.Wfold + o * 16;
+    for (int j = 0; j < 9; ++j) wf[j] = (float)(sh * w[j]);
+    for (int j = 9; j < 12; ++j) wf[j] = (float)(sd * w[j]);
+    wf[12] = (float)(sh * (ctr_h - mean_h) + p.bn_b[o] + sd * (ctr_d - mean_d) + p.dn_b[o]);
+    wf[13] = wf[14] = wf[15] = 0.f;
+    p.stats[NSTAT + o] = (float)mean_h;
+    p.stats[NSTAT + p.Cout + o] = (float)rstd_h;
+    p.stats[NSTAT + 2 * p.Cout + o] = (float)mean_d;
+    p.stats[NSTAT + 3 * p.Cout + o] = (float)rstd_d;
+  }
+  __syncthreads();
+  for (int j = tid; j < kSlots * NMOM; j += blockDim.x) p.moments[j] = 0.0;  // re-arm for the next launch
+  if (tid == 0) *p.counter = 0;
+}
+
 __global__ void __launch_bounds__(kThreads) gcn0_scores_kernel(const afb_gcn0_fwd_t p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int T = p.T, V = p.V, n = blockIdx.x;
-  float* xs = sm;                    // [T*V*3]
-  float* Ms = xs + T * V * 3;        // [3][V][V]
-  float* red = Ms + 3 * V * V;       // [8][NMOM]
+  float* xs = sm;                        // [T*V*3]
+  float* Ms = xs + a4(T * V * 3);        // [3][V][V]
+  float* rs = Ms + a4(3 * V * V);        // [kPosChunk][12]   r vectors of one chunk of positions
+  float* part = rs + kPosChunk * NR;     // [2][NMOM]
   __shared__ float coef[3][16];
+  __shared__ int is_last;
   const float* xg = p.x + (int64_t)n * T * V * 3;
   for (int i = threadIdx.x; i < T * V * 3; i += blockDim.x) xs[i] = xg[i];
   compute_coef(p, coef);
@@ -130,108 +205,56 @@ __global__ void __launch_bounds__(kThreads) gcn0_scores_kernel(const afb_gcn0_fw
     }
   }
   __syncthreads();
-  float acc[NMOM - 6];  // 90 used
-#pragma unroll
-  for (int j = 0; j < 90; ++j) acc[j] = 0.f;
-  for (int pos = threadIdx.x; pos < T * V; pos += blockDim.x) {
-    float r[NR];
-    position_r(xs, Ms, V, pos / V, pos % V, r);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-      acc[j] += r[j];
-#pragma unroll
-      for (int k = j; k < NR; ++k) acc[tri(j, k)] += r[j] * r[k];
+  // moments: thread (j, seg) owns moment j (12 first + 78 second) over every other position -- no shuffles
+  const int mj = threadIdx.x % 90, seg = threadIdx.x / 90;
+  int pa = 0, pb = 0;
+  if (mj >= NR) {
+    int rem = mj - NR;
+    pa = 0;
+    while (rem >= NR - pa) { rem -= NR - pa; ++pa; }
+    pb = pa + rem;
+  }
+  float macc = 0.f;
+  for (int c0 = 0; c0 < T * V; c0 += kPosChunk) {
+    const int np = min(kPosChunk, T * V - c0);
+    for (int it = threadIdx.x; it < np * 4; it += blockDim.x) {  // r vectors of this chunk: (position, subset | x)
+      const int pl = it >> 2, i = it & 3, pos = c0 + pl;
+      const int t = pos / V, v = pos % V;
+      const float* xt = xs + t * V * 3;
+      float* dst = rs + pl * NR;
+      if (i < 3) {
+        float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+        for (int u = 0; u < V; ++u) {
+          const float m = Ms[(i * V + u) * V + v];
+          z0 += xt[u * 3] * m; z1 += xt[u * 3 + 1] * m; z2 += xt[u * 3 + 2] * m;
+        }
+        dst[i * 3] = z0; dst[i * 3 + 1] = z1; dst[i * 3 + 2] = z2;
+      } else {
+        dst[9] = xt[v * 3]; dst[10] = xt[v * 3 + 1]; dst[11] = xt[v * 3 + 2];
+      }
     }
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int j = 0; j < 90; ++j) {
-    const float s = warp_sum(acc[j]);
-    if (lane == 0) red[warp * NMOM + j] = s;
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < NMOM; j += blockDim.x) {
-    float s = 0.f;
-    if (j < 90)
-      for (int w = 0; w < kThreads / 32; ++w) s += red[w * NMOM + j];
-    p.moments[(int64_t)n * NMOM + j] = s;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// forward 2: statistics + folded weights (single CTA)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) gcn0_finalize_kernel(const afb_gcn0_fwd_t p) {
-  __shared__ double dred[10][NMOM];
-  __shared__ double E[NR];
-  __shared__ double Cov[NR][NR];
-  const int tid = threadIdx.x;
-  const int col = tid % NMOM, rl = tid / NMOM;
-  if (rl < 10) {
-    double s = 0.0;
-    for (int n = rl; n < p.N; n += 10) s += (double)p.moments[(int64_t)n * NMOM + col];
-    dred[rl][col] = s;
-  }
-  __syncthreads();
-  if (tid < NMOM) {
-    double s = 0.0;
-    for (int l = 0; l < 10; ++l) s += dred[l][tid];
-    dred[0][tid] = s;
-  }
-  __syncthreads();
-  const double m = (double)p.N * p.T * p.V;
-  if (tid < NR) E[tid] = dred[0][tid] / m;
-  __syncthreads();
-  if (tid < NR * NR) {
-    const int j = tid / NR, k = tid % NR;
-    const int a = j < k ? j : k, b = j < k ? k : j;
-    Cov[j][k] = dred[0][tri(a, b)] / m - E[j] * E[k];
-  }
-  __syncthreads();
-  if (tid < NR) p.stats[tid] = (float)E[tid];
-  if (tid < NR * NR) p.stats[NR + tid] = (float)Cov[tid / NR][tid % NR];
-  for (int o = tid; o < p.Cout; o += blockDim.x) {
-    double w[NR];
-    double b = 0.0;
-    for (int i = 0; i < 3; ++i) {
-      for (int a = 0; a < 3; ++a) w[i * 3 + a] = p.Wd[i][o * 3 + a];
-      b += p.bd[i][o];
+    __syncthreads();
+    if (seg < 2) {
+      if (mj < NR) {
+        for (int pl = seg; pl < np; pl += 2) macc += rs[pl * NR + mj];
+      } else {
+        for (int pl = seg; pl < np; pl += 2) macc += rs[pl * NR + pa] * rs[pl * NR + pb];
+      }
     }
-    for (int a = 0; a < 3; ++a) w[9 + a] = p.Wdn[o * 3 + a];
-    double mean_h = b, mean_d = p.bdn[o], var_h = 0.0, var_d = 0.0;
-    for (int j = 0; j < 9; ++j) {
-      mean_h += w[j] * E[j];
-      for (int k = 0; k < 9; ++k) var_h += w[j] * Cov[j][k] * w[k];
-    }
-    for (int j = 9; j < 12; ++j) {
-      mean_d += w[j] * E[j];
-      for (int k = 9; k < 12; ++k) var_d += w[j] * Cov[j][k] * w[k];
-    }
-    if (var_h < 0.0) var_h = 0.0;
-    if (var_d < 0.0) var_d = 0.0;
-    // mean of the pre-BN activations at the batch centre (used to fold the constant term)
-    const double ctr_h = mean_h, ctr_d = mean_d;
-    if (p.training) {
-      const double unb = m > 1.0 ? m / (m - 1.0) : 1.0;
-      p.bn_rm[o] = (float)((1.0 - p.momentum) * p.bn_rm[o] + p.momentum * mean_h);
-      p.bn_rv[o] = (float)((1.0 - p.momentum) * p.bn_rv[o] + p.momentum * var_h * unb);
-      p.dn_rm[o] = (float)((1.0 - p.momentum) * p.dn_rm[o] + p.momentum * mean_d);
-      p.dn_rv[o] = (float)((1.0 - p.momentum) * p.dn_rv[o] + p.momentum * var_d * unb);
-    } else {
-      mean_h = p.bn_rm[o]; var_h = p.bn_rv[o];
-      mean_d = p.dn_rm[o]; var_d = p.dn_rv[o];
-    }
-    const double rstd_h = 1.0 / sqrt(var_h + (double)p.eps), rstd_d = 1.0 / sqrt(var_d + (double)p.eps);
-    const double sh = p.bn_g[o] * rstd_h, sd = p.dn_g[o] * rstd_d;
-    float* wf = p.Wfold + o * 16;
-    for (int j = 0; j < 9; ++j) wf[j] = (float)(sh * w[j]);
-    for (int j = 9; j < 12; ++j) wf[j] = (float)(sd * w[j]);
-    wf[12] = (float)(sh * (ctr_h - mean_h) + p.bn_b[o] + sd * (ctr_d - mean_d) + p.dn_b[o]);
-    wf[13] = wf[14] = wf[15] = 0.f;
-    p.stats[NSTAT + o] = (float)mean_h;
-    p.stats[NSTAT + p.Cout + o] = (float)rstd_h;
-    p.stats[NSTAT + 2 * p.Cout + o] = (float)mean_d;
-    p.stats[NSTAT + 3 * p.Cout + o] = (float)rstd_d;
+    __syncthreads();
+  }
+  if (seg < 2) part[seg * NMOM + mj] = macc;
+  __syncthreads();
+  if (threadIdx.x < 90)
+    atomicAdd(p.moments + (blockIdx.x % kSlots) * NMOM + threadIdx.x, (double)part[threadIdx.x] + (double)part[NMOM + threadIdx.x]);
+  // last CTA to finish turns the accumulated moments into statistics and folded weights
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(p.counter, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    gcn0_finalize(p, reinterpret_cast<double*>(sm));
   }
 }
 
@@ -662,7 +685,7 @@ int set_smem(K kernel, size_t bytes, const char* what) {
 }
 
 int check_fwd_args(const afb_gcn0_fwd_t* p) {
-  AFB_REQUIRE(p && p->x && p->A && p->PA && p->Mmat && p->moments && p->stats && p->Wfold && p->y, "gcn0: null pointer");
+  AFB_REQUIRE(p && p->x && p->A && p->PA && p->Mmat && p->moments && p->counter && p->stats && p->Wfold && p->y, "gcn0: null pointer");
   for (int i = 0; i < 3; ++i)
     AFB_REQUIRE(p->Wa[i] && p->ba[i] && p->Wb[i] && p->bb[i] && p->Wd[i] && p->bd[i], "gcn0: null weight pointer");
   AFB_REQUIRE(p->Wdn && p->bdn && p->bn_g && p->bn_b && p->dn_g && p->dn_b && p->bn_rm && p->bn_rv && p->dn_rm && p->dn_rv,
@@ -683,14 +706,13 @@ extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
   cudaStream_t st = as_stream(s);
   const int T = p->T, V = p->V;
   {
-    const size_t smem = ((size_t)T * V * 3 + 3 * V * V + 8 * NMOM) * sizeof(float);
+    size_t smem = ((size_t)a4(T * V * 3) + a4(3 * V * V) + (size_t)kPosChunk * NR + 2 * NMOM) * sizeof(float);
+    if (smem < 2048 + 8) smem = 2048 + 8;   // the finalize step reuses the buffer for ~252 doubles
     AFB_REQUIRE(smem <= 220 * 1024, "gcn0: T*V too large for the per-sample shared-memory stage (%zu B)", smem);
     if ((rc = set_smem(gcn0_scores_kernel, smem, "gcn0_scores"))) return rc;
     gcn0_scores_kernel<<<p->N, kThreads, smem, st>>>(*p);
     if ((rc = check_launch("gcn0_scores"))) return rc;
   }
-  gcn0_finalize_kernel<<<1, 1024, 0, st>>>(*p);
-  if ((rc = check_launch("gcn0_finalize"))) return rc;
   const int TT = pick_tt(T, V), chunks = ceil_div(T, TT);
   const int P16 = (TT * V + 15) / 16 * 16;
   const size_t head = ((size_t)a4(3 * V * V) + a4(TT * V * 3) + 16) * sizeof(float);

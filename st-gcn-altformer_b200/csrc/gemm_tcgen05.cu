@@ -427,15 +427,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int ch = u * ncl + c;
             const int n0 = ncol0 + ch * 32;
             float v[32], t[32];
-            const bool has_res = p.residual != nullptr && valid;
-            if (has_res) load32_dyn(p.residual, row * p.ldres + n0, p.res_dtype, t);  // issued before the TMEM wait
+            const bool last_pass = pass == (p.has_c2 ? 1 : 0);
+            const bool has_res = p.residual != nullptr && valid && last_pass;
+            const bool has_aux = p.act == AFB_ACT_GELU_BWD && valid;
+            // epilogue operands are requested before the TMEM wait so their latency overlaps it
+            if (has_res) load32_dyn(p.residual, row * p.ldres + n0, p.res_dtype, t);
+            else if (has_aux) load32_dyn(p.aux, row * p.ldaux + n0, p.aux_dtype, t);
             float4 bq[8];
             if (p.bias != nullptr) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) bq[q] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + q);
             }
             tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
-            const bool last_pass = pass == (p.has_c2 ? 1 : 0);
             if (last_pass && u + 2 >= units && c == ncl - 1) {  // this warp's last TMEM read of the accumulator
               tc_fence_before();
               __syncwarp();
@@ -465,11 +468,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
               } else if (p.act == AFB_ACT_GELU_BWD) {
-                if (valid) {
-                  float h[32];
-                  load32_dyn(p.aux, row * p.ldaux + n0, p.aux_dtype, h);
+                if (has_aux) {
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(h[i]);
+                  for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(t[i]);
                 }
               } else if (p.act == AFB_ACT_RELU) {
 #pragma unroll
@@ -484,7 +485,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int i = 0; i < 32; ++i) v[i] += t[i];
               }
             }
-            // stage: row = lane, 128-byte rows, 16-byte chunk index XOR (row & 7)  (SWIZZLE_128B)
+            // stage: row = lane, 128-byte rows, 16-byte chunk index XOR (row & 7)  (SWIZZLE_128B).  The previous
+            // TMA store of this warp must have finished READING the buffer; waiting here (not right after
+            // issuing it) lets that read overlap the TMEM load and the epilogue math of this unit.
+            if (c == 0) {
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+            }
             uint8_t* rowp = my_stage_ptr + lane * 128;
             if (out_bf16) {
 #pragma unroll
@@ -512,9 +519,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int col = ncol0 + u * 32 * ncl;
             tma_store_3d((p.has_c2 && pass == 0) ? &tmC2 : &tmC, my_stage, col, row_in_batch0, batch);
             bulk_commit();
-            bulk_wait_read0();
           }
-          __syncwarp();
         }
       }
       if (!arrived) {  // BN == 64 with bf16 output: the odd warps of each quarter have no unit in this tile
@@ -805,12 +810,18 @@ extern "C" int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s) {
   int BN = (p->N % 256 == 0) ? 256 : (p->N % 128 == 0 ? 128 : 64);
   bool stat = false;
   static const bool no_stat = getenv("AFB_GEMM_NO_STAT") != nullptr;
-  if (!no_stat) {
-    for (int bn = BN; bn >= 64; bn >>= 1) {
-      if (p->N % bn == 0 && k_blocks * bn * 128 <= 128 * 1024 && p->N / bn <= num_sms()) {
+  if (!no_stat && p->taps == 1) {
+    // L2->SM fill per 128-row m-tile: streaming re-fetches A and the B panel for each of its N/BN tiles,
+    // stationary(bn) re-fetches only A, N/bn times.  Pick the variant that moves fewer bytes.
+    const long a_tile = 128L * K * 2;
+    long best = (long)(p->N / BN) * (a_tile + (long)BN * K * 2);
+    for (int bn = 256; bn >= 64; bn >>= 1) {
+      if (p->N % bn != 0 || (long)k_blocks * bn * 128 > 128 * 1024 || p->N / bn > num_sms()) continue;
+      const long fill = (long)(p->N / bn) * a_tile;
+      if (fill < best) {
+        best = fill;
         BN = bn;
         stat = true;
-        break;
       }
     }
   }
@@ -832,6 +843,7 @@ extern "C" int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s) {
   a.residual = p->residual; a.res_dtype = p->res_dtype; a.ldres = p->ldres;
   a.row_scale = p->row_scale; a.row_scale_div = p->row_scale_div > 0 ? p->row_scale_div : 1;
   AFB_REQUIRE(p->act != AFB_ACT_GELU_BWD || p->aux != nullptr, "gemm_tn: GELU_BWD needs aux");
+  AFB_REQUIRE(p->act != AFB_ACT_GELU_BWD || p->residual == nullptr, "gemm_tn: GELU_BWD cannot be combined with a residual");
 
   CUtensorMap tmA, tmB, tmC, tmC2;
   int rc = make_map(&tmA, p->A, (uint64_t)p->k_per_tap, (uint64_t)p->rows_per_batch, (uint64_t)p->batches, (uint64_t)p->lda,

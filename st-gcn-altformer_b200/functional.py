@@ -498,7 +498,20 @@ def _p3(ts):
     return (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
 
 
+_gcn0_ws = {}
+
+
+def _gcn0_workspace(device):
+    """Persistent zero-initialised (moments fp64 [32, 96], CTA ticket) pair per device; the kernel re-arms it."""
+    key = (device.type, device.index)
+    if key not in _gcn0_ws:
+        _gcn0_ws[key] = (torch.zeros((_lib.GCN0_SLOTS, _lib.GCN0_NMOM), device=device, dtype=torch.float64),
+                         torch.zeros(1, device=device, dtype=torch.int32))
+    return _gcn0_ws[key]
+
+
 def _gcn0_struct(x, A, PA, mods, bufs, training, momentum, eps, Mmat, moments, stats, wfold, y):
+    counter = _gcn0_workspace(x.device)[1]
     N, T, V, _ = x.shape
     wa, ba, wb, bb, wd, bd, wdn, bdn, dng, dnb, bng, bnb = mods
     dn_rm, dn_rv, bn_rm, bn_rv = bufs
@@ -508,7 +521,7 @@ def _gcn0_struct(x, A, PA, mods, bufs, training, momentum, eps, Mmat, moments, s
                         bn_b=bnb.data_ptr(), dn_g=dng.data_ptr(), dn_b=dnb.data_ptr(), bn_rm=bn_rm.data_ptr(),
                         bn_rv=bn_rv.data_ptr(), dn_rm=dn_rm.data_ptr(), dn_rv=dn_rv.data_ptr(), N=N, T=T, V=V, Cout=Cout,
                         IC=IC, training=int(training), momentum=momentum, eps=eps, Mmat=Mmat.data_ptr(),
-                        moments=moments.data_ptr(), stats=stats.data_ptr(), Wfold=wfold.data_ptr(), y=y.data_ptr(),
+                        moments=moments.data_ptr(), counter=counter.data_ptr(), stats=stats.data_ptr(), Wfold=wfold.data_ptr(), y=y.data_ptr(),
                         y_dtype=ops.dt(y), precise=int(get_precision() == "fp32"))
 
 
@@ -534,7 +547,7 @@ class Gcn0Fn(torch.autograd.Function):
         Cout = wd[0].shape[0]
         dev = x.device
         Mmat = torch.empty((N, 3, V, V), device=dev, dtype=torch.float32)
-        moments = torch.empty((N, _lib.GCN0_NMOM), device=dev, dtype=torch.float32)
+        moments = _gcn0_workspace(dev)[0]
         stats = torch.empty(_lib.GCN0_NSTAT_BASE + 4 * Cout, device=dev, dtype=torch.float32)
         wfold = torch.empty((Cout, 16), device=dev, dtype=torch.float32)
         y = torch.empty((N * T * V, Cout), device=dev, dtype=act_dtype())
@@ -561,7 +574,7 @@ class Gcn0Fn(torch.autograd.Function):
         mods = (det(wa), det(ba), det(wb), det(bb), det(wd), det(bd), wdn.detach(), bdn.detach(), dng.detach(),
                 dnb.detach(), bng.detach(), bnb.detach())
         Cout = wd[0].shape[0]
-        moments = torch.empty(1, device=x.device, dtype=torch.float32)  # unused by backward
+        moments = _gcn0_workspace(x.device)[0]  # unused by backward
         f = _gcn0_struct(x, A, PA.detach(), mods, bufs, training, momentum, eps, Mmat, moments, stats, wfold, y)
         dy = _as_act(dy.contiguous())
         ws = torch.empty(32 * Cout + 256, device=x.device, dtype=torch.float32)

@@ -50,7 +50,7 @@ def ensure_device(t):
 
 
 LAUNCHES = [0]  # kernels launched through the C ABI (bench.py reports launches per step)
-_KERNELS_PER_CALL = {"afb_gcn0_fwd": 3, "afb_gcn0_bwd": 4}
+_KERNELS_PER_CALL = {"afb_gcn0_fwd": 2, "afb_gcn0_bwd": 4}
 
 
 def _call(name, *args):
