@@ -14,7 +14,10 @@
 //   gcn0_finalize_kernel 1 CTA: fp64 reduce of moments -> E, Cov -> BN stats -> folded weights
 //   gcn0_apply_kernel    per (sample, frame chunk): z -> A operand -> MMA -> ReLU -> coalesced store
 // Backward (parameter gradients only): gcn0_bwd_q / fin1 / dz / fin2, see afb_gcn0_bwd.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "mma_utils.cuh"
 
 namespace afb {
 namespace {
@@ -386,6 +389,135 @@ __global__ void __launch_bounds__(kThreads) gcn0_apply_kernel(const afb_gcn0_fwd
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward 3 (bf16 performance path): both stages on the tensor cores, one warp per frame.
+//   stage 1  z[v, slot] = c[slot, v] + sum_{i,u} M_i[u,v] * (x[u,a] - E x_a)        (slot = 3i + a)
+//            A = [M_0^T | M_1^T | M_2^T] (bf16, per sample, staged once per CTA), B = block-sparse copy of
+//            the centred frame; the fp32 accumulator starts at c = E[x_a] * colsum(M_i)[v] - E[z_slot], so
+//            the result is already centred and bf16 rounding only touches deviations.
+//   stage 2  y[v, :] = relu(Wfold * [z ; x - E x ; 1])  -- the stage-1 accumulators ARE the A fragments.
+// The frame's 128-channel rows are staged in the warp's shared-memory tile and leave as 16-byte coalesced
+// stores (a frame is V consecutive 256-byte rows of the output).
+// ---------------------------------------------------------------------------------------------
+template <int COUT, int VP>   // VP = V rounded up to 16
+__global__ void __launch_bounds__(kThreads) gcn0_apply_mma_kernel(const afb_gcn0_fwd_t p, int TT, int chunks) {
+  using namespace mmau;
+  constexpr int AP = VP + 8;          // A-operand pitch (elements)
+  constexpr int OP = COUT + 8;        // output staging pitch
+  constexpr int MT = VP / 16;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int V = p.V, T = p.T;
+  const int n = blockIdx.x / chunks, t0 = (blockIdx.x % chunks) * TT;
+  const int tt = min(TT, T - t0);
+  float* Ms = reinterpret_cast<float*>(smraw);                 // [3*V*V] fp32 (staging for the operand build)
+  float* xs = Ms + a4(3 * V * V);                              // [TT*V*3]
+  float* cs = xs + a4(TT * V * 3);                             // [9][VP] accumulator initialisers
+  float* colsum = cs + 9 * VP;                                 // [3][VP]
+  float* ctr = colsum + 3 * VP;                                // [16]
+  bf16* Asm = reinterpret_cast<bf16*>(ctr + 16);               // [3][VP][AP]
+  bf16* stage = Asm + 3 * VP * AP;                             // [8 warps][VP][OP]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+
+  const float* Mg = p.Mmat + (int64_t)n * 3 * V * V;
+  for (int i = threadIdx.x; i < 3 * V * V; i += blockDim.x) Ms[i] = Mg[i];
+  const float* xg = p.x + ((int64_t)n * T + t0) * V * 3;
+  for (int i = threadIdx.x; i < tt * V * 3; i += blockDim.x) xs[i] = xg[i];
+  if (threadIdx.x < 16) ctr[threadIdx.x] = threadIdx.x < NR ? p.stats[threadIdx.x] : 0.f;
+  uint32_t bfrag[COUT / 8][2];
+#pragma unroll
+  for (int nt = 0; nt < COUT / 8; ++nt) {
+    const float* wf = p.Wfold + (nt * 8 + g) * 16;
+    bfrag[nt][0] = pack2(wf[2 * t], wf[2 * t + 1]);
+    bfrag[nt][1] = pack2(wf[2 * t + 8], wf[2 * t + 9]);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 3 * VP * AP; e += blockDim.x) {  // A_i[v][u] = M_i[u][v], zero padded
+    const int i = e / (VP * AP), r = e % (VP * AP), v = r / AP, u = r % AP;
+    Asm[e] = __float2bfloat16_rn((v < V && u < V) ? Ms[(i * V + u) * V + v] : 0.f);
+  }
+  for (int e = threadIdx.x; e < 3 * VP; e += blockDim.x) {
+    const int i = e / VP, v = e % VP;
+    float s = 0.f;
+    if (v < V)
+      for (int u = 0; u < V; ++u) s += Ms[(i * V + u) * V + v];
+    colsum[e] = s;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 9 * VP; e += blockDim.x) {
+    const int slot = e / VP, v = e % VP;
+    cs[e] = v < V ? ctr[9 + slot % 3] * colsum[(slot / 3) * VP + v] - ctr[slot] : 0.f;
+  }
+  __syncthreads();
+
+  const int slot_i = g / 3, slot_a = g % 3;      // z slot owned by this lane's B column in n-tile 0
+  bf16* mystage = stage + warp * VP * OP;
+  for (int fl = warp; fl < tt; fl += kThreads / 32) {
+    const float* xt = xs + fl * V * 3;
+    auto xc = [&](int u, int a) { return u < V ? xt[u * 3 + a] - ctr[9 + a] : 0.f; };
+    // B fragments of the centred frame: n-tile 0 (slots 0-7) and the single z slot (8) of n-tile 1
+    uint32_t bx[MT][2], bx1[MT][2];
+#pragma unroll
+    for (int ku = 0; ku < MT; ++ku) {
+      const int u0 = ku * 16 + 2 * t;
+      bx[ku][0] = pack2(xc(u0, slot_a), xc(u0 + 1, slot_a));
+      bx[ku][1] = pack2(xc(u0 + 8, slot_a), xc(u0 + 9, slot_a));
+      bx1[ku][0] = g == 0 ? pack2(xc(u0, 2), xc(u0 + 1, 2)) : 0u;
+      bx1[ku][1] = g == 0 ? pack2(xc(u0 + 8, 2), xc(u0 + 9, 2)) : 0u;
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int v0 = mt * 16 + g, v1 = v0 + 8;
+      float z0[4], z1[4];   // n-tile 0 (slots 2t, 2t+1) and n-tile 1 (slots 8+2t, 9+2t) for rows v0 / v1
+      z0[0] = cs[(2 * t) * VP + v0]; z0[1] = cs[(2 * t + 1) * VP + v0];
+      z0[2] = cs[(2 * t) * VP + v1]; z0[3] = cs[(2 * t + 1) * VP + v1];
+      z1[0] = t == 0 ? cs[8 * VP + v0] : 0.f; z1[1] = 0.f;
+      z1[2] = t == 0 ? cs[8 * VP + v1] : 0.f; z1[3] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int ku = 0; ku < MT; ++ku) {
+          uint32_t a[4];
+          ldsm_x4(smem_u32(Asm + (i * VP + mt * 16 + (lane & 15)) * AP + ku * 16 + (lane >> 4) * 8), a);
+          const bool mine = slot_i == i;
+          mma(z0, a, mine ? bx[ku][0] : 0u, mine ? bx[ku][1] : 0u);
+          if (i == 2) mma(z1, a, bx1[ku][0], bx1[ku][1]);
+        }
+      // stage-2 A fragment: slots 0-7 from z0, slot 8 from z1, slots 9-11 = centred x, slot 12 = 1
+      uint32_t a2[4];
+      a2[0] = pack2(z0[0], z0[1]);
+      a2[1] = pack2(z0[2], z0[3]);
+      if (t == 0) {
+        a2[2] = pack2(z1[0], xc(v0, 0));
+        a2[3] = pack2(z1[2], xc(v1, 0));
+      } else if (t == 1) {
+        a2[2] = pack2(xc(v0, 1), xc(v0, 2));
+        a2[3] = pack2(xc(v1, 1), xc(v1, 2));
+      } else if (t == 2) {
+        a2[2] = pack2(1.f, 0.f);
+        a2[3] = a2[2];
+      } else {
+        a2[2] = 0u;
+        a2[3] = 0u;
+      }
+#pragma unroll
+      for (int nt = 0; nt < COUT / 8; ++nt) {
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        mma(d, a2, bfrag[nt][0], bfrag[nt][1]);
+        bf16* o0 = mystage + v0 * OP + nt * 8 + 2 * t;
+        *reinterpret_cast<uint32_t*>(o0) = pack2(fmaxf(d[0], 0.f), fmaxf(d[1], 0.f));
+        *reinterpret_cast<uint32_t*>(o0 + 8 * OP) = pack2(fmaxf(d[2], 0.f), fmaxf(d[3], 0.f));
+      }
+    }
+    __syncwarp();
+    bf16* yg = reinterpret_cast<bf16*>(p.y) + (((int64_t)n * T + t0 + fl) * V) * COUT;
+    for (int idx = lane; idx < V * (COUT / 8); idx += 32) {
+      const int r = idx / (COUT / 8), c8 = idx % (COUT / 8);
+      *reinterpret_cast<uint4*>(yg + (int64_t)r * COUT + c8 * 8) = *reinterpret_cast<const uint4*>(mystage + r * OP + c8 * 8);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
 // workspace layout (floats): Q [Cout][16] | U [Cout][16] | cvec [16] | Kmat [9][9 -> 96] | gram [3][16]
@@ -717,7 +849,20 @@ extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
   const int P16 = (TT * V + 15) / 16 * 16;
   const size_t head = ((size_t)a4(3 * V * V) + a4(TT * V * 3) + 16) * sizeof(float);
   const bool mma = !p->precise && p->y_dtype == AFB_BF16 && p->Cout == 128;
-  if (mma) {
+  static const bool old_apply = getenv("AFB_GCN0_APPLY_V1") != nullptr;
+  if (mma && !old_apply && V <= 48) {
+    const int TT2 = T < 8 ? T : 8, chunks2 = ceil_div(T, TT2);
+    const int VP = V <= 16 ? 16 : (V <= 32 ? 32 : 48);
+    const size_t smem2 = ((size_t)a4(3 * V * V) + a4(TT2 * V * 3) + 12 * VP + 16) * sizeof(float) + (size_t)3 * VP * (VP + 8) * 2 +
+                         (size_t)(kThreads / 32) * VP * (128 + 8) * 2;
+#define LAUNCH_APPLY_MMA(VP_)                                                                           \
+  do {                                                                                                  \
+    if ((rc = set_smem(gcn0_apply_mma_kernel<128, VP_>, smem2, "gcn0_apply_mma"))) return rc;           \
+    gcn0_apply_mma_kernel<128, VP_><<<p->N * chunks2, kThreads, smem2, st>>>(*p, TT2, chunks2);         \
+  } while (0)
+    if (VP == 16) LAUNCH_APPLY_MMA(16); else if (VP == 32) LAUNCH_APPLY_MMA(32); else LAUNCH_APPLY_MMA(48);
+#undef LAUNCH_APPLY_MMA
+  } else if (mma) {
     const size_t smem = head + (size_t)P16 * kARow * 2 + (size_t)P16 * (128 + 8) * 2;
     if ((rc = set_smem(gcn0_apply_kernel<true, bf16, 128>, smem, "gcn0_apply"))) return rc;
     gcn0_apply_kernel<true, bf16, 128><<<p->N * chunks, kThreads, smem, st>>>(*p, TT, chunks);

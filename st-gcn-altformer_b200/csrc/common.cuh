@@ -122,4 +122,23 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return fmaf(x * 0.3989422804014327f, u, cdf);
 }
 
+// bf16-mode GELU: tanh form on the MUFU.TANH unit (1 special-function op instead of 2).  |gelu_tanh - gelu_erf|
+// <= 4.7e-4, below the bf16 resolution of the stored value; the fp32 parity mode keeps the erf form above.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_fast_f(float x) {
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);   // sqrt(2/pi) (x + 0.044715 x^3)
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(u), hx);
+}
+__device__ __forceinline__ float gelu_fast_grad_f(float x) {
+  const float x2 = x * x;
+  const float th = tanh_approx(x * fmaf(0.0356774081f, x2, 0.7978845608f));
+  const float du = fmaf(0.1070322243f, x2, 0.7978845608f);           // d/dx of the tanh argument
+  return fmaf(0.5f * x * du, fmaf(-th, th, 1.0f), fmaf(0.5f, th, 0.5f));
+}
+
 }  // namespace afb

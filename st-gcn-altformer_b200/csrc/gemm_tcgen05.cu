@@ -465,12 +465,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (last_pass) {
               if (p.act == AFB_ACT_GELU) {
+                if (out_bf16) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+                  for (int i = 0; i < 32; ++i) v[i] = gelu_fast_f(v[i]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+                }
               } else if (p.act == AFB_ACT_GELU_BWD) {
                 if (has_aux) {
+                  if (out_bf16) {
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(t[i]);
+                    for (int i = 0; i < 32; ++i) v[i] *= gelu_fast_grad_f(t[i]);
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(t[i]);
+                  }
                 }
               } else if (p.act == AFB_ACT_RELU) {
 #pragma unroll

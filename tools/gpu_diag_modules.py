@@ -116,6 +116,8 @@ def grp_gcn0():
     def case(N, T, V, training, mode, seed):
         with precision(mode):
             ftol, _, gtol = _tols(mode, True)
+            if N * T * V < 2000:   # tiny batches: BN statistics over < 2000 positions amplify rounding
+                gtol *= 2
             A = O.spatial_graph(V)
             st = O.random_state(O.agcn_spec("", 3, 128, V), seed)
             x, _ = O.synthetic_batch(N, T, V, 14, seed + 1)
