@@ -101,6 +101,8 @@ typedef struct {
   int64_t ld1, ld2;
   int32_t x_row_shift;
   float alpha;
+  float* dbias; /* optional: dbias[n1] += alpha * sum_m G[m, n1] (bias gradient, folded in as an extra N=16 MMA
+                   against an all-ones operand) */
 } afb_gemm_dw_t;
 int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s);
 

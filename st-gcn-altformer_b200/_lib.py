@@ -26,7 +26,7 @@ class GemmTn(C.Structure):
 
 class GemmDw(C.Structure):
     _fields_ = [("G", vp), ("X", vp), ("dW", vp), ("rows_per_batch", i64), ("batches", i32), ("N1", i32), ("N2", i32),
-                ("ldg", i32), ("ldx", i32), ("ld1", i64), ("ld2", i64), ("x_row_shift", i32), ("alpha", f32)]
+                ("ldg", i32), ("ldx", i32), ("ld1", i64), ("ld2", i64), ("x_row_shift", i32), ("alpha", f32), ("dbias", vp)]
 
 
 class GemmSimt(C.Structure):

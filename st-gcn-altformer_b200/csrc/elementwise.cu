@@ -592,6 +592,14 @@ __global__ void axpby_kernel(const float* __restrict__ a, float wa, const float*
 }  // namespace
 }  // namespace afb
 
+namespace afb {
+// bf16 fast paths (layernorm_bf16.cu)
+int layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows, int D,
+                       float eps, cudaStream_t st);
+int layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
+                       void* dx, float* dgamma, float* dbeta, int64_t rows, int D, cudaStream_t st);
+}  // namespace afb
+
 using namespace afb;
 
 #define DISPATCH_DT(dt, T, ...)                        \
@@ -651,6 +659,8 @@ extern "C" int afb_layernorm_fwd(const void* x, int xd, const float* gamma, cons
   AFB_REQUIRE(x && gamma && beta && y && rows > 0, "layernorm_fwd: bad args");
   AFB_REQUIRE(D == 128 || D == 256 || D == 512, "layernorm: D=%d unsupported (128, 256 or 512)", D);
   cudaStream_t st = as_stream(s);
+  if (xd == AFB_BF16 && yd == AFB_BF16 && (D == 256 || D == 512) && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0)
+    return layernorm_fwd_bf16(x, gamma, beta, y, mean, rstd, rows, D, eps, st);
   if (xd == AFB_BF16 && yd == AFB_BF16) return ln_fwd_dispatch<bf16, bf16>(x, gamma, beta, y, mean, rstd, rows, D, eps, st);
   if (xd == AFB_F32 && yd == AFB_BF16) return ln_fwd_dispatch<float, bf16>(x, gamma, beta, y, mean, rstd, rows, D, eps, st);
   if (xd == AFB_F32 && yd == AFB_F32) return ln_fwd_dispatch<float, float>(x, gamma, beta, y, mean, rstd, rows, D, eps, st);
@@ -676,6 +686,8 @@ extern "C" int afb_layernorm_bwd(const void* dy, int dyd, const void* x, int xd,
   AFB_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0, "layernorm_bwd: bad args");
   AFB_REQUIRE(D == 128 || D == 256 || D == 512, "layernorm: D=%d unsupported (128, 256 or 512)", D);
   AFB_REQUIRE(dyd == xd && xd == dxd && (dres == nullptr || drd == xd), "layernorm_bwd: all activations must share one dtype");
+  if (xd == AFB_BF16 && (D == 256 || D == 512) && (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)dres) & 15) == 0)
+    return layernorm_bwd_bf16(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D, as_stream(s));
   if (xd == AFB_BF16) return ln_bwd_dispatch<bf16>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D, as_stream(s));
   return ln_bwd_dispatch<float>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D, as_stream(s));
 }

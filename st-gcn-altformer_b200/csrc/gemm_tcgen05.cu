@@ -203,7 +203,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // (<= 128 KB) and only A tiles stream through the ring -- cuts the L2->SM fill per tile by 3x for the
 // K <= 256/512 linears whose weight panel would otherwise be re-fetched for every 128-row tile.
 template <int BN, bool STAT> struct TnCfg {
-  static constexpr int kStages = STAT ? 4 : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8));
+  static constexpr int kStages = STAT ? 8 : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8));   // STAT: upper bound, see TnArgs::stages
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;                       // one k-block of the B panel
   static constexpr int kResKBlocks = (128 * 1024) / kBBytes;        // resident k-blocks (STAT)
@@ -211,11 +211,19 @@ template <int BN, bool STAT> struct TnCfg {
   static constexpr int kStageTx = STAT ? kABytes : kABytes + kBBytes;
   static constexpr int kTmemCols = BN >= 256 ? 512 : (BN >= 128 ? 256 : 128);
   static constexpr int kStagingBytes = kTnEpiWarps * 4096;          // one 32 x 128 B box per epilogue warp
-  static constexpr int kSmemBytes = kStages * kABytes + kBRegion + kStagingBytes + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kFixedBytes = kStagingBytes + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kSmemMax = 232448;  // 227 KB opt-in limit per CTA
+  // streaming: fixed ring.  stationary: the ring takes whatever the resident panel leaves (host: stat_stages()).
+  static constexpr int kSmemBytes = STAT ? kSmemMax : kStages * kABytes + kBRegion + kFixedBytes;
+  static int stat_stages(int k_blocks) {
+    int st = (kSmemMax - kFixedBytes - k_blocks * kBBytes) / kABytes;
+    return st > 8 ? 8 : st;
+  }
 };
 
 struct TnArgs {
   int m_tiles_per_batch, n_tiles, total_m_tiles, k_blocks;
+  int stages;   // ring depth actually used (stationary mode: as many A stages as fit beside the weight panel)
   int rows_per_batch, batches, N;
   int kb_per_tap, tap_row_stride, tap_pad;
   int out_dtype, act, has_c2;
@@ -274,10 +282,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* smem = smem_raw + (base - raw_addr);
 
+  const int nstages = STAT ? p.stages : Cfg::kStages;
   const uint32_t sA = base;
-  const uint32_t sB = base + Cfg::kStages * Cfg::kABytes;
-  const uint32_t sStage = sB + Cfg::kBRegion;
-  constexpr uint32_t kBarOff = Cfg::kStages * Cfg::kABytes + Cfg::kBRegion + Cfg::kStagingBytes;
+  const uint32_t sB = base + nstages * Cfg::kABytes;
+  const uint32_t b_region = STAT ? (uint32_t)p.k_blocks * Cfg::kBBytes : (uint32_t)Cfg::kBRegion;
+  const uint32_t sStage = sB + b_region;
+  const uint32_t kBarOff = nstages * Cfg::kABytes + b_region + Cfg::kStagingBytes;
   const uint32_t bar0 = base + kBarOff;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (Cfg::kStages + s); };
@@ -294,7 +304,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -347,7 +357,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_load_2d(&tmB, full_bar(stage), sB + stage * Cfg::kBBytes + j * (64 * 128), w.n_blk * BN + j * 64, kb * BK);
             }
           }
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -377,7 +387,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -394,7 +404,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lane_grp = warp & 3;
     const int half = ew >> 2;
     const uint32_t my_stage = sStage + ew * 4096;
-    uint8_t* my_stage_ptr = smem + Cfg::kStages * Cfg::kABytes + Cfg::kBRegion + ew * 4096;
+    uint8_t* my_stage_ptr = smem + nstages * Cfg::kABytes + b_region + ew * 4096;
     const bool out_bf16 = p.out_dtype == AFB_BF16;
     const int ncl = out_bf16 ? 2 : 1;          // tcgen05.ld chunks per 128-byte staging row
     const int units = BN / (32 * ncl);
@@ -557,9 +567,11 @@ template <int BN2> struct DwCfg {
   static constexpr int kABytes = 64 * 128 * 2;      // 64 rows x 128 n1
   static constexpr int kBBytes = 64 * BN2 * 2;      // 64 rows x BN2 n2
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = BN2 >= 256 ? 256 : (BN2 >= 128 ? 128 : 64);
+  // accumulator columns [0, BN2) hold dW; columns [BN2, BN2 + 16) hold G^T * ones (the bias gradient)
+  static constexpr int kTmemCols = BN2 >= 256 ? 512 : (BN2 >= 128 ? 256 : 128);
   static constexpr int kScratchBytes = kEpiWarps * 32 * kScratchStride * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 256 + 1024;
+  static constexpr int kOnesBytes = 8192;           // one all-ones [64 x 64] bf16 tile (MN-major B operand)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + kOnesBytes + 256 + 1024;
 };
 
 struct DwArgs {
@@ -570,6 +582,7 @@ struct DwArgs {
   float* dW;
   long long ld1, ld2;
   float alpha;
+  float* dbias;   // optional: dbias[n1] += alpha * sum_m G[m, n1]
 };
 
 template <int BN2>
@@ -583,13 +596,14 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   const uint32_t sA = base;
   const uint32_t sB = base + Cfg::kStages * Cfg::kABytes;
   float* scratch = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  const uint32_t bar0 = base + Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes;
+  const uint32_t sOnes = base + Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes;
+  constexpr uint32_t kDwBarOff = Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes + Cfg::kOnesBytes;
+  const uint32_t bar0 = base + kDwBarOff;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (Cfg::kStages + s); };
   const uint32_t tfull_bar = bar0 + 8u * (2 * Cfg::kStages);
   const uint32_t tmem_slot = bar0 + 8u * (2 * Cfg::kStages + 1);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes + 8 * (2 * Cfg::kStages + 1));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + kDwBarOff + 8 * (2 * Cfg::kStages + 1));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -603,6 +617,13 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   const int rb_begin = split * per;
   const int rb_end = min(rb_begin + per, p.total_row_blocks);
   const int n_rb = max(rb_end - rb_begin, 0);
+  // the CTAs of the first n2 tile also reduce G over rows (bias gradient) with one extra N=16 MMA per k-step
+  const bool do_bias = p.dbias != nullptr && n2_blk == 0;
+  if (do_bias) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes);
+    for (int i = threadIdx.x; i < Cfg::kOnesBytes / 4; i += blockDim.x) ones[i] = 0x3f803f80u;  // bf16 1.0 pairs
+    fence_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmG);
@@ -642,6 +663,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
     } else if (warp == 1) {
       if (lane == 0) {
         constexpr uint32_t idesc = make_idesc(128, BN2, 1, 1);
+        constexpr uint32_t idesc_ones = make_idesc(128, 16, 1, 1);
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0; i < n_rb; ++i) {
@@ -654,6 +676,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
             const uint64_t adesc = make_desc(a_addr + k * 2048, 8192, 1024);
             const uint64_t bdesc = make_desc(b_addr + k * 2048, 8192, 1024);
             umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+            if (do_bias) umma_bf16(tmem_base + BN2, adesc, make_desc(sOnes, 8192, 1024), idesc_ones, (i | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
@@ -680,6 +703,12 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           if (n1 < p.N1 && n2 < p.N2) atomicAdd(p.dW + n1 * p.ld1 + n2 * p.ld2, p.alpha * my[r * kScratchStride + lane]);
         }
         __syncwarp();
+      }
+      if (do_bias) {   // column BN2 of the accumulator = sum over this CTA's rows of G[:, n1]
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)BN2, v);
+        const int n1 = n1_blk * 128 + lane_grp * 32 + lane;
+        if (n1 < p.N1) atomicAdd(p.dbias + n1, p.alpha * v[0]);
       }
     }
   }
@@ -825,7 +854,8 @@ extern "C" int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s) {
     // stationary(bn) re-fetches only A, N/bn times.  Pick the variant that moves fewer bytes.
     const long a_tile = 128L * K * 2;
     long best = (long)(p->N / BN) * (a_tile + (long)BN * K * 2);
-    for (int bn = 256; bn >= 64; bn >>= 1) {
+    static const int max_stat_bn = getenv("AFB_GEMM_STAT_BN") ? atoi(getenv("AFB_GEMM_STAT_BN")) : 256;
+    for (int bn = max_stat_bn; bn >= 64; bn >>= 1) {
       if (p->N % bn != 0 || (long)k_blocks * bn * 128 > 128 * 1024 || p->N / bn > num_sms()) continue;
       const long fill = (long)(p->N / bn) * a_tile;
       if (fill < best) {
@@ -841,6 +871,11 @@ extern "C" int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s) {
   a.total_m_tiles = a.m_tiles_per_batch * p->batches;
   a.kb_per_tap = kb_per_tap;
   a.k_blocks = k_blocks;
+  a.stages = 0;
+  if (stat) {
+    a.stages = BN == 256 ? TnCfg<256, true>::stat_stages(k_blocks) : (BN == 128 ? TnCfg<128, true>::stat_stages(k_blocks) : TnCfg<64, true>::stat_stages(k_blocks));
+    AFB_REQUIRE(a.stages >= 2, "gemm_tn: internal: stationary panel leaves no room for the A ring");
+  }
   a.rows_per_batch = (int)p->rows_per_batch;
   a.batches = p->batches;
   a.N = p->N;
@@ -903,7 +938,7 @@ extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
   if (splits > max_splits) splits = max_splits;
   a.splits = splits;
   a.N1 = p->N1; a.N2 = p->N2; a.x_row_shift = p->x_row_shift;
-  a.dW = p->dW; a.ld1 = p->ld1; a.ld2 = p->ld2; a.alpha = p->alpha;
+  a.dW = p->dW; a.ld1 = p->ld1; a.ld2 = p->ld2; a.alpha = p->alpha; a.dbias = p->dbias;
   CUtensorMap tmG, tmX;
   int rc = make_map(&tmG, p->G, (uint64_t)p->N1, (uint64_t)p->rows_per_batch, (uint64_t)p->batches, (uint64_t)p->ldg,
                     (uint64_t)p->rows_per_batch * p->ldg, 64, 64, 3);

@@ -143,10 +143,13 @@ def mm_dx(g, w_param, **epi):
     return ops.gemm_tn(ops.split3(g, 0), w_dx(w_param), K, b_mn_major=True, out_dtype=torch.float32, **epi)
 
 
-def mm_dw(g, x, dW, **kw):
-    """dW [N, K] += g [M, N]^T @ x [M, K]."""
+def mm_dw(g, x, dW, dbias=None, **kw):
+    """dW [N, K] += g [M, N]^T @ x [M, K];  dbias [N] += column sums of g (folded into the same kernel in
+    bf16 mode; a separate fp32 reduction in parity mode)."""
     if _PRECISION[0] == "bf16":
-        return ops.gemm_dw(g, x, dW, **kw)
+        return ops.gemm_dw(g, x, dW, dbias=dbias, **kw)
+    if dbias is not None:
+        ops.colsum(g, dbias)
     N1, N2 = g.shape[1], x.shape[1]
     gs, xs = ops.split3(g, 0), ops.split3(x, 1)     # (hi|lo|hi) x (hi|hi|lo)
     kw.setdefault("ld1", N2)
@@ -179,12 +182,9 @@ class LinearFn(torch.autograd.Function):
         g = dy if row_scale is None else ops.scale_rows(dy, row_scale, ctx.div)
         dx = mm_dx(g, weight) if ctx.needs_input_grad[0] else None
         sw = _grad_sink(weight)
-        mm_dw(g, x, sw[0].view(weight.shape[0], -1))
-        db = None
-        if bias is not None:
-            sb = _grad_sink(bias)
-            ops.colsum(g, sb[0])
-            db = _ret(sb)
+        sb = _grad_sink(bias) if bias is not None else None
+        mm_dw(g, x, sw[0].view(weight.shape[0], -1), dbias=None if sb is None else sb[0])
+        db = None if sb is None else _ret(sb)
         dpos = None
         if pos is not None:
             sp = _grad_sink(pos)
@@ -286,12 +286,10 @@ def _mlp_fwd(x, w1, b1, w2, b2, residual, keep, div):
 def _mlp_bwd(g, x, h_act, h_pre, w1, b1, w2, b2, need_dx=True):
     """g: gradient w.r.t. the (already DropPath-scaled) fc2 output."""
     s2, sb2 = _grad_sink(w2), _grad_sink(b2)
-    mm_dw(g, h_act, s2[0])
-    ops.colsum(g, sb2[0])
+    mm_dw(g, h_act, s2[0], dbias=sb2[0])
     dpre = mm_dx(g, w2, act=ACT_GELU_BWD, aux=h_pre)
     s1, sb1 = _grad_sink(w1), _grad_sink(b1)
-    mm_dw(dpre, x, s1[0])
-    ops.colsum(dpre, sb1[0])
+    mm_dw(dpre, x, s1[0], dbias=sb1[0])
     dx = mm_dx(dpre, w1) if need_dx else None
     return dx, (_ret(s1), _ret(sb1), _ret(s2), _ret(sb2))
 
@@ -347,17 +345,13 @@ class BlockFn(torch.autograd.Function):
         g1 = ops.layernorm_bwd(dln2, x1, n2w.detach(), mean2, rstd2, sg2[0], sb2[0], dres=g2)
         gs1 = g1 if keep1 is None else ops.scale_rows(g1, keep1, L)
         sp, spb = _grad_sink(pw), _grad_sink(pb)
-        mm_dw(gs1, ao, sp[0])
-        ops.colsum(gs1, spb[0])
+        mm_dw(gs1, ao, sp[0], dbias=spb[0])
         dao = mm_dx(gs1, pw)
         dqkv = ops.attention_bwd(qkv, dao, B, L, heads)
         sq = _grad_sink(qkvw)
-        mm_dw(dqkv, ln1, sq[0])
-        gqb = None
-        if qkvb is not None:
-            sqb = _grad_sink(qkvb)
-            ops.colsum(dqkv, sqb[0])
-            gqb = _ret(sqb)
+        sqb = _grad_sink(qkvb) if qkvb is not None else None
+        mm_dw(dqkv, ln1, sq[0], dbias=None if sqb is None else sqb[0])
+        gqb = None if sqb is None else _ret(sqb)
         dln1 = mm_dx(dqkv, qkvw)
         sg1, sb1 = _grad_sink(n1w), _grad_sink(n1b)
         g0 = ops.layernorm_bwd(dln1, x, n1w.detach(), mean1, rstd1, sg1[0], sb1[0], dres=g1)

@@ -90,9 +90,10 @@ def gemm_tn(a, b, N, *, k_per_tap=None, taps=1, tap_row_stride=0, tap_pad=0, row
 
 
 def gemm_dw(g, x, dW, *, N1=None, N2=None, rows_per_batch=None, batches=1, ld1=None, ld2=1, x_row_shift=0, alpha=1.0,
-            g_col0=0, x_col0=0):
-    """dW[n1*ld1 + n2*ld2] += alpha * sum_m g[m, g_col0 + n1] * x[m + shift, x_col0 + n2]  (fp32 atomics)."""
-    need_cuda(g, x, dW)
+            g_col0=0, x_col0=0, dbias=None):
+    """dW[n1*ld1 + n2*ld2] += alpha * sum_m g[m, g_col0 + n1] * x[m + shift, x_col0 + n2]  (fp32 atomics);
+    dbias[n1] += alpha * sum_m g[m, g_col0 + n1] when given."""
+    need_cuda(g, x, dW, dbias)
     if g.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dW.dtype != torch.float32:
         raise RuntimeError("gemm_dw: g, x must be bfloat16 and dW float32")
     M = g.shape[0]
@@ -102,7 +103,7 @@ def gemm_dw(g, x, dW, *, N1=None, N2=None, rows_per_batch=None, batches=1, ld1=N
     N2 = x.shape[1] if N2 is None else N2
     p = _lib.GemmDw(G=ptr(g) + 2 * g_col0, X=ptr(x) + 2 * x_col0, dW=ptr(dW), rows_per_batch=rows_per_batch,
                     batches=batches, N1=N1, N2=N2, ldg=g.shape[1], ldx=x.shape[1],
-                    ld1=N2 if ld1 is None else ld1, ld2=ld2, x_row_shift=x_row_shift, alpha=alpha)
+                    ld1=N2 if ld1 is None else ld1, ld2=ld2, x_row_shift=x_row_shift, alpha=alpha, dbias=ptr(dbias))
     _call("afb_gemm_dw", C.byref(p), stream())
     return dW
 

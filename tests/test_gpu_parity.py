@@ -49,11 +49,15 @@ def test_gcn0_against_reference_golden(name, train):
         if train:
             cot = torch.randn(y.shape, generator=torch.Generator().manual_seed(7)).cuda()
             (y.float() * cot).sum().backward()
-            for k, p in mod.named_parameters():
+            from tools.gpu_diag_modules import is_zero_class
+            named = dict(mod.named_parameters())
+            for k, p in named.items():
                 ref = case["grad." + k]
-                rn = ref["norm"] if isinstance(ref, dict) else float(ref.norm())
-                if rn < 1e-4:
-                    assert float(p.grad.norm()) < 1e-3, k
+                if is_zero_class(k, True):
+                    # analytically zero (the reference only holds fp32 round-off there): absolute check against
+                    # the scale of the sibling weight gradient
+                    scale = float(named[k[:-4] + "weight"].grad.norm())
+                    assert float(p.grad.norm()) <= 1e-3 * scale, (k, float(p.grad.norm()), scale)
                 else:
                     G.check_entry(ref, p.grad, 5e-4, k)
     finally:

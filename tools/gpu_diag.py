@@ -333,6 +333,12 @@ def grp_gemm_dw():
             dW = torch.zeros(N1, N2, device=DEV)
             ops.gemm_dw(G, X, dW)
             report(f"gemm_dw M={M} N1={N1} N2={N2}", dW, G.float().t() @ X.float(), 2e-3)
+        for (M, N1, N2) in ((1000, 256, 256), (5000, 768, 256), (700, 512, 1024), (900, 96, 128)):   # fused bias gradient
+            G, X = g(M, N1, seed=5, scale=0.1, dtype=torch.bfloat16), g(M, N2, seed=6, dtype=torch.bfloat16)
+            dW, db = torch.zeros(N1, N2, device=DEV), torch.zeros(N1, device=DEV)
+            ops.gemm_dw(G, X, dW, dbias=db)
+            report(f"gemm_dw+dbias M={M} N1={N1} N2={N2} dW", dW, G.float().t() @ X.float(), 2e-3)
+            report(f"gemm_dw+dbias M={M} N1={N1} N2={N2} dbias", db, G.float().sum(0), 2e-3)
         G, X = g(3000, 384, seed=3, scale=0.1, dtype=torch.bfloat16), g(3000, 192, seed=4, dtype=torch.bfloat16)
         dW = torch.zeros(128, 64, device=DEV)
         ops.gemm_dw(G, X, dW, N1=128, N2=64, ld1=64, g_col0=128, x_col0=64)
