@@ -247,6 +247,10 @@ typedef struct {
   int32_t* counter;    /* persistent, zero-initialised CTA ticket (re-armed by the kernel) */
   float* stats;        /* out [AFB_GCN0_NSTAT_BASE + 4*Cout]: E[r] (12), Cov(r) (144), mean_h, rstd_h, mean_d, rstd_d */
   float* Wfold;        /* out [Cout][16]: BN-folded weights of the apply pass */
+  void* Aop;           /* out (optional) bf16 [N][3][VP][VP+8], VP = V rounded up to 16: A_i[v][u] = M_i[u][v] */
+  float* colsum;       /* out (optional) [N][3][VP]: sum_u M_i[u][v] */
+  void* Wfrag;         /* out (optional) uint32 [Cout/8][32][2]: Wfold as mma.m16n8k16 B fragments (bf16 pairs);
+                          the tensor-core apply pass needs Aop, colsum and Wfrag (V <= 48) */
   void* y;             /* out [N*T*V][Cout] */
   int32_t y_dtype;
   int32_t precise;     /* 1: fp32 FMA apply (parity mode); 0: bf16 mma.sync apply */

@@ -40,7 +40,7 @@ class Gcn0Fwd(C.Structure):
                 ("Wd", vp * 3), ("bd", vp * 3), ("Wdn", vp), ("bdn", vp), ("bn_g", vp), ("bn_b", vp), ("dn_g", vp),
                 ("dn_b", vp), ("bn_rm", vp), ("bn_rv", vp), ("dn_rm", vp), ("dn_rv", vp), ("N", i32), ("T", i32),
                 ("V", i32), ("Cout", i32), ("IC", i32), ("training", i32), ("momentum", f32), ("eps", f32),
-                ("Mmat", vp), ("moments", vp), ("counter", vp), ("stats", vp), ("Wfold", vp), ("y", vp), ("y_dtype", i32),
+                ("Mmat", vp), ("moments", vp), ("counter", vp), ("stats", vp), ("Wfold", vp), ("Aop", vp), ("colsum", vp), ("Wfrag", vp), ("y", vp), ("y_dtype", i32),
                 ("precise", i32)]
 
 

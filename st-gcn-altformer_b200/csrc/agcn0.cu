@@ -30,6 +30,11 @@ constexpr int kThreads = 256;
 __host__ __device__ constexpr int a4(int n) { return (n + 3) & ~3; }  // keep smem sections 16-byte aligned
 __host__ __device__ constexpr int tri(int j, int k) { return NR + j * NR - (j * (j - 1)) / 2 + (k - j); }  // j <= k
 
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 struct Coef {  // per subset: C (3x3), e (3), f (3)
   float v[3][16];
 };
@@ -154,6 +159,13 @@ __device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm 
     for (int j = 9; j < 12; ++j) wf[j] = (float)(sd * w[j]);
     wf[12] = (float)(sh * (ctr_h - mean_h) + p.bn_b[o] + sd * (ctr_d - mean_d) + p.dn_b[o]);
     wf[13] = wf[14] = wf[15] = 0.f;
+    if (p.Wfrag != nullptr) {   // mma.m16n8k16 B fragments of Wfold^T, one uint2 per (n-tile, lane)
+      uint32_t* frag = reinterpret_cast<uint32_t*>(p.Wfrag) + ((o >> 3) * 32 + (o & 7) * 4) * 2;
+      for (int t = 0; t < 4; ++t) {
+        frag[t * 2] = pack_bf16(wf[2 * t], wf[2 * t + 1]);
+        frag[t * 2 + 1] = pack_bf16(wf[2 * t + 8], wf[2 * t + 9]);
+      }
+    }
     p.stats[NSTAT + o] = (float)mean_h;
     p.stats[NSTAT + p.Cout + o] = (float)rstd_h;
     p.stats[NSTAT + 2 * p.Cout + o] = (float)mean_d;
@@ -208,6 +220,21 @@ __global__ void __launch_bounds__(kThreads) gcn0_scores_kernel(const afb_gcn0_fw
     }
   }
   __syncthreads();
+  if (p.Aop != nullptr) {   // operands of the tensor-core apply pass: A_i[v][u] = M_i[u][v] (bf16, zero padded) + colsum
+    const int VP = p.V <= 16 ? 16 : (p.V <= 32 ? 32 : 48), AP = VP + 8;
+    bf16* Ag = reinterpret_cast<bf16*>(p.Aop) + (int64_t)n * 3 * VP * AP;
+    for (int e = threadIdx.x; e < 3 * VP * AP; e += blockDim.x) {
+      const int i = e / (VP * AP), r = e % (VP * AP), v = r / AP, u = r % AP;
+      Ag[e] = __float2bfloat16_rn((v < V && u < V) ? Ms[(i * V + u) * V + v] : 0.f);
+    }
+    for (int e = threadIdx.x; e < 3 * VP; e += blockDim.x) {
+      const int i = e / VP, v = e % VP;
+      float cs = 0.f;
+      if (v < V)
+        for (int u = 0; u < V; ++u) cs += Ms[(i * V + u) * V + v];
+      p.colsum[(int64_t)n * 3 * VP + e] = cs;
+    }
+  }
   // moments: thread (j, seg) owns moment j (12 first + 78 second) over every other position -- no shuffles
   const int mj = threadIdx.x % 90, seg = threadIdx.x / 90;
   int pa = 0, pb = 0;
@@ -265,11 +292,6 @@ __global__ void __launch_bounds__(kThreads) gcn0_scores_kernel(const afb_gcn0_fw
 // forward 3: apply
 // ---------------------------------------------------------------------------------------------
 constexpr int kARow = 24;  // bf16 elements per A-operand row (16 used): 48 B rows keep LDS.32 conflict-free
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -408,38 +430,29 @@ __global__ void __launch_bounds__(kThreads) gcn0_apply_mma_kernel(const afb_gcn0
   const int V = p.V, T = p.T;
   const int n = blockIdx.x / chunks, t0 = (blockIdx.x % chunks) * TT;
   const int tt = min(TT, T - t0);
-  float* Ms = reinterpret_cast<float*>(smraw);                 // [3*V*V] fp32 (staging for the operand build)
-  float* xs = Ms + a4(3 * V * V);                              // [TT*V*3]
+  float* xs = reinterpret_cast<float*>(smraw);                 // [TT*V*3]
   float* cs = xs + a4(TT * V * 3);                             // [9][VP] accumulator initialisers
   float* colsum = cs + 9 * VP;                                 // [3][VP]
   float* ctr = colsum + 3 * VP;                                // [16]
-  bf16* Asm = reinterpret_cast<bf16*>(ctr + 16);               // [3][VP][AP]
+  bf16* Asm = reinterpret_cast<bf16*>(ctr + 16);               // [3][VP][AP]  (built by gcn0_scores)
   bf16* stage = Asm + 3 * VP * AP;                             // [8 warps][VP][OP]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
 
-  const float* Mg = p.Mmat + (int64_t)n * 3 * V * V;
-  for (int i = threadIdx.x; i < 3 * V * V; i += blockDim.x) Ms[i] = Mg[i];
+  {
+    const uint4* Ag = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.Aop) + (int64_t)n * 3 * VP * AP);
+    uint4* As4 = reinterpret_cast<uint4*>(Asm);
+    for (int i = threadIdx.x; i < 3 * VP * AP / 8; i += blockDim.x) As4[i] = Ag[i];
+  }
   const float* xg = p.x + ((int64_t)n * T + t0) * V * 3;
   for (int i = threadIdx.x; i < tt * V * 3; i += blockDim.x) xs[i] = xg[i];
   if (threadIdx.x < 16) ctr[threadIdx.x] = threadIdx.x < NR ? p.stats[threadIdx.x] : 0.f;
+  if (threadIdx.x < 3 * VP) colsum[threadIdx.x] = p.colsum[(int64_t)n * 3 * VP + threadIdx.x];
   uint32_t bfrag[COUT / 8][2];
 #pragma unroll
   for (int nt = 0; nt < COUT / 8; ++nt) {
-    const float* wf = p.Wfold + (nt * 8 + g) * 16;
-    bfrag[nt][0] = pack2(wf[2 * t], wf[2 * t + 1]);
-    bfrag[nt][1] = pack2(wf[2 * t + 8], wf[2 * t + 9]);
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 3 * VP * AP; e += blockDim.x) {  // A_i[v][u] = M_i[u][v], zero padded
-    const int i = e / (VP * AP), r = e % (VP * AP), v = r / AP, u = r % AP;
-    Asm[e] = __float2bfloat16_rn((v < V && u < V) ? Ms[(i * V + u) * V + v] : 0.f);
-  }
-  for (int e = threadIdx.x; e < 3 * VP; e += blockDim.x) {
-    const int i = e / VP, v = e % VP;
-    float s = 0.f;
-    if (v < V)
-      for (int u = 0; u < V; ++u) s += Ms[(i * V + u) * V + v];
-    colsum[e] = s;
+    const uint2 f = reinterpret_cast<const uint2*>(p.Wfrag)[nt * 32 + lane];
+    bfrag[nt][0] = f.x;
+    bfrag[nt][1] = f.y;
   }
   __syncthreads();
   for (int e = threadIdx.x; e < 9 * VP; e += blockDim.x) {
@@ -850,10 +863,10 @@ extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
   const size_t head = ((size_t)a4(3 * V * V) + a4(TT * V * 3) + 16) * sizeof(float);
   const bool mma = !p->precise && p->y_dtype == AFB_BF16 && p->Cout == 128;
   static const bool old_apply = getenv("AFB_GCN0_APPLY_V1") != nullptr;
-  if (mma && !old_apply && V <= 48) {
-    const int TT2 = T < 8 ? T : 8, chunks2 = ceil_div(T, TT2);
+  if (mma && !old_apply && V <= 48 && p->Aop != nullptr && p->colsum != nullptr && p->Wfrag != nullptr) {
+    const int TT2 = T < 16 ? T : 16, chunks2 = ceil_div(T, TT2);
     const int VP = V <= 16 ? 16 : (V <= 32 ? 32 : 48);
-    const size_t smem2 = ((size_t)a4(3 * V * V) + a4(TT2 * V * 3) + 12 * VP + 16) * sizeof(float) + (size_t)3 * VP * (VP + 8) * 2 +
+    const size_t smem2 = ((size_t)a4(TT2 * V * 3) + 12 * VP + 16) * sizeof(float) + (size_t)3 * VP * (VP + 8) * 2 +
                          (size_t)(kThreads / 32) * VP * (128 + 8) * 2;
 #define LAUNCH_APPLY_MMA(VP_)                                                                           \
   do {                                                                                                  \

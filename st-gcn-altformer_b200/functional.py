@@ -504,8 +504,9 @@ def _gcn0_workspace(device):
     return _gcn0_ws[key]
 
 
-def _gcn0_struct(x, A, PA, mods, bufs, training, momentum, eps, Mmat, moments, stats, wfold, y):
+def _gcn0_struct(x, A, PA, mods, bufs, training, momentum, eps, Mmat, moments, stats, wfold, y, mma_ws=None):
     counter = _gcn0_workspace(x.device)[1]
+    aop, colsum, wfrag = (None, None, None) if mma_ws is None else mma_ws
     N, T, V, _ = x.shape
     wa, ba, wb, bb, wd, bd, wdn, bdn, dng, dnb, bng, bnb = mods
     dn_rm, dn_rv, bn_rm, bn_rv = bufs
@@ -515,7 +516,8 @@ def _gcn0_struct(x, A, PA, mods, bufs, training, momentum, eps, Mmat, moments, s
                         bn_b=bnb.data_ptr(), dn_g=dng.data_ptr(), dn_b=dnb.data_ptr(), bn_rm=bn_rm.data_ptr(),
                         bn_rv=bn_rv.data_ptr(), dn_rm=dn_rm.data_ptr(), dn_rv=dn_rv.data_ptr(), N=N, T=T, V=V, Cout=Cout,
                         IC=IC, training=int(training), momentum=momentum, eps=eps, Mmat=Mmat.data_ptr(),
-                        moments=moments.data_ptr(), counter=counter.data_ptr(), stats=stats.data_ptr(), Wfold=wfold.data_ptr(), y=y.data_ptr(),
+                        moments=moments.data_ptr(), counter=counter.data_ptr(), stats=stats.data_ptr(), Wfold=wfold.data_ptr(), Aop=ops.ptr(aop), colsum=ops.ptr(colsum),
+                        Wfrag=ops.ptr(wfrag), y=y.data_ptr(),
                         y_dtype=ops.dt(y), precise=int(get_precision() == "fp32"))
 
 
@@ -548,7 +550,13 @@ class Gcn0Fn(torch.autograd.Function):
         det = lambda ts: [t.detach() for t in ts]  # noqa: E731
         mods = (det(wa), det(ba), det(wb), det(bb), det(wd), det(bd), wdn.detach(), bdn.detach(), dng.detach(),
                 dnb.detach(), bng.detach(), bnb.detach())
-        st = _gcn0_struct(x, A, PA.detach(), mods, bufs, training, momentum, eps, Mmat, moments, stats, wfold, y)
+        mma_ws = None
+        if y.dtype == torch.bfloat16 and Cout == 128 and V <= 48:   # operands of the tensor-core apply pass
+            VP = 16 if V <= 16 else (32 if V <= 32 else 48)
+            mma_ws = (torch.empty((N, 3, VP, VP + 8), device=dev, dtype=torch.bfloat16),
+                      torch.empty((N, 3, VP), device=dev, dtype=torch.float32),
+                      torch.empty((Cout // 8, 32, 2), device=dev, dtype=torch.int32))
+        st = _gcn0_struct(x, A, PA.detach(), mods, bufs, training, momentum, eps, Mmat, moments, stats, wfold, y, mma_ws)
         ops._call("afb_gcn0_fwd", C.byref(st), ops.stream())
         ctx.save_for_backward(x, A, PA, Mmat, stats, wfold, y, *params, *bufs)
         ctx.cfg = (training, momentum, eps)
