@@ -48,7 +48,7 @@ template <int DH, int LP, int HG> struct Geo {
   static constexpr int O_PITCH = W + 8;
   static constexpr int S_PITCH = LP + 8;
   static constexpr int kThreads = HG * 32;
-  static constexpr size_t fwd_bytes = ((size_t)LP * QKV_PITCH + (size_t)LP * O_PITCH) * 2;
+  static constexpr size_t fwd_bytes = (size_t)LP * QKV_PITCH * 2;   // O is staged over the consumed Q rows
   static constexpr size_t bwd_bytes = ((size_t)LP * QKV_PITCH + (size_t)LP * O_PITCH + (size_t)HG * 2 * LP * S_PITCH) * 2;
 };
 
@@ -87,16 +87,19 @@ __device__ __forceinline__ void scores_softmax(const bf16* sq, int qcol, int kco
   for (int nj = 0; nj < LP / 8; ++nj)
 #pragma unroll
     for (int e = 0; e < 4; ++e) s[nj][e] = 0.f;
+  const int nt_valid = (L + 7) >> 3;   // key tiles holding at least one real key (warp-uniform)
 #pragma unroll
-  for (int n2 = 0; n2 < LP / 16; ++n2)
+  for (int n2 = 0; n2 < LP / 16; ++n2) {
+    if (2 * n2 >= nt_valid) break;
 #pragma unroll
     for (int kk = 0; kk < DH / 16; ++kk) {
       uint32_t kb[4];
       const int id = lane >> 3;
       ldsm_x4(smem_u32(sq + (n2 * 16 + (lane & 7) + (id >> 1) * 8) * PITCH + kcol + kk * 16 + (id & 1) * 8), kb);
       mma(s[2 * n2], qa[kk], kb[0], kb[1]);
-      mma(s[2 * n2 + 1], qa[kk], kb[2], kb[3]);
+      if (2 * n2 + 1 < nt_valid) mma(s[2 * n2 + 1], qa[kk], kb[2], kb[3]);
     }
+  }
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int nj = 0; nj < LP / 8; ++nj) {
@@ -157,7 +160,6 @@ __global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __res
   using G = Geo<DH, LP, HG>;
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* sq = reinterpret_cast<bf16*>(smraw);
-  bf16* so = sq + LP * G::QKV_PITCH;
   const int groups = heads / HG;
   const int64_t b = blockIdx.x / groups;
   const int h0 = (blockIdx.x % groups) * HG;
@@ -186,10 +188,11 @@ __global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __res
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
     mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(pa, sq, vcol, acc);
-    store_acc<DH / 8, G::O_PITCH>(so, mi * 16, hw * DH, acc, 1.f, 1.f);
+    __syncwarp();   // every lane has consumed this tile's Q fragments: the rows can take the output
+    store_acc<DH / 8, G::QKV_PITCH>(sq, mi * 16, qcol, acc, 1.f, 1.f);
   }
   __syncthreads();
-  store_tile<G::W, G::O_PITCH>(o + b * L * D + h0 * DH, D, so, L, G::kThreads);
+  store_tile<G::W, G::QKV_PITCH>(o + b * L * D + h0 * DH, D, sq, L, G::kThreads);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -227,15 +230,18 @@ __global__ void __launch_bounds__(HG * 32) attn_bwd_mma_kernel(const bf16* __res
     for (int nj = 0; nj < LP / 8; ++nj)
 #pragma unroll
       for (int e = 0; e < 4; ++e) dp[nj][e] = 0.f;
+    const int nt_valid = (L + 7) >> 3;   // key tiles with at least one real key; P is exactly 0 beyond them
 #pragma unroll
-    for (int n2 = 0; n2 < LP / 16; ++n2)
+    for (int n2 = 0; n2 < LP / 16; ++n2) {
+      if (2 * n2 >= nt_valid) break;
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {  // dP = dO V^T : B[k = d][n = key] = V[key][d] (non-transposed load)
         uint32_t vb[4];
         ldsm_x4(smem_u32(sq + (n2 * 16 + (lane & 7) + (id >> 1) * 8) * G::QKV_PITCH + vcol + kk * 16 + (id & 1) * 8), vb);
         mma(dp[2 * n2], da[kk], vb[0], vb[1]);
-        mma(dp[2 * n2 + 1], da[kk], vb[2], vb[3]);
+        if (2 * n2 + 1 < nt_valid) mma(dp[2 * n2 + 1], da[kk], vb[2], vb[3]);
       }
+    }
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
     for (int nj = 0; nj < LP / 8; ++nj) {
