@@ -60,11 +60,16 @@ __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t ld
   for (int idx = threadIdx.x; idx < total; idx += nthreads) {
     const int row = idx / (PARTS * C16), rem = idx % (PARTS * C16);
     const int part = rem / C16, c = rem % C16;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row < L) v = *reinterpret_cast<const uint4*>(src + row * ld + part * part_stride + c * 8);
-    *reinterpret_cast<uint4*>(dst + row * PITCH + part * W + c * 8) = v;
+    bf16* d = dst + row * PITCH + part * W + c * 8;
+    if (row < L)   // asynchronous 16-byte copies: every chunk of the tile is in flight at once (cp_async_wait_all below)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d)),
+                   "l"(src + row * ld + part * part_stride + c * 8)
+                   : "memory");
+    else
+      *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 template <int W, int PITCH>
 __device__ __forceinline__ void store_tile(bf16* dst, int64_t ld, const bf16* src, int L, int nthreads) {
   constexpr int C16 = W / 8;
@@ -165,6 +170,7 @@ __global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __res
   const int h0 = (blockIdx.x % groups) * HG;
   const int D = heads * DH;
   load_tile<G::W, G::QKV_PITCH, 3>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L, LP, G::kThreads);
+  cp_async_wait_all();
   __syncthreads();
   const int hw = threadIdx.x >> 5;
   const int qcol = hw * DH, kcol = G::W + hw * DH, vcol = 2 * G::W + hw * DH;
@@ -212,6 +218,7 @@ __global__ void __launch_bounds__(HG * 32) attn_bwd_mma_kernel(const bf16* __res
   const int D = heads * DH;
   load_tile<G::W, G::QKV_PITCH, 3>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L, LP, G::kThreads);
   load_tile<G::W, G::O_PITCH, 1>(sdo, dO + b * L * D + h0 * DH, D, 0, L, LP, G::kThreads);
+  cp_async_wait_all();
   __syncthreads();
   const int qcol = hw * DH, kcol = G::W + hw * DH, vcol = 2 * G::W + hw * DH, ocol = hw * DH;
   const float scale_log2 = scale * 1.4426950408889634f;

@@ -125,6 +125,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// same load without the wait: lets several loads (and global loads) be in flight before one tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // Shared-memory matrix descriptor (sm_100 format): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 |
 // SWIZZLE_128B (2) <<61.   K-major tiles: rows of 128 B, 8-row groups 1024 B apart (SBO).
 // MN-major tiles: 64-element (128 B) MN runs, 8 k-rows per 1024 B atom (SBO), next 64 MN at LBO.
@@ -227,6 +242,7 @@ struct TnArgs {
   int rows_per_batch, batches, N;
   int kb_per_tap, tap_row_stride, tap_pad;
   int out_dtype, act, has_c2;
+  int epi_kind;   // EPI_*: compile-time specialised epilogue for the hot bf16 combinations, else EPI_GENERIC
   float alpha;
   const float* bias;
   const float* pos;
@@ -271,6 +287,183 @@ struct TileWalk {
     }
   }
 };
+
+// Specialised epilogues.  The runtime-flag epilogue in the kernel body costs ~290 instructions per 32-column
+// chunk (ncu r01: 11% FFMA, >40% flag tests / branches / uniform moves) and, with two epilogue warps per
+// scheduler, made every K <= 512 linear epilogue-issue bound.  The hot bf16 combinations get a straight-line
+// version: one 128-byte output unit (64 columns) per step, both TMEM loads and the residual / aux row loads in
+// flight together, no per-chunk flag tests.
+enum { EPI_GENERIC = 0, EPI_BIAS, EPI_BIAS_RES, EPI_BIAS_GELU_C2, EPI_GELU_BWD, EPI_PLAIN };
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& r, float* o) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o[2 * j] = __uint_as_float(w[j] << 16);
+    o[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+
+// 8 consecutive columns of this thread's row -> bf16 -> 16-byte chunk q of the 128B-swizzled staging row
+__device__ __forceinline__ void sts_pack8(uint8_t* rowp, int q, int lane, const float* x) {
+  uint32_t wv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+    wv[j] = *reinterpret_cast<uint32_t*>(&h2);
+  }
+  *reinterpret_cast<uint4*>(rowp + ((q ^ (lane & 7)) * 16)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+}
+// the previous TMA store of this warp must have finished reading the staging buffer before it is rewritten
+__device__ __forceinline__ void staging_acquire(int lane) {
+  if (lane == 0) bulk_wait_read0();
+  __syncwarp();
+}
+// hand the staged [32 rows x 128 B] unit to the TMA store engine
+__device__ __forceinline__ void staging_store(uint32_t stage_addr, int lane, const CUtensorMap* map, int col, int row0, int batch) {
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(map, stage_addr, col, row0, batch);
+    bulk_commit();
+  }
+}
+
+// The whole epilogue-warp loop for one specialised kind.  Residual / aux rows are software-pipelined one output
+// unit ahead in registers (raw_next), on top of the L2 prefetch one tile ahead: the row loads of a unit are in
+// flight while the previous unit is converted, staged and stored, instead of being waited for right after issue.
+template <int BN, bool STAT, int KIND>
+__device__ __forceinline__ void epi_fast_loop(const TnArgs& p, const CUtensorMap* tmC, const CUtensorMap* tmC2, uint32_t tmem_base,
+                                              uint32_t tfull0, uint32_t tempty0, uint8_t* stage_ptr, uint32_t stage_addr, int lane,
+                                              int lane_grp, int half) {
+  constexpr bool kBias = KIND == EPI_BIAS || KIND == EPI_BIAS_RES || KIND == EPI_BIAS_GELU_C2;
+  constexpr bool kRes = KIND == EPI_BIAS_RES;
+  constexpr bool kAux = KIND == EPI_GELU_BWD;
+  constexpr bool kRow = kRes || kAux;   // reads one bf16 row operand per output element
+  constexpr bool kScale = KIND == EPI_BIAS_RES || KIND == EPI_GELU_BWD || KIND == EPI_PLAIN;
+  constexpr int UNITS = BN / 64;
+  uint8_t* rowp = stage_ptr + lane * 128;
+  const bf16* rsrc = reinterpret_cast<const bf16*>(kRes ? p.residual : p.aux);
+  const int ldr = kRes ? p.ldres : p.ldaux;
+
+  // address of this thread's row operand for unit u of tile t (nullptr: row beyond the batch)
+  auto row_ptr = [&](const TileWalk<STAT>& t, int u) -> const uint4* {
+    const int rl = (t.mt % p.m_tiles_per_batch) * BM + lane_grp * 32 + lane;
+    if (rl >= p.rows_per_batch) return nullptr;
+    const int64_t r = (int64_t)(t.mt / p.m_tiles_per_batch) * p.rows_per_batch + rl;
+    return reinterpret_cast<const uint4*>(rsrc + r * ldr + t.n_blk * BN + u * 64);
+  };
+  auto l2_prefetch = [&](const TileWalk<STAT>& t) {
+    if (!kRow) return;
+    for (int u = half; u < UNITS; u += 2) {
+      const uint4* ptr = row_ptr(t, u);
+      if (ptr != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+  };
+  auto issue = [&](uint4* r, const uint4* ptr) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r[q] = ptr != nullptr ? __ldg(ptr + q) : make_uint4(0u, 0u, 0u, 0u);
+  };
+
+  TileWalk<STAT> w(p);
+  uint4 raw_next[kRow ? 8 : 1];
+  if (kRow && w.valid() && half < UNITS) {
+    l2_prefetch(w);
+    issue(raw_next, row_ptr(w, half));
+  }
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (; w.valid(); w.next()) {
+    const int batch = w.mt / p.m_tiles_per_batch;
+    const int row_in_batch0 = (w.mt % p.m_tiles_per_batch) * BM + lane_grp * 32;
+    const bool valid = row_in_batch0 + lane < p.rows_per_batch;
+    const int64_t row = (int64_t)batch * p.rows_per_batch + row_in_batch0 + lane;
+    const int ncol0 = w.n_blk * BN;
+    TileWalk<STAT> wn = w;
+    wn.next();
+    if (wn.valid()) l2_prefetch(wn);
+    float rscale = 1.f;
+    if (kScale && p.row_scale != nullptr && valid) rscale = p.row_scale[row / p.row_scale_div];
+    const uint32_t tmem_tile = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
+    mbar_wait(tfull0 + 8u * acc, acc_phase);
+    tc_fence_after();
+    bool arrived = false;
+#pragma unroll 1
+    for (int u = half; u < UNITS; u += 2) {
+      const int n0 = ncol0 + u * 64;
+      uint4 raw[kRow ? 8 : 1];
+      if (kRow) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) raw[q] = raw_next[q];
+        if (u + 2 < UNITS) issue(raw_next, row_ptr(w, u + 2));
+        else if (wn.valid()) issue(raw_next, row_ptr(wn, half));
+      }
+      float pre[KIND == EPI_BIAS_GELU_C2 ? 64 : 1];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {   // two 32-column TMEM loads per unit keep the live register set small
+        uint32_t av[32];
+        tmem_ld32_issue(tmem_tile + (uint32_t)(u * 64 + c * 32), av);
+        tmem_wait_ld();
+        if (c == 1 && u + 2 >= UNITS) {   // this warp's last TMEM read of the accumulator stage
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+          arrived = true;
+        }
+        if (c == 0) staging_acquire(lane);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int q = c * 4 + q4;
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(av[8 * q4 + i]);
+          if (kBias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * q);
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * q + 1);
+            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+          }
+          if (KIND == EPI_BIAS_GELU_C2) {   // pre-activation goes out first; keep it for the GELU round below
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pre[8 * q + i] = x[i];
+          }
+          if (kAux) {
+            float t[8];
+            unpack_bf16x8(raw[q], t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] *= gelu_fast_grad_f(t[i]);
+          }
+          if (kScale && p.row_scale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] *= rscale;
+          }
+          if (kRes) {
+            float t[8];
+            unpack_bf16x8(raw[q], t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] += t[i];
+          }
+          sts_pack8(rowp, q, lane, x);
+        }
+      }
+      staging_store(stage_addr, lane, KIND == EPI_BIAS_GELU_C2 ? tmC2 : tmC, n0, row_in_batch0, batch);
+      if (KIND == EPI_BIAS_GELU_C2) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) pre[i] = gelu_fast_f(pre[i]);   // overlaps the store's smem read
+        staging_acquire(lane);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sts_pack8(rowp, q, lane, pre + 8 * q);
+        staging_store(stage_addr, lane, tmC, n0, row_in_batch0, batch);
+      }
+    }
+    if (!arrived) {   // BN == 64: the odd warp of each lane quarter has no unit
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+  }
+}
 
 template <int BN, bool B_MN, bool STAT>
 __global__ void __launch_bounds__(kTnThreads, 1)
@@ -408,9 +601,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool out_bf16 = p.out_dtype == AFB_BF16;
     const int ncl = out_bf16 ? 2 : 1;          // tcgen05.ld chunks per 128-byte staging row
     const int units = BN / (32 * ncl);
+    if (p.epi_kind != EPI_GENERIC) {
+#define AFB_EPI_FAST(KIND) \
+  epi_fast_loop<BN, STAT, KIND>(p, &tmC, &tmC2, tmem_base, tfull_bar(0), tempty_bar(0), my_stage_ptr, my_stage, lane, lane_grp, half)
+      switch (p.epi_kind) {
+        case EPI_BIAS: AFB_EPI_FAST(EPI_BIAS); break;
+        case EPI_BIAS_RES: AFB_EPI_FAST(EPI_BIAS_RES); break;
+        case EPI_BIAS_GELU_C2: AFB_EPI_FAST(EPI_BIAS_GELU_C2); break;
+        case EPI_GELU_BWD: AFB_EPI_FAST(EPI_GELU_BWD); break;
+        default: AFB_EPI_FAST(EPI_PLAIN); break;
+      }
+#undef AFB_EPI_FAST
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (TileWalk<STAT> w(p); w.valid(); w.next()) {
+    bool first_tile = true;
+    auto prefetch_tile = [&](const TileWalk<STAT>& t) {
+      if (p.residual == nullptr && p.aux == nullptr) return;
+      const int rl = (t.mt % p.m_tiles_per_batch) * BM + lane_grp * 32 + lane;
+      if (rl >= p.rows_per_batch) return;
+      const int64_t r = (int64_t)(t.mt / p.m_tiles_per_batch) * p.rows_per_batch + rl;
+      for (int u = half; u < units; u += 2) {
+        const int n0 = t.n_blk * BN + u * 32 * ncl;
+        if (p.residual != nullptr) prefetch_row(p.residual, r * p.ldres + n0, p.res_dtype, 32 * ncl);
+        if (p.aux != nullptr) prefetch_row(p.aux, r * p.ldaux + n0, p.aux_dtype, 32 * ncl);
+      }
+    };
+    for (TileWalk<STAT> w(p); p.epi_kind == EPI_GENERIC && w.valid(); w.next()) {
       const int batch = w.mt / p.m_tiles_per_batch;
       const int m0 = (w.mt % p.m_tiles_per_batch) * BM;
       const int row_in_batch0 = m0 + lane_grp * 32;
@@ -418,9 +635,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = row_local < p.rows_per_batch;
       const int64_t row = (int64_t)batch * p.rows_per_batch + row_local;
       const int ncol0 = w.n_blk * BN;
-      if (valid) {  // warm L2 with this row's epilogue operands while the accumulator is being produced
-        if (p.residual != nullptr) prefetch_row(p.residual, row * p.ldres + ncol0, p.res_dtype, BN);
-        if (p.aux != nullptr) prefetch_row(p.aux, row * p.ldaux + ncol0, p.aux_dtype, BN);
+      // Warm L2 with the epilogue operands (residual / aux rows) ONE TILE AHEAD: the per-thread row loads below
+      // only keep ~16 KB in flight per SM, which caps an HBM-latency stream at ~1.2 TB/s; as L2 hits they run
+      // at several TB/s.  Each warp prefetches the 128-byte units it will read itself.
+      if (first_tile) {
+        prefetch_tile(w);
+        first_tile = false;
+      }
+      {
+        TileWalk<STAT> wn = w;
+        wn.next();
+        if (wn.valid()) prefetch_tile(wn);
       }
       float rscale = 1.f;
       if (p.row_scale != nullptr && valid) rscale = p.row_scale[row / p.row_scale_div];
@@ -887,6 +1112,16 @@ extern "C" int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s) {
   a.aux = p->aux; a.aux_dtype = p->aux_dtype; a.ldaux = p->ldaux;
   a.residual = p->residual; a.res_dtype = p->res_dtype; a.ldres = p->ldres;
   a.row_scale = p->row_scale; a.row_scale_div = p->row_scale_div > 0 ? p->row_scale_div : 1;
+  a.epi_kind = EPI_GENERIC;
+  static const bool no_fast_epi = getenv("AFB_GEMM_GENERIC_EPI") != nullptr;
+  if (!no_fast_epi && p->out_dtype == AFB_BF16 && p->alpha == 1.f && p->pos == nullptr) {
+    const bool res = p->residual != nullptr, bias = p->bias != nullptr, rs = p->row_scale != nullptr;
+    if (p->act == AFB_ACT_NONE && bias && !res && !rs) a.epi_kind = EPI_BIAS;
+    else if (p->act == AFB_ACT_NONE && bias && res && p->res_dtype == AFB_BF16) a.epi_kind = EPI_BIAS_RES;
+    else if (p->act == AFB_ACT_GELU && bias && a.has_c2 && !res && !rs) a.epi_kind = EPI_BIAS_GELU_C2;
+    else if (p->act == AFB_ACT_GELU_BWD && !bias && !res && p->aux != nullptr && p->aux_dtype == AFB_BF16) a.epi_kind = EPI_GELU_BWD;
+    else if (p->act == AFB_ACT_NONE && !bias && !res) a.epi_kind = EPI_PLAIN;
+  }
   AFB_REQUIRE(p->act != AFB_ACT_GELU_BWD || p->aux != nullptr, "gemm_tn: GELU_BWD needs aux");
   AFB_REQUIRE(p->act != AFB_ACT_GELU_BWD || p->residual == nullptr, "gemm_tn: GELU_BWD cannot be combined with a residual");
 

@@ -1,5 +1,6 @@
 """Time the tcgen05 GEMMs on the cfg2 shapes (M = 256*32*22 tokens) with CUDA events, and serve as the
-target of `ncu --set full` captures.  Usage: python tools/prof_gemm.py [iters]"""
+target of `ncu --set full` captures
+(PROF_ONCE=1 + `ncu --profile-from-start off`: one captured launch per shape).  Usage: python tools/prof_gemm.py [iters]"""
 import os
 import sys
 
@@ -15,10 +16,20 @@ dev = "cuda"
 torch.manual_seed(0)
 
 
+ONCE = os.environ.get("PROF_ONCE") == "1"   # ncu --profile-from-start off: capture exactly one launch per shape
+
+
 def bench(name, fn, flops, bytes_):
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
+    if ONCE:
+        torch.cuda.profiler.start()
+        fn()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(f"{name:44s} captured", flush=True)
+        return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
