@@ -783,17 +783,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// dW kernel: contraction over rows.  A = G^T (MN-major, M-dim = N1 tile of 128), B = X^T (MN-major,
-// N-dim = N2 tile of BN2).  Each CTA owns one (n1 tile, n2 tile, row-split) and accumulates its row
-// blocks in TMEM, then adds its partial into dW with fp32 atomics.
+// dW kernel: contraction over rows.  A = G^T (MN-major, M-dim = N1 tile), B = X^T (MN-major, N-dim = N2 tile
+// of BN2).  Each CTA owns one (n1 tile, n2 tile, row-split), accumulates its row blocks in TMEM and adds its
+// partial into dW with fp32 atomics.
+//   BN1 = 256 (N1 % 256 == 0): two M=128 accumulators share every X tile -- the kernel is bound by the L2->SM
+//   fill (~6300 B/clk chip-wide), and a 256 x 256 tile moves 64 KB per 64-row block instead of 2 x 48 KB.
+//   TMEM is then full (2 x 256 columns), so the bias gradient (column sums of G) is accumulated by the
+//   otherwise idle epilogue warps straight from the G tiles in shared memory.
+//   BN1 = 128: one accumulator; the bias gradient rides on one extra N=16 MMA against an all-ones tile.
 // ---------------------------------------------------------------------------------------------
-template <int BN2> struct DwCfg {
-  static constexpr int kStages = BN2 >= 256 ? 4 : 6;
-  static constexpr int kABytes = 64 * 128 * 2;      // 64 rows x 128 n1
+template <int BN1, int BN2> struct DwCfg {
+  static constexpr int kABytes = 64 * BN1 * 2;      // 64 rows x BN1 n1
   static constexpr int kBBytes = 64 * BN2 * 2;      // 64 rows x BN2 n2
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // accumulator columns [0, BN2) hold dW; columns [BN2, BN2 + 16) hold G^T * ones (the bias gradient)
-  static constexpr int kTmemCols = BN2 >= 256 ? 512 : (BN2 >= 128 ? 256 : 128);
+  static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;
+  static constexpr bool kOnesTrick = BN1 == 128;
+  // BN1 == 128: accumulator columns [0, BN2) hold dW, [BN2, BN2 + 16) hold G^T * ones (the bias gradient)
+  static constexpr int kUsedCols = kOnesTrick ? BN2 + 16 : 2 * BN2;
+  static constexpr int kTmemCols = kUsedCols > 256 ? 512 : (kUsedCols > 128 ? 256 : 128);
   static constexpr int kScratchBytes = kEpiWarps * 32 * kScratchStride * 4;
   static constexpr int kOnesBytes = 8192;           // one all-ones [64 x 64] bf16 tile (MN-major B operand)
   static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + kOnesBytes + 256 + 1024;
@@ -810,10 +817,10 @@ struct DwArgs {
   float* dbias;   // optional: dbias[n1] += alpha * sum_m G[m, n1]
 };
 
-template <int BN2>
+template <int BN1, int BN2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const DwArgs p) {
-  using Cfg = DwCfg<BN2>;
+  using Cfg = DwCfg<BN1, BN2>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -842,9 +849,10 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   const int rb_begin = split * per;
   const int rb_end = min(rb_begin + per, p.total_row_blocks);
   const int n_rb = max(rb_end - rb_begin, 0);
-  // the CTAs of the first n2 tile also reduce G over rows (bias gradient) with one extra N=16 MMA per k-step
+  // the CTAs of the first n2 tile also reduce G over rows (bias gradient)
   const bool do_bias = p.dbias != nullptr && n2_blk == 0;
-  if (do_bias) {
+  const bool smem_bias = do_bias && !Cfg::kOnesTrick;
+  if (do_bias && Cfg::kOnesTrick) {
     uint32_t* ones = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kScratchBytes);
     for (int i = threadIdx.x; i < Cfg::kOnesBytes / 4; i += blockDim.x) ones[i] = 0x3f803f80u;  // bf16 1.0 pairs
     fence_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
@@ -855,7 +863,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), smem_bias ? 1 + kEpiWarps : 1);   // MMA commit (+ the column-sum warps)
     }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
@@ -877,8 +885,8 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-            tma_load_3d(&tmG, full_bar(stage), sA + stage * Cfg::kABytes + j * 8192, n1_blk * 128 + j * 64, r0, batch);
+          for (int j = 0; j < BN1 / 64; ++j)
+            tma_load_3d(&tmG, full_bar(stage), sA + stage * Cfg::kABytes + j * 8192, n1_blk * BN1 + j * 64, r0, batch);
 #pragma unroll
           for (int j = 0; j < BN2 / 64; ++j)
             tma_load_3d(&tmX, full_bar(stage), sB + stage * Cfg::kBBytes + j * 8192, n2_blk * BN2 + j * 64, r0 + p.x_row_shift, batch);
@@ -898,10 +906,14 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           const uint32_t b_addr = sB + stage * Cfg::kBBytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 16 contraction rows per MMA = two 8-row atoms
-            const uint64_t adesc = make_desc(a_addr + k * 2048, 8192, 1024);
             const uint64_t bdesc = make_desc(b_addr + k * 2048, 8192, 1024);
-            umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
-            if (do_bias) umma_bf16(tmem_base + BN2, adesc, make_desc(sOnes, 8192, 1024), idesc_ones, (i | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int h = 0; h < BN1 / 128; ++h) {   // 128 n1 columns = two 64-column boxes per accumulator
+              const uint64_t adesc = make_desc(a_addr + h * 16384 + k * 2048, 8192, 1024);
+              umma_bf16(tmem_base + (uint32_t)(h * BN2), adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+              if (Cfg::kOnesTrick && do_bias)
+                umma_bf16(tmem_base + BN2, adesc, make_desc(sOnes, 8192, 1024), idesc_ones, (i | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
@@ -911,28 +923,55 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
     } else {
       const int ew = warp - 2;
       const int lane_grp = warp & 3;
+      if (smem_bias) {
+        // column sums of the G tiles while the MMAs run: thread = one bf16 pair (2 of the 256 n1 columns),
+        // 64 rows per stage, 128-byte rows with the 16-byte chunk index XOR (row & 7) (SWIZZLE_128B)
+        const int box = ew, word = lane;           // 4 warps x 32 lanes x 2 columns = 256
+        float s0 = 0.f, s1 = 0.f;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < n_rb; ++i) {
+          mbar_wait(full_bar(stage), phase);
+          const uint8_t* g = smem + stage * Cfg::kABytes + box * 8192 + (word & 3) * 4;
+#pragma unroll 16
+          for (int r = 0; r < 64; ++r) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(g + r * 128 + (((word >> 2) ^ (r & 7)) << 4));
+            s0 += __uint_as_float(v << 16);
+            s1 += __uint_as_float(v & 0xffff0000u);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        const int n1 = n1_blk * BN1 + box * 64 + word * 2;
+        if (n1 < p.N1) atomicAdd(p.dbias + n1, p.alpha * s0);
+        if (n1 + 1 < p.N1) atomicAdd(p.dbias + n1 + 1, p.alpha * s1);
+      }
       float* my = scratch + ew * 32 * kScratchStride;
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
-      for (int ch = 0; ch < BN2 / 32; ++ch) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(ch * 32), v);
+#pragma unroll 1
+      for (int h = 0; h < BN1 / 128; ++h) {
+        for (int ch = 0; ch < BN2 / 32; ++ch) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(h * BN2 + ch * 32), v);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(my + lane * kScratchStride + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        __syncwarp();
-        const int n2 = n2_blk * BN2 + ch * 32 + lane;
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(my + lane * kScratchStride + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+          const int n2 = n2_blk * BN2 + ch * 32 + lane;
 #pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const int n1 = n1_blk * 128 + lane_grp * 32 + r;
-          if (n1 < p.N1 && n2 < p.N2) atomicAdd(p.dW + n1 * p.ld1 + n2 * p.ld2, p.alpha * my[r * kScratchStride + lane]);
+          for (int r = 0; r < 32; ++r) {
+            const int n1 = n1_blk * BN1 + h * 128 + lane_grp * 32 + r;
+            if (n1 < p.N1 && n2 < p.N2) atomicAdd(p.dW + n1 * p.ld1 + n2 * p.ld2, p.alpha * my[r * kScratchStride + lane]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
-      if (do_bias) {   // column BN2 of the accumulator = sum over this CTA's rows of G[:, n1]
+      if (Cfg::kOnesTrick && do_bias) {   // column BN2 of the accumulator = sum over this CTA's rows of G[:, n1]
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)BN2, v);
-        const int n1 = n1_blk * 128 + lane_grp * 32 + lane;
+        const int n1 = n1_blk * BN1 + lane_grp * 32 + lane;
         if (n1 < p.N1) atomicAdd(p.dbias + n1, p.alpha * v[0]);
       }
     }
@@ -1029,12 +1068,12 @@ int launch_tn_stat(bool stat, const CUtensorMap& tmA, const CUtensorMap& tmB, co
   return stat ? launch_tn<BN, B_MN, true>(tmA, tmB, tmC, tmC2, a, st) : launch_tn<BN, B_MN, false>(tmA, tmB, tmC, tmC2, a, st);
 }
 
-template <int BN2>
+template <int BN1, int BN2>
 int launch_dw(const CUtensorMap& tmG, const CUtensorMap& tmX, const DwArgs& a, cudaStream_t st) {
-  using Cfg = DwCfg<BN2>;
+  using Cfg = DwCfg<BN1, BN2>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_dw_kernel<BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_dw_kernel<BN1, BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("gemm_dw: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
@@ -1042,7 +1081,7 @@ int launch_dw(const CUtensorMap& tmG, const CUtensorMap& tmX, const DwArgs& a, c
     configured = true;
   }
   const int grid = a.n1_tiles * a.n2_tiles * a.splits;
-  gemm_dw_kernel<BN2><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmG, tmX, a);
+  gemm_dw_kernel<BN1, BN2><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmG, tmX, a);
   return check_launch("gemm_dw");
 }
 
@@ -1159,13 +1198,17 @@ extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
   AFB_REQUIRE(p->ldg % 8 == 0 && p->ldx % 8 == 0, "gemm_dw: leading dims must be 16-byte aligned");
   AFB_REQUIRE(((uintptr_t)p->G & 15) == 0 && ((uintptr_t)p->X & 15) == 0, "gemm_dw: operands must be 16-byte aligned");
   const int BN2 = (p->N2 % 256 == 0) ? 256 : (p->N2 % 128 == 0 ? 128 : 64);
+  static const bool no_wide = getenv("AFB_DW_BN1_128") != nullptr;
+  const int BN1 = (!no_wide && p->N1 % 256 == 0) ? 256 : 128;
   DwArgs a;
-  a.n1_tiles = ceil_div(p->N1, 128);
+  a.n1_tiles = ceil_div(p->N1, BN1);
   a.n2_tiles = p->N2 / BN2;
   a.row_blocks_per_batch = ceil_div(p->rows_per_batch, 64);
   a.total_row_blocks = a.row_blocks_per_batch * p->batches;
   const int tiles = a.n1_tiles * a.n2_tiles;
-  int splits = (2 * num_sms()) / tiles;
+  // one CTA per SM (the smem ring takes ~200 KB): 256-wide tiles run as ONE wave, each CTA paying the pipeline
+  // fill and the atomic epilogue once; the narrower tiles keep two waves (shorter tails for the conv shapes)
+  int splits = ((BN1 == 256 ? 1 : 2) * num_sms()) / tiles;
   if (splits < 1) splits = 1;
   if (splits > a.total_row_blocks) splits = a.total_row_blocks;
   // keep at least 8 row blocks per split so the atomic epilogue is amortised
@@ -1182,7 +1225,12 @@ extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
                 (uint64_t)p->rows_per_batch * p->ldx, 64, 64, 3);
   if (rc) return rc;
   cudaStream_t st = as_stream(s);
-  if (BN2 == 256) return launch_dw<256>(tmG, tmX, a, st);
-  if (BN2 == 128) return launch_dw<128>(tmG, tmX, a, st);
-  return launch_dw<64>(tmG, tmX, a, st);
+  if (BN1 == 256) {
+    if (BN2 == 256) return launch_dw<256, 256>(tmG, tmX, a, st);
+    if (BN2 == 128) return launch_dw<256, 128>(tmG, tmX, a, st);
+    return launch_dw<256, 64>(tmG, tmX, a, st);
+  }
+  if (BN2 == 256) return launch_dw<128, 256>(tmG, tmX, a, st);
+  if (BN2 == 128) return launch_dw<128, 128>(tmG, tmX, a, st);
+  return launch_dw<128, 64>(tmG, tmX, a, st);
 }

@@ -333,7 +333,8 @@ def grp_gemm_dw():
             dW = torch.zeros(N1, N2, device=DEV)
             ops.gemm_dw(G, X, dW)
             report(f"gemm_dw M={M} N1={N1} N2={N2}", dW, G.float().t() @ X.float(), 2e-3)
-        for (M, N1, N2) in ((1000, 256, 256), (5000, 768, 256), (700, 512, 1024), (900, 96, 128)):   # fused bias gradient
+        for (M, N1, N2) in ((1000, 256, 256), (5000, 768, 256), (700, 512, 1024), (900, 96, 128), (30000, 256, 128), (2000, 256, 64),
+                           (180224, 512, 256)):   # fused bias gradient
             G, X = g(M, N1, seed=5, scale=0.1, dtype=torch.bfloat16), g(M, N2, seed=6, dtype=torch.bfloat16)
             dW, db = torch.zeros(N1, N2, device=DEV), torch.zeros(N1, device=DEV)
             ops.gemm_dw(G, X, dW, dbias=db)

@@ -60,6 +60,12 @@ bench("dX    mn 768->256", lambda: ops.gemm_tn(g768, wqkv, 256, b_mn_major=True)
 bench("dpre  mn 256->512 gelu_bwd", lambda: ops.gemm_tn(x256, wfc2, 512, b_mn_major=True, act=ops.ACT_GELU_BWD, aux=x512),
       2 * M * 256 * 512, M * (256 + 1024) * 2)
 bench("dW    768x256", lambda: ops.gemm_dw(g768, x256, dW), 2 * M * 768 * 256, M * 1024 * 2)
+db768, db512, db256 = torch.zeros(768, device=dev), torch.zeros(512, device=dev), torch.zeros(256, device=dev)
+dW2, dW3, dW4 = torch.zeros(256, 256, device=dev), torch.zeros(512, 256, device=dev), torch.zeros(256, 512, device=dev)
+bench("dW    768x256 +dbias (qkv)", lambda: ops.gemm_dw(g768, x256, dW, dbias=db768), 2 * M * 768 * 256, M * 1024 * 2)
+bench("dW    256x256 +dbias (proj)", lambda: ops.gemm_dw(res, x256, dW2, dbias=db256), 2 * M * 256 * 256, M * 512 * 2)
+bench("dW    512x256 +dbias (fc1)", lambda: ops.gemm_dw(g512, x256, dW3, dbias=db512), 2 * M * 512 * 256, M * 768 * 2)
+bench("dW    256x512 +dbias (fc2)", lambda: ops.gemm_dw(res, x512, dW4, dbias=db256), 2 * M * 512 * 256, M * 768 * 2)
 x128 = mk(M, 128)
 wconv = mk(128, 9 * 128, s=0.03)
 bench("conv  9x1 128->128", lambda: ops.gemm_tn(x128, wconv, 128, k_per_tap=128, taps=9, tap_row_stride=22, tap_pad=4, rows_per_batch=704,
