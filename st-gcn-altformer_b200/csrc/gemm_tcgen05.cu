@@ -815,6 +815,7 @@ struct DwArgs {
   long long ld1, ld2;
   float alpha;
   float* dbias;   // optional: dbias[n1] += alpha * sum_m G[m, n1]
+  int vec4;       // ld2 == 1 and 16-byte aligned rows: the epilogue uses red.global.add.v4.f32
 };
 
 template <int BN1, int BN2>
@@ -959,11 +960,26 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(my + lane * kScratchStride + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           __syncwarp();
-          const int n2 = n2_blk * BN2 + ch * 32 + lane;
+          if (p.vec4) {   // dW rows contiguous in n2: 16-byte vector reductions, 8 lanes per row, 4 rows per instruction
+            const int c4 = (lane & 7) * 4;
+            const int n2 = n2_blk * BN2 + ch * 32 + c4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + (lane >> 3);
+              const int n1 = n1_blk * BN1 + h * 128 + lane_grp * 32 + r;
+              const float4 v4 = *reinterpret_cast<const float4*>(my + r * kScratchStride + c4);
+              if (n1 < p.N1)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dW + n1 * p.ld1 + n2), "f"(p.alpha * v4.x),
+                             "f"(p.alpha * v4.y), "f"(p.alpha * v4.z), "f"(p.alpha * v4.w)
+                             : "memory");
+            }
+          } else {
+            const int n2 = n2_blk * BN2 + ch * 32 + lane;
 #pragma unroll 4
-          for (int r = 0; r < 32; ++r) {
-            const int n1 = n1_blk * BN1 + h * 128 + lane_grp * 32 + r;
-            if (n1 < p.N1 && n2 < p.N2) atomicAdd(p.dW + n1 * p.ld1 + n2 * p.ld2, p.alpha * my[r * kScratchStride + lane]);
+            for (int r = 0; r < 32; ++r) {
+              const int n1 = n1_blk * BN1 + h * 128 + lane_grp * 32 + r;
+              if (n1 < p.N1 && n2 < p.N2) atomicAdd(p.dW + n1 * p.ld1 + n2 * p.ld2, p.alpha * my[r * kScratchStride + lane]);
+            }
           }
           __syncwarp();
         }
@@ -1217,6 +1233,7 @@ extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
   a.splits = splits;
   a.N1 = p->N1; a.N2 = p->N2; a.x_row_shift = p->x_row_shift;
   a.dW = p->dW; a.ld1 = p->ld1; a.ld2 = p->ld2; a.alpha = p->alpha; a.dbias = p->dbias;
+  a.vec4 = (p->ld2 == 1 && p->ld1 % 4 == 0 && ((uintptr_t)p->dW & 15) == 0) ? 1 : 0;
   CUtensorMap tmG, tmX;
   int rc = make_map(&tmG, p->G, (uint64_t)p->N1, (uint64_t)p->rows_per_batch, (uint64_t)p->batches, (uint64_t)p->ldg,
                     (uint64_t)p->rows_per_batch * p->ldg, 64, 64, 3);
