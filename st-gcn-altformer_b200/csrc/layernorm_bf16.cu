@@ -46,35 +46,52 @@ __global__ void __launch_bounds__(kBlock) ln_fwd_bf16_kernel(const bf16* __restr
     load8f(gamma + c * 256 + lane * 8, g[c]);
     load8f(beta + c * 256 + lane * 8, b[c]);
   }
-  for (int64_t row = warp0; row < rows; row += nwarps) {
-    float v[NC][8];
-    float s = 0.f;
+  // two rows per iteration: both rows' loads are issued before either reduction starts (twice the bytes in flight)
+  for (int64_t row = warp0; row < rows; row += 2 * nwarps) {
+    const int64_t row2 = row + nwarps;
+    const bool has2 = row2 < rows;
+    uint4 ra[NC], rb[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      unpack8(*reinterpret_cast<const uint4*>(x + row * D + c * 256 + lane * 8), v[c]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s += v[c][i];
+      ra[c] = *reinterpret_cast<const uint4*>(x + row * D + c * 256 + lane * 8);
+      rb[c] = has2 ? *reinterpret_cast<const uint4*>(x + row2 * D + c * 256 + lane * 8) : make_uint4(0u, 0u, 0u, 0u);
     }
-    const float mu = warp_sum(s) * (1.0f / D);
-    float q = 0.f;
+    float va[NC][8], vb[NC][8];
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      unpack8(ra[c], va[c]);
+      unpack8(rb[c], vb[c]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sa += va[c][i]; sb += vb[c][i]; }
+    }
+    const float mua = warp_sum(sa) * (1.0f / D), mub = warp_sum(sb) * (1.0f / D);
+    float qa = 0.f, qb = 0.f;
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        v[c][i] -= mu;
-        q += v[c][i] * v[c][i];
+        va[c][i] -= mua;
+        vb[c][i] -= mub;
+        qa += va[c][i] * va[c][i];
+        qb += vb[c][i] * vb[c][i];
       }
-    const float rs = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    const float rsa = rsqrtf(warp_sum(qa) * (1.0f / D) + eps), rsb = rsqrtf(warp_sum(qb) * (1.0f / D) + eps);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       float o[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaf(v[c][i] * rs, g[c][i], b[c][i]);
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(va[c][i] * rsa, g[c][i], b[c][i]);
       *reinterpret_cast<uint4*>(y + row * D + c * 256 + lane * 8) = pack8(o);
+      if (has2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(vb[c][i] * rsb, g[c][i], b[c][i]);
+        *reinterpret_cast<uint4*>(y + row2 * D + c * 256 + lane * 8) = pack8(o);
+      }
     }
     if (lane == 0) {
-      if (mean) mean[row] = mu;
-      if (rstd) rstd[row] = rs;
+      if (mean) { mean[row] = mua; if (has2) mean[row2] = mub; }
+      if (rstd) { rstd[row] = rsa; if (has2) rstd[row2] = rsb; }
     }
   }
 }
@@ -154,8 +171,10 @@ __global__ void __launch_bounds__(kBlock) ln_bwd_bf16_kernel(const bf16* __restr
   }
 }
 
-inline int grid_rows(int64_t rows, int max_blocks) {
-  int64_t g = (rows + kBlock / 32 - 1) / (kBlock / 32);
+// rows_per_warp: minimum rows each warp should own (amortises per-block setup and the backward's dgamma/dbeta atomics)
+inline int grid_rows(int64_t rows, int max_blocks, int rows_per_warp = 1) {
+  const int64_t per_block = (int64_t)(kBlock / 32) * rows_per_warp;
+  int64_t g = (rows + per_block - 1) / per_block;
   if (g < 1) g = 1;
   if (g > max_blocks) g = max_blocks;
   return (int)g;
@@ -165,7 +184,7 @@ inline int grid_rows(int64_t rows, int max_blocks) {
 
 int layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows, int D,
                        float eps, cudaStream_t st) {
-  const int grid = grid_rows(rows, 148 * 8);
+  const int grid = grid_rows(rows, 148 * 8, 2);
   if (D == 256)
     ln_fwd_bf16_kernel<1><<<grid, kBlock, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, rows, eps);
   else
@@ -175,7 +194,7 @@ int layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, voi
 
 int layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
                        void* dx, float* dgamma, float* dbeta, int64_t rows, int D, cudaStream_t st) {
-  const int grid = grid_rows(rows, 148 * 6);
+  const int grid = grid_rows(rows, 148 * 6, 8);   // every block ends with 2*D global atomics
   if (D == 256)
     ln_bwd_bf16_kernel<1><<<grid, kBlock, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (const bf16*)dres, (bf16*)dx, dgamma,
                                                     dbeta, rows);

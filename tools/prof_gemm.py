@@ -44,6 +44,38 @@ def mk(r, c, dt=torch.bfloat16, s=1.0):
     return (s * torch.randn(r, c, device=dev)).to(dt)
 
 
+if os.environ.get("SHAPES") == "512":
+    # temporal AltFormer stage of cfg2: 256 sequences x 32 tokens, D = 512, hidden 1024
+    M5 = 256 * 32
+    a512, a1024, a1536 = mk(M5, 512), mk(M5, 1024), mk(M5, 1536)
+    w_qkv, w_proj, w_fc1, w_fc2 = mk(1536, 512, s=0.05), mk(512, 512, s=0.05), mk(1024, 512, s=0.05), mk(512, 1024, s=0.05)
+    z1536, z512, z1024 = torch.zeros(1536, device=dev), torch.zeros(512, device=dev), torch.zeros(1024, device=dev)
+    r512 = mk(M5, 512)
+    F = lambda n, k: 2 * M5 * n * k
+    Bt = lambda *cols: M5 * sum(cols) * 2
+    bench("T qkv   1536x512 +bias", lambda: ops.gemm_tn(a512, w_qkv, 1536, bias=z1536), F(1536, 512), Bt(512, 1536))
+    bench("T proj  512x512 +bias+res", lambda: ops.gemm_tn(a512, w_proj, 512, bias=z512, residual=r512), F(512, 512), Bt(512, 512, 512))
+    bench("T fc1   1024x512 +gelu+preact", lambda: ops.gemm_tn(a512, w_fc1, 1024, bias=z1024, act=ops.ACT_GELU, want_preact=True),
+          F(1024, 512), Bt(512, 2048))
+    bench("T fc2   512x1024 +bias+res", lambda: ops.gemm_tn(a1024, w_fc2, 512, bias=z512, residual=r512), F(512, 1024), Bt(1024, 1024))
+    bench("T dX    1536->512", lambda: ops.gemm_tn(a1536, w_qkv, 512, b_mn_major=True), F(1536, 512), Bt(1536, 512))
+    bench("T dao   512->512", lambda: ops.gemm_tn(a512, w_proj, 512, b_mn_major=True), F(512, 512), Bt(512, 512))
+    bench("T dpre  512->1024 gelu_bwd", lambda: ops.gemm_tn(a512, w_fc2, 1024, b_mn_major=True, act=ops.ACT_GELU_BWD, aux=a1024),
+          F(512, 1024), Bt(512, 2048))
+    bench("T dx1   1024->512", lambda: ops.gemm_tn(a1024, w_fc1, 512, b_mn_major=True), F(1024, 512), Bt(1024, 512))
+    g1, g2, g3, g4 = torch.zeros(1536, 512, device=dev), torch.zeros(512, 512, device=dev), torch.zeros(1024, 512, device=dev), torch.zeros(512, 1024, device=dev)
+    bench("T dW    1536x512 +dbias", lambda: ops.gemm_dw(a1536, a512, g1, dbias=z1536), F(1536, 512), Bt(1536, 512))
+    bench("T dW    512x512 +dbias", lambda: ops.gemm_dw(r512, a512, g2, dbias=z512), F(512, 512), Bt(512, 512))
+    bench("T dW    1024x512 +dbias", lambda: ops.gemm_dw(a1024, a512, g3, dbias=z1024), F(1024, 512), Bt(1024, 512))
+    bench("T dW    512x1024 +dbias", lambda: ops.gemm_dw(r512, a1024, g4, dbias=z512), F(512, 1024), Bt(512, 1024))
+    gam5, bet5 = torch.ones(512, device=dev), torch.zeros(512, device=dev)
+    bench("T layernorm fwd D=512", lambda: ops.layernorm_fwd(a512, gam5, bet5, 1e-6), 0, Bt(512, 512))
+    y5, mean5, rstd5 = ops.layernorm_fwd(a512, gam5, bet5, 1e-6)
+    dg5, db5 = torch.zeros(512, device=dev), torch.zeros(512, device=dev)
+    bench("T layernorm bwd D=512 (+dres)", lambda: ops.layernorm_bwd(a512, a512, gam5, mean5, rstd5, dg5, db5, dres=a512), 0, Bt(512, 512, 512, 512))
+    print("done512")
+    sys.exit(0)
+
 x256, x512 = mk(M, 256), mk(M, 512)
 wqkv, wproj, wfc1, wfc2 = mk(768, 256, s=0.05), mk(256, 256, s=0.05), mk(512, 256, s=0.05), mk(256, 512, s=0.05)
 bq, b256, b512 = torch.zeros(768, device=dev), torch.zeros(256, device=dev), torch.zeros(512, device=dev)
