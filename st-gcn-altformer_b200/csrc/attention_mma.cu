@@ -52,21 +52,30 @@ template <int DH, int LP, int HG> struct Geo {
   static constexpr size_t bwd_bytes = ((size_t)LP * QKV_PITCH + (size_t)LP * O_PITCH + (size_t)HG * 2 * LP * S_PITCH) * 2;
 };
 
-// rows [0, L) of three W-wide column windows of a [.., ld] matrix -> smem tile; rows [L, LP) zeroed.
-template <int W, int PITCH, int PARTS>
-__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t ld, int64_t part_stride, int L, int LP, int nthreads) {
+// rows [0, L) of PARTS W-wide column windows of a [.., ld] matrix -> smem tile; rows [L, LP) zeroed.
+// One warp per (row, part): the pair index is warp-uniform, so the address arithmetic is a handful of uniform
+// instructions per 512 contiguous bytes (the previous per-16-byte-chunk div/mod made the copy loop the top
+// issue-slot consumer of the forward kernel, ncu r01).
+template <int W, int PITCH, int PARTS, int LP, int NT>
+__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t ld, int64_t part_stride, int L) {
   constexpr int C16 = W / 8;  // 16-byte chunks per part row
-  const int total = LP * PARTS * C16;
-  for (int idx = threadIdx.x; idx < total; idx += nthreads) {
-    const int row = idx / (PARTS * C16), rem = idx % (PARTS * C16);
-    const int part = rem / C16, c = rem % C16;
-    bf16* d = dst + row * PITCH + part * W + c * 8;
-    if (row < L)   // asynchronous 16-byte copies: every chunk of the tile is in flight at once (cp_async_wait_all below)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d)),
-                   "l"(src + row * ld + part * part_stride + c * 8)
-                   : "memory");
-    else
-      *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+  constexpr int NW = NT / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j0 = 0; j0 < LP * PARTS; j0 += NW) {
+    const int j = j0 + warp;
+    if ((LP * PARTS) % NW != 0 && j >= LP * PARTS) break;
+    const int row = j / PARTS, part = j - row * PARTS;
+    bf16* d = dst + row * PITCH + part * W;
+    const bf16* sp = src + row * ld + part * part_stride;
+#pragma unroll
+    for (int c = lane; c < C16; c += 32) {
+      if (row < L)   // asynchronous 16-byte copies: every chunk of the tile is in flight at once (cp_async_wait_all below)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d + c * 8)), "l"(sp + c * 8)
+                     : "memory");
+      else
+        *reinterpret_cast<uint4*>(d + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __res
   const int64_t b = blockIdx.x / groups;
   const int h0 = (blockIdx.x % groups) * HG;
   const int D = heads * DH;
-  load_tile<G::W, G::QKV_PITCH, 3>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L, LP, G::kThreads);
+  load_tile<G::W, G::QKV_PITCH, 3, LP, G::kThreads>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L);
   cp_async_wait_all();
   __syncthreads();
   const int hw = threadIdx.x >> 5;
@@ -216,8 +225,8 @@ __global__ void __launch_bounds__(HG * 32) attn_bwd_mma_kernel(const bf16* __res
   const int64_t b = blockIdx.x / groups;
   const int h0 = (blockIdx.x % groups) * HG;
   const int D = heads * DH;
-  load_tile<G::W, G::QKV_PITCH, 3>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L, LP, G::kThreads);
-  load_tile<G::W, G::O_PITCH, 1>(sdo, dO + b * L * D + h0 * DH, D, 0, L, LP, G::kThreads);
+  load_tile<G::W, G::QKV_PITCH, 3, LP, G::kThreads>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L);
+  load_tile<G::W, G::O_PITCH, 1, LP, G::kThreads>(sdo, dO + b * L * D + h0 * DH, D, 0, L);
   cp_async_wait_all();
   __syncthreads();
   const int qcol = hw * DH, kcol = G::W + hw * DH, vcol = 2 * G::W + hw * DH, ocol = hw * DH;

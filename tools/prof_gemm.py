@@ -16,6 +16,7 @@ dev = "cuda"
 torch.manual_seed(0)
 
 
+GRAPH = os.environ.get("GRAPH") == "1"       # time a CUDA-graph replay (small kernels: removes host launch gaps)
 ONCE = os.environ.get("PROF_ONCE") == "1"   # ncu --profile-from-start off: capture exactly one launch per shape
 
 
@@ -31,11 +32,23 @@ def bench(name, fn, flops, bytes_):
         print(f"{name:44s} captured", flush=True)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
+    if GRAPH:   # replay a captured graph of `iters` launches: no host launch cost between the kernels
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for _ in range(iters):
+                fn()
+        gr.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    else:
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
     us = 1e3 * e0.elapsed_time(e1) / iters
     print(f"{name:44s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s  {bytes_ / us / 1e3:8.1f} GB/s", flush=True)
 
