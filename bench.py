@@ -250,13 +250,22 @@ def main():
     def step_resident():
         trainer.step(x_dev, y_dev)
 
-    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    # e2e: every step uploads its batch from pinned host memory (straight into the step's input buffers) and
+    # reads its loss back (as get_acc does, train_sttran.py:105-109).  The read-back is asynchronous and consumed
+    # one step later, so the host enqueues step i+1 while step i runs; the timed region ends with a full sync.
+    host_loss = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"i": 0, "last": float("nan")}
 
     def step_e2e():
-        xd = x_pin.to(dev, non_blocking=True)
-        yd = y_pin.to(dev, non_blocking=True)
-        loss, _ = trainer.step(xd, yd)
-        host_loss.copy_(loss, non_blocking=False)   # D2H read of the step's result (as get_acc does, train_sttran.py:105-109)
+        k = e2e_state["i"] & 1
+        loss, _ = trainer.step(x_pin, y_pin)
+        host_loss[k].copy_(loss, non_blocking=True)
+        loss_ready[k].record()
+        if e2e_state["i"] > 0:
+            loss_ready[k ^ 1].synchronize()
+            e2e_state["last"] = float(host_loss[k ^ 1])
+        e2e_state["i"] += 1
 
     for _ in range(max(args.warmup, 3)):
         step_resident()

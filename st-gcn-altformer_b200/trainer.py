@@ -115,10 +115,13 @@ class DataParallelTrainer:
         AF.bump_weights_epoch()
 
     def step(self, x, labels):
-        """x (n, T, V, 3) float32 and labels (n,) int64 of THIS rank's shard, on the trainer's device.
+        """x (n, T, V, 3) float32 and labels (n,) int64 of THIS rank's shard: tensors on the trainer's device, or
+        (pinned) host tensors, which are copied asynchronously straight into the step's input buffers.
         Returns (loss, logits) as device tensors (no host sync)."""
         self.model.train()
         if not self.use_graph:
+            if not x.is_cuda:
+                x, labels = x.to(self.device, non_blocking=True), labels.to(self.device, non_blocking=True)
             out = self._fwd_bwd(x, labels)
             self._optimize()
             return out
@@ -132,7 +135,7 @@ class DataParallelTrainer:
         return sloss, slogits
 
     def _capture(self, x, labels):
-        sx, sy = x.clone(), labels.clone()
+        sx, sy = x.to(self.device, copy=True), labels.to(self.device, copy=True)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):            # warm-up outside capture (lazy inits, smem attributes, caches)
