@@ -32,6 +32,8 @@ extern "C" {
 #define AFB_ACT_GELU 1     /* out = gelu_erf(v); if C2 != NULL the pre-activation v is stored there */
 #define AFB_ACT_GELU_BWD 2 /* out = v * gelu'(aux) */
 #define AFB_ACT_RELU 3
+#define AFB_RS_VALUE 0
+#define AFB_RS_BIAS 1
 
 typedef void* afb_stream;
 
@@ -81,6 +83,9 @@ typedef struct {
   int32_t ldres;
   const float* row_scale;
   int32_t row_scale_div;
+  int32_t row_scale_mode; /* AFB_RS_VALUE: v *= row_scale (above).  AFB_RS_BIAS: the A rows already carry the scale
+                             (DropPath folded into the saved activation), so only the bias term is scaled:
+                             v = alpha*acc + row_scale*bias[n] (+ residual). */
 } afb_gemm_tn_t;
 int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s);
 
@@ -101,8 +106,11 @@ typedef struct {
   int64_t ld1, ld2;
   int32_t x_row_shift;
   float alpha;
-  float* dbias; /* optional: dbias[n1] += alpha * sum_m G[m, n1] (bias gradient, folded in as an extra N=16 MMA
-                   against an all-ones operand) */
+  float* dbias; /* optional: dbias[n1] += alpha * sum_m G[m, n1] (bias gradient: column sums of the G tiles taken
+                   from shared memory while the MMAs run, or one extra N=16 MMA against an all-ones operand) */
+  const float* dbias_row_scale; /* optional (needs N1 % 256 == 0): dbias[n1] += alpha * sum_m rs[m / row_scale_div] * G[m, n1]
+                                   -- the DropPath keep factor of the bias path; dW itself is NOT scaled */
+  int32_t row_scale_div;
 } afb_gemm_dw_t;
 int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s);
 
@@ -150,10 +158,11 @@ int afb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, 
 /* ------------------------------------------------------------------------------------------ *
  * Small-sequence multi-head attention (model_ST.py:49-67): qkv [B*L, 3*D] with feature index
  * s*D + h*dh + d -> o [B*L, D].  L <= 64, dh in {8,16,32,64}.  Softmax probabilities never leave
- * the SM.  keep (optional, [B]) zeroes whole sequences (DropPath support).
+ * the SM.  out_scale (optional, [B]) multiplies whole output sequences (DropPath keep factor; a
+ * sequence with factor 0 is written as zeros without being computed).
  * ------------------------------------------------------------------------------------------ */
 int afb_attention_fwd(const void* qkv, void* o, int dtype, int64_t B, int L, int heads, int dh, float scale,
-                      afb_stream s);
+                      const float* out_scale, afb_stream s);
 int afb_attention_bwd(const void* qkv, const void* dO, void* dqkv, int dtype, int64_t B, int L, int heads,
                       int dh, float scale, afb_stream s);
 

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libaltformer_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_RELU = 0, 1, 2, 3
+RS_VALUE, RS_BIAS = 0, 1
 GCN0_NMOM, GCN0_NSTAT_BASE, GCN0_SLOTS = 96, 160, 32
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -21,12 +22,14 @@ class GemmTn(C.Structure):
                 ("k_per_tap", i32), ("taps", i32), ("tap_row_stride", i32), ("tap_pad", i32), ("lda", i32),
                 ("ldb", i32), ("ldc", i32), ("b_mn_major", i32), ("out_dtype", i32), ("act", i32), ("alpha", f32),
                 ("bias", vp), ("pos", vp), ("pos_rows", i32), ("aux", vp), ("aux_dtype", i32), ("ldaux", i32),
-                ("residual", vp), ("res_dtype", i32), ("ldres", i32), ("row_scale", vp), ("row_scale_div", i32)]
+                ("residual", vp), ("res_dtype", i32), ("ldres", i32), ("row_scale", vp), ("row_scale_div", i32),
+                ("row_scale_mode", i32)]
 
 
 class GemmDw(C.Structure):
     _fields_ = [("G", vp), ("X", vp), ("dW", vp), ("rows_per_batch", i64), ("batches", i32), ("N1", i32), ("N2", i32),
-                ("ldg", i32), ("ldx", i32), ("ld1", i64), ("ld2", i64), ("x_row_shift", i32), ("alpha", f32), ("dbias", vp)]
+                ("ldg", i32), ("ldx", i32), ("ld1", i64), ("ld2", i64), ("x_row_shift", i32), ("alpha", f32), ("dbias", vp),
+                ("dbias_row_scale", vp), ("row_scale_div", i32)]
 
 
 class GemmSimt(C.Structure):
@@ -81,7 +84,7 @@ def _declare(L):
         "afb_split3": [vp, vp, i64, i32, i32, vp],
         "afb_layernorm_fwd": [vp, i32, vp, vp, vp, i32, vp, vp, i64, i32, f32, vp],
         "afb_layernorm_bwd": [vp, i32, vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, i64, i32, vp],
-        "afb_attention_fwd": [vp, vp, i32, i64, i32, i32, i32, f32, vp],
+        "afb_attention_fwd": [vp, vp, i32, i64, i32, i32, i32, f32, vp, vp],
         "afb_attention_bwd": [vp, vp, vp, i32, i64, i32, i32, i32, f32, vp],
         "afb_colstats": [vp, i32, i64, i32, i32, vp, vp, vp],
         "afb_colsum": [vp, i32, i64, i32, i32, vp, i32, vp, vp],

@@ -10,7 +10,7 @@
 namespace afb {
 // tensor-core path (attention_mma.cu)
 bool attention_mma_supported(int L, int heads, int dh);
-int attention_fwd_mma(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st);
+int attention_fwd_mma(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, const float* out_scale, cudaStream_t st);
 int attention_bwd_mma(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st);
 
 namespace {
@@ -33,7 +33,7 @@ __device__ __forceinline__ void load_slice(float* dst, const T* src, int L, int 
 
 template <typename T>
 __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ o, int64_t items, int L, int heads,
-                                                       int dh, float scale, int per_warp_floats) {
+                                                       int dh, float scale, int per_warp_floats, const float* __restrict__ out_scale) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
   load_slice<T>(v, base + 2 * D, L, dh, ld, lane);
   __syncwarp();
   const int j0 = lane, j1 = lane + 32;
+  const float os = out_scale != nullptr ? out_scale[b] : 1.f;   // DropPath keep factor of this sequence
   for (int i = 0; i < L; ++i) {
     float s0 = -INFINITY, s1 = -INFINITY;
     if (j0 < L) {
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
     for (int d = lane; d < dh; d += 32) {
       float a = 0.f;
       for (int j = 0; j < L; ++j) a += prow[j] * v[j * st + d];
-      stf<T>(o + (b * L + i) * D + h * dh + d, a);
+      stf<T>(o + (b * L + i) * D + h * dh + d, a * os);
     }
     __syncwarp();
   }
@@ -154,10 +155,11 @@ int configure_smem(K kernel, int bytes) {
 
 using namespace afb;
 
-extern "C" int afb_attention_fwd(const void* qkv, void* o, int dt, int64_t B, int L, int heads, int dh, float scale, afb_stream s) {
+extern "C" int afb_attention_fwd(const void* qkv, void* o, int dt, int64_t B, int L, int heads, int dh, float scale,
+                                 const float* out_scale, afb_stream s) {
   AFB_REQUIRE(qkv && o && B > 0, "attention_fwd: bad args");
   AFB_REQUIRE(L >= 1 && L <= 64 && dh >= 1 && dh <= 64, "attention: L=%d dh=%d unsupported (L<=64, dh<=64)", L, dh);
-  if (use_mma(dt, L, heads, dh)) return attention_fwd_mma(qkv, o, B, L, heads, dh, scale, as_stream(s));
+  if (use_mma(dt, L, heads, dh)) return attention_fwd_mma(qkv, o, B, L, heads, dh, scale, out_scale, as_stream(s));
   const int per_warp = 3 * L * (dh + 1) + L + 3;
   int warps = kSmemBudget / (per_warp * 4);
   if (warps > 8) warps = 8;
@@ -168,10 +170,12 @@ extern "C" int afb_attention_fwd(const void* qkv, void* o, int dt, int64_t B, in
   int rc;
   if (dt == AFB_BF16) {
     if ((rc = configure_smem(attn_fwd_kernel<bf16>, smem))) return rc;
-    attn_fwd_kernel<bf16><<<grid, warps * 32, smem, as_stream(s)>>>((const bf16*)qkv, (bf16*)o, items, L, heads, dh, scale, per_warp);
+    attn_fwd_kernel<bf16><<<grid, warps * 32, smem, as_stream(s)>>>((const bf16*)qkv, (bf16*)o, items, L, heads, dh, scale, per_warp,
+                                                                     out_scale);
   } else {
     if ((rc = configure_smem(attn_fwd_kernel<float>, smem))) return rc;
-    attn_fwd_kernel<float><<<grid, warps * 32, smem, as_stream(s)>>>((const float*)qkv, (float*)o, items, L, heads, dh, scale, per_warp);
+    attn_fwd_kernel<float><<<grid, warps * 32, smem, as_stream(s)>>>((const float*)qkv, (float*)o, items, L, heads, dh, scale, per_warp,
+                                                                       out_scale);
   }
   return check_launch("attention_fwd");
 }

@@ -170,7 +170,8 @@ __device__ __forceinline__ void store_acc(bf16* dst, int row0, int col, const fl
 
 // ---------------------------------------------------------------------------------------------
 template <int DH, int LP, int HG>
-__global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int L, int heads, float scale) {
+__global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int L, int heads, float scale,
+                                                               const float* __restrict__ out_scale) {
   using G = Geo<DH, LP, HG>;
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* sq = reinterpret_cast<bf16*>(smraw);
@@ -178,6 +179,13 @@ __global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __res
   const int64_t b = blockIdx.x / groups;
   const int h0 = (blockIdx.x % groups) * HG;
   const int D = heads * DH;
+  const float os = out_scale != nullptr ? out_scale[b] : 1.f;   // DropPath keep factor of this sequence
+  if (os == 0.f) {   // dropped sequence: zeros, nothing to compute
+    bf16* dst = o + b * L * D + h0 * DH;
+    for (int idx = threadIdx.x; idx < L * (G::W / 8); idx += G::kThreads)
+      *reinterpret_cast<uint4*>(dst + (idx / (G::W / 8)) * (int64_t)D + (idx % (G::W / 8)) * 8) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
   load_tile<G::W, G::QKV_PITCH, 3, LP, G::kThreads>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L);
   cp_async_wait_all();
   __syncthreads();
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __res
       for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
     mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(pa, sq, vcol, acc);
     __syncwarp();   // every lane has consumed this tile's Q fragments: the rows can take the output
-    store_acc<DH / 8, G::QKV_PITCH>(sq, mi * 16, qcol, acc, 1.f, 1.f);
+    store_acc<DH / 8, G::QKV_PITCH>(sq, mi * 16, qcol, acc, os, os);
   }
   __syncthreads();
   store_tile<G::W, G::QKV_PITCH>(o + b * L * D + h0 * DH, D, sq, L, G::kThreads);
@@ -347,11 +355,12 @@ int set_smem(K kernel, size_t bytes) {
 }
 
 template <int DH, int LP, int HG>
-int launch_fwd(const void* qkv, void* o, int64_t B, int L, int heads, float scale, cudaStream_t st) {
+int launch_fwd(const void* qkv, void* o, int64_t B, int L, int heads, float scale, const float* out_scale, cudaStream_t st) {
   using G = Geo<DH, LP, HG>;
   int rc = set_smem(attn_fwd_mma_kernel<DH, LP, HG>, G::fwd_bytes);
   if (rc) return rc;
-  attn_fwd_mma_kernel<DH, LP, HG><<<(unsigned)(B * (heads / HG)), G::kThreads, G::fwd_bytes, st>>>((const bf16*)qkv, (bf16*)o, L, heads, scale);
+  attn_fwd_mma_kernel<DH, LP, HG><<<(unsigned)(B * (heads / HG)), G::kThreads, G::fwd_bytes, st>>>((const bf16*)qkv, (bf16*)o, L, heads, scale,
+                                                                                                    out_scale);
   return check_launch("attention_fwd_mma");
 }
 template <int DH, int LP, int HG>
@@ -393,9 +402,9 @@ bool attention_mma_supported(int L, int heads, int dh) {
     return attn_mma::FN<64, 64, 4>(__VA_ARGS__);                                                \
   } while (0)
 
-int attention_fwd_mma(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st) {
+int attention_fwd_mma(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, const float* out_scale, cudaStream_t st) {
   const bool bwd = false;
-  AFB_ATTN_DISPATCH(launch_fwd, qkv, o, B, L, heads, scale, st);
+  AFB_ATTN_DISPATCH(launch_fwd, qkv, o, B, L, heads, scale, out_scale, st);
 }
 int attention_bwd_mma(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st) {
   const bool bwd = true;

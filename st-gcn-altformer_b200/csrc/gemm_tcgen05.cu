@@ -253,6 +253,7 @@ struct TnArgs {
   int res_dtype, ldres;
   const float* row_scale;
   int row_scale_div;
+  int rs_bias;   // AFB_RS_BIAS: the row scale multiplies only the bias term (A rows are pre-scaled)
 };
 
 // Tile walk of one CTA.  Streaming: tiles blockIdx.x, +grid, ... over (m-tile, n-block) with n fastest, so
@@ -383,7 +384,9 @@ __device__ __forceinline__ void epi_fast_loop(const TnArgs& p, const CUtensorMap
     wn.next();
     if (wn.valid()) l2_prefetch(wn);
     float rscale = 1.f;
-    if (kScale && p.row_scale != nullptr && valid) rscale = p.row_scale[row / p.row_scale_div];
+    if ((kScale || KIND == EPI_BIAS_GELU_C2) && p.row_scale != nullptr && valid) rscale = p.row_scale[row / p.row_scale_div];
+    const float bscale = p.rs_bias ? rscale : 1.f;    // scale of the bias term
+    const float vscale = p.rs_bias ? 1.f : rscale;    // scale of the finished value
     const uint32_t tmem_tile = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
     mbar_wait(tfull0 + 8u * acc, acc_phase);
     tc_fence_after();
@@ -420,8 +423,13 @@ __device__ __forceinline__ void epi_fast_loop(const TnArgs& p, const CUtensorMap
           if (kBias) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * q);
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * q + 1);
-            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            if (kRes) {   // the only biased kind that takes a row scale
+              x[0] = fmaf(b0.x, bscale, x[0]); x[1] = fmaf(b0.y, bscale, x[1]); x[2] = fmaf(b0.z, bscale, x[2]); x[3] = fmaf(b0.w, bscale, x[3]);
+              x[4] = fmaf(b1.x, bscale, x[4]); x[5] = fmaf(b1.y, bscale, x[5]); x[6] = fmaf(b1.z, bscale, x[6]); x[7] = fmaf(b1.w, bscale, x[7]);
+            } else {
+              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            }
           }
           if (KIND == EPI_BIAS_GELU_C2) {   // pre-activation goes out first; keep it for the GELU round below
 #pragma unroll
@@ -435,7 +443,7 @@ __device__ __forceinline__ void epi_fast_loop(const TnArgs& p, const CUtensorMap
           }
           if (kScale && p.row_scale != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] *= rscale;
+            for (int i = 0; i < 8; ++i) x[i] *= vscale;
           }
           if (kRes) {
             float t[8];
@@ -449,7 +457,7 @@ __device__ __forceinline__ void epi_fast_loop(const TnArgs& p, const CUtensorMap
       staging_store(stage_addr, lane, KIND == EPI_BIAS_GELU_C2 ? tmC2 : tmC, n0, row_in_batch0, batch);
       if (KIND == EPI_BIAS_GELU_C2) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) pre[i] = gelu_fast_f(pre[i]);   // overlaps the store's smem read
+        for (int i = 0; i < 64; ++i) pre[i] = gelu_fast_f(pre[i]) * vscale;   // overlaps the store's smem read
         staging_acquire(lane);
 #pragma unroll
         for (int q = 0; q < 8; ++q) sts_pack8(rowp, q, lane, pre + 8 * q);
@@ -684,8 +692,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 const float4 b4 = bq[q];
-                v[4 * q] = v[4 * q] * p.alpha + b4.x; v[4 * q + 1] = v[4 * q + 1] * p.alpha + b4.y;
-                v[4 * q + 2] = v[4 * q + 2] * p.alpha + b4.z; v[4 * q + 3] = v[4 * q + 3] * p.alpha + b4.w;
+                const float bs = p.rs_bias ? rscale : 1.f;
+                v[4 * q] = v[4 * q] * p.alpha + b4.x * bs; v[4 * q + 1] = v[4 * q + 1] * p.alpha + b4.y * bs;
+                v[4 * q + 2] = v[4 * q + 2] * p.alpha + b4.z * bs; v[4 * q + 3] = v[4 * q + 3] * p.alpha + b4.w * bs;
               }
             } else if (p.alpha != 1.f) {
 #pragma unroll
@@ -721,7 +730,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
               }
-              if (p.row_scale != nullptr) {
+              if (p.row_scale != nullptr && !p.rs_bias) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] *= rscale;
               }
@@ -816,6 +825,9 @@ struct DwArgs {
   float alpha;
   float* dbias;   // optional: dbias[n1] += alpha * sum_m G[m, n1]
   int vec4;       // ld2 == 1 and 16-byte aligned rows: the epilogue uses red.global.add.v4.f32
+  const float* dbias_rs;   // optional per-row factor of the bias gradient (smem column-sum path only)
+  int rs_div;
+  long long rows_per_batch;
 };
 
 template <int BN1, int BN2>
@@ -932,13 +944,33 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0; i < n_rb; ++i) {
+          float sc0 = 1.f, sc1 = 1.f;   // factors of tile rows `lane` and `lane + 32` (rows past the batch are zero-filled)
+          if (p.dbias_rs != nullptr) {
+            const int rb = rb_begin + i;
+            const long long bat = rb / p.row_blocks_per_batch;
+            const long long r0 = (long long)(rb % p.row_blocks_per_batch) * 64 + lane;
+            const long long ra = bat * p.rows_per_batch + min(r0, p.rows_per_batch - 1);
+            const long long rb2 = bat * p.rows_per_batch + min(r0 + 32, p.rows_per_batch - 1);
+            sc0 = p.dbias_rs[ra / p.rs_div];
+            sc1 = p.dbias_rs[rb2 / p.rs_div];
+          }
           mbar_wait(full_bar(stage), phase);
           const uint8_t* g = smem + stage * Cfg::kABytes + box * 8192 + (word & 3) * 4;
+          if (p.dbias_rs != nullptr) {
 #pragma unroll 16
-          for (int r = 0; r < 64; ++r) {
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(g + r * 128 + (((word >> 2) ^ (r & 7)) << 4));
-            s0 += __uint_as_float(v << 16);
-            s1 += __uint_as_float(v & 0xffff0000u);
+            for (int r = 0; r < 64; ++r) {
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(g + r * 128 + (((word >> 2) ^ (r & 7)) << 4));
+              const float f = __shfl_sync(0xffffffffu, r < 32 ? sc0 : sc1, r & 31);
+              s0 = fmaf(f, __uint_as_float(v << 16), s0);
+              s1 = fmaf(f, __uint_as_float(v & 0xffff0000u), s1);
+            }
+          } else {
+#pragma unroll 16
+            for (int r = 0; r < 64; ++r) {
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(g + r * 128 + (((word >> 2) ^ (r & 7)) << 4));
+              s0 += __uint_as_float(v << 16);
+              s1 += __uint_as_float(v & 0xffff0000u);
+            }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(empty_bar(stage));
@@ -1171,15 +1203,17 @@ extern "C" int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s) {
   a.aux = p->aux; a.aux_dtype = p->aux_dtype; a.ldaux = p->ldaux;
   a.residual = p->residual; a.res_dtype = p->res_dtype; a.ldres = p->ldres;
   a.row_scale = p->row_scale; a.row_scale_div = p->row_scale_div > 0 ? p->row_scale_div : 1;
+  a.rs_bias = (p->row_scale != nullptr && p->row_scale_mode == AFB_RS_BIAS) ? 1 : 0;
+  AFB_REQUIRE(!a.rs_bias || p->act == AFB_ACT_NONE, "gemm_tn: AFB_RS_BIAS cannot be combined with an activation");
   a.epi_kind = EPI_GENERIC;
   static const bool no_fast_epi = getenv("AFB_GEMM_GENERIC_EPI") != nullptr;
   if (!no_fast_epi && p->out_dtype == AFB_BF16 && p->alpha == 1.f && p->pos == nullptr) {
     const bool res = p->residual != nullptr, bias = p->bias != nullptr, rs = p->row_scale != nullptr;
     if (p->act == AFB_ACT_NONE && bias && !res && !rs) a.epi_kind = EPI_BIAS;
     else if (p->act == AFB_ACT_NONE && bias && res && p->res_dtype == AFB_BF16) a.epi_kind = EPI_BIAS_RES;
-    else if (p->act == AFB_ACT_GELU && bias && a.has_c2 && !res && !rs) a.epi_kind = EPI_BIAS_GELU_C2;
+    else if (p->act == AFB_ACT_GELU && bias && a.has_c2 && !res) a.epi_kind = EPI_BIAS_GELU_C2;
     else if (p->act == AFB_ACT_GELU_BWD && !bias && !res && p->aux != nullptr && p->aux_dtype == AFB_BF16) a.epi_kind = EPI_GELU_BWD;
-    else if (p->act == AFB_ACT_NONE && !bias && !res) a.epi_kind = EPI_PLAIN;
+    else if (p->act == AFB_ACT_NONE && !bias && !res && !a.rs_bias) a.epi_kind = EPI_PLAIN;
   }
   AFB_REQUIRE(p->act != AFB_ACT_GELU_BWD || p->aux != nullptr, "gemm_tn: GELU_BWD needs aux");
   AFB_REQUIRE(p->act != AFB_ACT_GELU_BWD || p->residual == nullptr, "gemm_tn: GELU_BWD cannot be combined with a residual");
@@ -1238,6 +1272,10 @@ extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
   a.N1 = p->N1; a.N2 = p->N2; a.x_row_shift = p->x_row_shift;
   a.dW = p->dW; a.ld1 = p->ld1; a.ld2 = p->ld2; a.alpha = p->alpha; a.dbias = p->dbias;
   a.vec4 = (p->ld2 == 1 && p->ld1 % 4 == 0 && ((uintptr_t)p->dW & 15) == 0) ? 1 : 0;
+  a.dbias_rs = p->dbias != nullptr ? p->dbias_row_scale : nullptr;
+  a.rs_div = p->row_scale_div > 0 ? p->row_scale_div : 1;
+  a.rows_per_batch = p->rows_per_batch;
+  AFB_REQUIRE(a.dbias_rs == nullptr || BN1 == 256, "gemm_dw: dbias_row_scale needs N1 %% 256 == 0 (N1=%d)", p->N1);
   CUtensorMap tmG, tmX;
   int rc = make_map(&tmG, p->G, (uint64_t)p->N1, (uint64_t)p->rows_per_batch, (uint64_t)p->batches, (uint64_t)p->ldg,
                     (uint64_t)p->rows_per_batch * p->ldg, 64, 64, 3);

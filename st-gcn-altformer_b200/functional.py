@@ -277,17 +277,35 @@ def attention_core(qkv, B, L, heads):
     return AttentionCoreFn.apply(qkv, B, L, heads)
 
 
+def _fold_keep(keep, width):
+    """DropPath folding (bf16 mode, width % 256 == 0): instead of materialising keep * g in the backward pass, the
+    SAVED activation carries the keep factor (h_act, attention output), the following linear scales only its
+    bias by it, and the backward takes dW from the pre-scaled activation, dbias from a row-scaled column sum and
+    dX through the GEMM's row-scale epilogue -- no scale_rows pass over the gradient."""
+    return keep is not None and _PRECISION[0] == "bf16" and width % 256 == 0
+
+
 def _mlp_fwd(x, w1, b1, w2, b2, residual, keep, div):
+    """returns y, h_act (carrying the keep factor when _fold_keep), h_pre"""
+    if _fold_keep(keep, w2.shape[0]):
+        h_act, h_pre = mm_fwd(x, w1, bias=b1, act=ACT_GELU, want_preact=True, row_scale=keep, row_scale_div=div)
+        y = mm_fwd(h_act, w2, bias=b2, residual=residual, row_scale=keep, row_scale_div=div, row_scale_bias_only=True)
+        return y, h_act, h_pre
     h_act, h_pre = mm_fwd(x, w1, bias=b1, act=ACT_GELU, want_preact=True)
     y = mm_fwd(h_act, w2, bias=b2, residual=residual, row_scale=keep, row_scale_div=div)
     return y, h_act, h_pre
 
 
-def _mlp_bwd(g, x, h_act, h_pre, w1, b1, w2, b2, need_dx=True):
-    """g: gradient w.r.t. the (already DropPath-scaled) fc2 output."""
+def _mlp_bwd(g, x, h_act, h_pre, w1, b1, w2, b2, need_dx=True, keep=None, div=1):
+    """g: gradient w.r.t. the fc2 output -- already DropPath-scaled unless keep is given (folded path: h_act
+    carries the factor, the bias gradient and dX apply it here)."""
     s2, sb2 = _grad_sink(w2), _grad_sink(b2)
-    mm_dw(g, h_act, s2[0], dbias=sb2[0])
-    dpre = mm_dx(g, w2, act=ACT_GELU_BWD, aux=h_pre)
+    if keep is not None:
+        mm_dw(g, h_act, s2[0], dbias=sb2[0], dbias_row_scale=keep, row_scale_div=div)
+        dpre = mm_dx(g, w2, act=ACT_GELU_BWD, aux=h_pre, row_scale=keep, row_scale_div=div)
+    else:
+        mm_dw(g, h_act, s2[0], dbias=sb2[0])
+        dpre = mm_dx(g, w2, act=ACT_GELU_BWD, aux=h_pre)
     s1, sb1 = _grad_sink(w1), _grad_sink(b1)
     mm_dw(dpre, x, s1[0], dbias=sb1[0])
     dx = mm_dx(dpre, w1) if need_dx else None
@@ -324,8 +342,12 @@ class BlockFn(torch.autograd.Function):
         d = lambda t: None if t is None else t.detach()  # noqa: E731
         ln1, mean1, rstd1 = ops.layernorm_fwd(x, d(n1w), d(n1b), eps)
         qkv = mm_fwd(ln1, qkvw, bias=d(qkvb))
-        ao = ops.attention_fwd(qkv, B, L, heads)
-        x1 = mm_fwd(ao, pw, bias=d(pb), residual=x, row_scale=keep1, row_scale_div=L)
+        if _fold_keep(keep1, pw.shape[0]):   # ao carries keep1 (dropped sequences are not even computed)
+            ao = ops.attention_fwd(qkv, B, L, heads, out_scale=keep1)
+            x1 = mm_fwd(ao, pw, bias=d(pb), residual=x, row_scale=keep1, row_scale_div=L, row_scale_bias_only=True)
+        else:
+            ao = ops.attention_fwd(qkv, B, L, heads)
+            x1 = mm_fwd(ao, pw, bias=d(pb), residual=x, row_scale=keep1, row_scale_div=L)
         ln2, mean2, rstd2 = ops.layernorm_fwd(x1, d(n2w), d(n2b), eps)
         x2, h_act, h_pre = _mlp_fwd(ln2, w1, d(b1), w2, d(b2), x1, keep2, L)
         ctx.save_for_backward(x, mean1, rstd1, ln1, qkv, ao, x1, mean2, rstd2, ln2, h_act, h_pre, keep1, keep2,
@@ -339,14 +361,21 @@ class BlockFn(torch.autograd.Function):
          n1w, n1b, qkvw, qkvb, pw, pb, n2w, n2b, w1, b1, w2, b2) = ctx.saved_tensors
         B, L, heads = ctx.cfg
         g2 = _as_act(g2.contiguous())
-        gs = g2 if keep2 is None else ops.scale_rows(g2, keep2, L)
-        dln2, (gw1, gb1, gw2, gb2) = _mlp_bwd(gs, ln2, h_act, h_pre, w1, b1, w2, b2)
+        if _fold_keep(keep2, w2.shape[0]):
+            dln2, (gw1, gb1, gw2, gb2) = _mlp_bwd(g2, ln2, h_act, h_pre, w1, b1, w2, b2, keep=keep2, div=L)
+        else:
+            gs = g2 if keep2 is None else ops.scale_rows(g2, keep2, L)
+            dln2, (gw1, gb1, gw2, gb2) = _mlp_bwd(gs, ln2, h_act, h_pre, w1, b1, w2, b2)
         sg2, sb2 = _grad_sink(n2w), _grad_sink(n2b)
         g1 = ops.layernorm_bwd(dln2, x1, n2w.detach(), mean2, rstd2, sg2[0], sb2[0], dres=g2)
-        gs1 = g1 if keep1 is None else ops.scale_rows(g1, keep1, L)
         sp, spb = _grad_sink(pw), _grad_sink(pb)
-        mm_dw(gs1, ao, sp[0], dbias=spb[0])
-        dao = mm_dx(gs1, pw)
+        if _fold_keep(keep1, pw.shape[0]):
+            mm_dw(g1, ao, sp[0], dbias=spb[0], dbias_row_scale=keep1, row_scale_div=L)
+            dao = mm_dx(g1, pw, row_scale=keep1, row_scale_div=L)
+        else:
+            gs1 = g1 if keep1 is None else ops.scale_rows(g1, keep1, L)
+            mm_dw(gs1, ao, sp[0], dbias=spb[0])
+            dao = mm_dx(gs1, pw)
         dqkv = ops.attention_bwd(qkv, dao, B, L, heads)
         sq = _grad_sink(qkvw)
         sqb = _grad_sink(qkvb) if qkvb is not None else None

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, BF16, F32  # noqa: F401
+from ._lib import ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, BF16, F32, RS_BIAS, RS_VALUE  # noqa: F401
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -63,8 +63,9 @@ def _call(name, *args):
 # ------------------------------------------------------------------------------------------------
 def gemm_tn(a, b, N, *, k_per_tap=None, taps=1, tap_row_stride=0, tap_pad=0, rows_per_batch=None, batches=1,
             b_mn_major=False, out_dtype=torch.bfloat16, bias=None, act=ACT_NONE, want_preact=False, aux=None,
-            residual=None, row_scale=None, row_scale_div=1, pos=None, alpha=1.0, out=None):
-    """C = epilogue(A @ B^T).  a [M, lda] bf16, b [N, K] bf16 (or [K, N] when b_mn_major)."""
+            residual=None, row_scale=None, row_scale_div=1, row_scale_bias_only=False, pos=None, alpha=1.0, out=None):
+    """C = epilogue(A @ B^T).  a [M, lda] bf16, b [N, K] bf16 (or [K, N] when b_mn_major).
+    row_scale_bias_only: the rows of `a` already carry row_scale, so only the bias term is multiplied by it."""
     need_cuda(a, b, bias, aux, residual, row_scale, pos, out)
     ensure_device(a)
     if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
@@ -84,16 +85,16 @@ def gemm_tn(a, b, N, *, k_per_tap=None, taps=1, tap_row_stride=0, tap_pad=0, row
                     aux=ptr(aux), aux_dtype=0 if aux is None else dt(aux), ldaux=0 if aux is None else aux.shape[1],
                     residual=ptr(residual), res_dtype=0 if residual is None else dt(residual),
                     ldres=0 if residual is None else residual.shape[1], row_scale=ptr(row_scale),
-                    row_scale_div=row_scale_div)
+                    row_scale_div=row_scale_div, row_scale_mode=RS_BIAS if row_scale_bias_only else RS_VALUE)
     _call("afb_gemm_tn", C.byref(p), stream())
     return (c, c2) if want_preact else c
 
 
 def gemm_dw(g, x, dW, *, N1=None, N2=None, rows_per_batch=None, batches=1, ld1=None, ld2=1, x_row_shift=0, alpha=1.0,
-            g_col0=0, x_col0=0, dbias=None):
+            g_col0=0, x_col0=0, dbias=None, dbias_row_scale=None, row_scale_div=1):
     """dW[n1*ld1 + n2*ld2] += alpha * sum_m g[m, g_col0 + n1] * x[m + shift, x_col0 + n2]  (fp32 atomics);
-    dbias[n1] += alpha * sum_m g[m, g_col0 + n1] when given."""
-    need_cuda(g, x, dW, dbias)
+    dbias[n1] += alpha * sum_m (rs[m // row_scale_div]) * g[m, g_col0 + n1] when given (rs = dbias_row_scale or 1)."""
+    need_cuda(g, x, dW, dbias, dbias_row_scale)
     if g.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dW.dtype != torch.float32:
         raise RuntimeError("gemm_dw: g, x must be bfloat16 and dW float32")
     M = g.shape[0]
@@ -103,7 +104,8 @@ def gemm_dw(g, x, dW, *, N1=None, N2=None, rows_per_batch=None, batches=1, ld1=N
     N2 = x.shape[1] if N2 is None else N2
     p = _lib.GemmDw(G=ptr(g) + 2 * g_col0, X=ptr(x) + 2 * x_col0, dW=ptr(dW), rows_per_batch=rows_per_batch,
                     batches=batches, N1=N1, N2=N2, ldg=g.shape[1], ldx=x.shape[1],
-                    ld1=N2 if ld1 is None else ld1, ld2=ld2, x_row_shift=x_row_shift, alpha=alpha, dbias=ptr(dbias))
+                    ld1=N2 if ld1 is None else ld1, ld2=ld2, x_row_shift=x_row_shift, alpha=alpha, dbias=ptr(dbias),
+                    dbias_row_scale=ptr(dbias_row_scale), row_scale_div=row_scale_div)
     _call("afb_gemm_dw", C.byref(p), stream())
     return dW
 
@@ -195,12 +197,13 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None):
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
-def attention_fwd(qkv, B, L, heads):
-    need_cuda(qkv)
+def attention_fwd(qkv, B, L, heads, out_scale=None):
+    """out_scale (B,) float32: per-sequence factor of the output (DropPath keep); factor-0 sequences are not computed."""
+    need_cuda(qkv, out_scale)
     D = qkv.shape[1] // 3
     dh = D // heads
     o = torch.empty((B * L, D), device=qkv.device, dtype=qkv.dtype)
-    _call("afb_attention_fwd", ptr(qkv), ptr(o), dt(qkv), B, L, heads, dh, float(dh) ** -0.5, stream())
+    _call("afb_attention_fwd", ptr(qkv), ptr(o), dt(qkv), B, L, heads, dh, float(dh) ** -0.5, ptr(out_scale), stream())
     return o
 
 

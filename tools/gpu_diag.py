@@ -258,6 +258,40 @@ def grp_gemm_tn():
         report("gemm_tn in-place accumulate", acc, _mm_ref(a, b) + 1, 2e-3)
     check(epilogues)
 
+    def fast_epilogues():
+        # bf16 outputs take the specialised straight-line epilogues (EPI_* kinds); BN 64 / 128 / 256 tiles,
+        # ragged last m-tile, DropPath row scales in both modes
+        L = 22
+        for (M, N, K) in ((22 * 13, 64, 128), (22 * 50, 128, 256), (22 * 300, 256, 256), (22 * 40, 512, 256), (22 * 400, 256, 512)):
+            a, b = g(M, K, seed=1, dtype=torch.bfloat16), g(N, K, seed=2, scale=0.1, dtype=torch.bfloat16)
+            bias = g(N, seed=3)
+            res = g(M, N, seed=5, dtype=torch.bfloat16)
+            rs = (torch.rand(M // L, device=DEV) > 0.3).float() / 0.7
+            rsr = rs.repeat_interleave(L)[:, None]
+            mm = _mm_ref(a, b)
+            tag = f"{M}x{N}x{K}"
+            report(f"fast bias {tag}", ops.gemm_tn(a, b, N, bias=bias), mm + bias, 1e-2)
+            report(f"fast bias+res {tag}", ops.gemm_tn(a, b, N, bias=bias, residual=res), mm + bias + res.float(), 1e-2)
+            report(f"fast bias+res+rs {tag}", ops.gemm_tn(a, b, N, bias=bias, residual=res, row_scale=rs, row_scale_div=L),
+                   rsr * (mm + bias) + res.float(), 1e-2)
+            report(f"fast bias+res+rs(bias only) {tag}",
+                   ops.gemm_tn(a, b, N, bias=bias, residual=res, row_scale=rs, row_scale_div=L, row_scale_bias_only=True),
+                   mm + rsr * bias + res.float(), 1e-2)
+            y, pre = ops.gemm_tn(a, b, N, bias=bias, act=ops.ACT_GELU, want_preact=True)
+            report(f"fast gelu {tag}", y, torch.nn.functional.gelu(mm + bias), 1e-2)
+            report(f"fast gelu preact {tag}", pre, mm + bias, 1e-2)
+            y, pre = ops.gemm_tn(a, b, N, bias=bias, act=ops.ACT_GELU, want_preact=True, row_scale=rs, row_scale_div=L)
+            report(f"fast gelu*rs {tag}", y, rsr * torch.nn.functional.gelu(mm + bias), 1e-2)
+            report(f"fast gelu*rs preact {tag}", pre, mm + bias, 1e-2)
+            aux = g(M, N, seed=6, dtype=torch.bfloat16)
+            xr = aux.float().requires_grad_(True)
+            torch.nn.functional.gelu(xr).backward(torch.ones_like(xr))
+            report(f"fast gelu_bwd {tag}", ops.gemm_tn(a, b, N, act=ops.ACT_GELU_BWD, aux=aux), mm * xr.grad, 1.2e-2)
+            report(f"fast gelu_bwd*rs {tag}", ops.gemm_tn(a, b, N, act=ops.ACT_GELU_BWD, aux=aux, row_scale=rs, row_scale_div=L),
+                   rsr * mm * xr.grad, 1.2e-2)
+            report(f"fast plain*rs {tag}", ops.gemm_tn(a, b, N, row_scale=rs, row_scale_div=L), rsr * mm, 1e-2)
+    check(fast_epilogues)
+
     def conv_taps():
         for (Nb, T, V, Cc, Co) in ((2, 8, 22, 64, 64), (3, 32, 22, 128, 128), (2, 16, 46, 128, 128), (2, 5, 7, 64, 128)):
             x = g(Nb, Cc, T, V, seed=1, dtype=torch.bfloat16)
@@ -340,6 +374,13 @@ def grp_gemm_dw():
             ops.gemm_dw(G, X, dW, dbias=db)
             report(f"gemm_dw+dbias M={M} N1={N1} N2={N2} dW", dW, G.float().t() @ X.float(), 2e-3)
             report(f"gemm_dw+dbias M={M} N1={N1} N2={N2} dbias", db, G.float().sum(0), 2e-3)
+        for (M, N1, N2, L) in ((22 * 100, 256, 256, 22), (32 * 300, 512, 1024, 32), (22 * 77, 256, 512, 22)):   # row-scaled bias gradient
+            G, X = g(M, N1, seed=7, scale=0.1, dtype=torch.bfloat16), g(M, N2, seed=8, dtype=torch.bfloat16)
+            rs = (torch.rand(M // L, device=DEV) > 0.3).float() / 0.7
+            dW, db = torch.zeros(N1, N2, device=DEV), torch.zeros(N1, device=DEV)
+            ops.gemm_dw(G, X, dW, dbias=db, dbias_row_scale=rs, row_scale_div=L)
+            report(f"gemm_dw+dbias*rs M={M} N1={N1} N2={N2} dW", dW, G.float().t() @ X.float(), 2e-3)
+            report(f"gemm_dw+dbias*rs M={M} N1={N1} N2={N2} dbias", db, (rs.repeat_interleave(L)[:, None] * G.float()).sum(0), 2e-3)
         G, X = g(3000, 384, seed=3, scale=0.1, dtype=torch.bfloat16), g(3000, 192, seed=4, dtype=torch.bfloat16)
         dW = torch.zeros(128, 64, device=DEV)
         ops.gemm_dw(G, X, dW, N1=128, N2=64, ld1=64, g_col0=128, x_col0=64)
@@ -384,6 +425,9 @@ def grp_attention():
                 do = g(B * L, D, seed=9, dtype=dtp)
                 oref.backward(do.float())
                 report(f"attention_bwd B={B} L={L} dh={dh} {dtp}", ops.attention_bwd(qkv, do, B, L, H), qr.grad, tol)
+                keep = torch.tensor([0.0 if i % 3 == 1 else 1.25 for i in range(B)], device=DEV)
+                report(f"attention_fwd*keep B={B} L={L} dh={dh} {dtp}", ops.attention_fwd(qkv, B, L, H, out_scale=keep),
+                       keep.repeat_interleave(L)[:, None] * oref.detach(), tol)
     check(attn)
 
 
