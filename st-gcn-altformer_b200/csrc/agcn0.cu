@@ -39,23 +39,22 @@ struct Coef {  // per subset: C (3x3), e (3), f (3)
   float v[3][16];
 };
 
+// one warp per coefficient, lanes over the inner channels (a serial 32-long chain of dependent global loads per
+// thread used to cost ~3 us at the head of every CTA)
 __device__ void compute_coef(const afb_gcn0_fwd_t& p, float (*coef)[16]) {
-  for (int t = threadIdx.x; t < 45; t += blockDim.x) {
+  const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int t = threadIdx.x >> 5; t < 45; t += nw) {
     const int i = t / 15, q = t % 15;
     const float* Wa = p.Wa[i];
     const float* Wb = p.Wb[i];
     float acc = 0.f;
-    if (q < 9) {
-      const int a = q / 3, b = q % 3;
-      for (int c = 0; c < p.IC; ++c) acc += Wa[c * 3 + a] * Wb[c * 3 + b];
-    } else if (q < 12) {
-      const int a = q - 9;
-      for (int c = 0; c < p.IC; ++c) acc += Wa[c * 3 + a] * p.bb[i][c];
-    } else {
-      const int b = q - 12;
-      for (int c = 0; c < p.IC; ++c) acc += p.ba[i][c] * Wb[c * 3 + b];
+    for (int c = lane; c < p.IC; c += 32) {
+      if (q < 9) acc += Wa[c * 3 + q / 3] * Wb[c * 3 + q % 3];
+      else if (q < 12) acc += Wa[c * 3 + (q - 9)] * p.bb[i][c];
+      else acc += p.ba[i][c] * Wb[c * 3 + (q - 12)];
     }
-    coef[i][q] = acc;
+    acc = warp_sum(acc);
+    if (lane == 0) coef[i][q] = acc;
   }
 }
 
@@ -122,7 +121,9 @@ __device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm 
   __syncthreads();
   if (tid < NR) p.stats[tid] = (float)E[tid];
   for (int e = tid; e < NR * NR; e += blockDim.x) p.stats[NR + e] = (float)Cov[e];
-  for (int o = tid; o < p.Cout; o += blockDim.x) {
+  // 4 lanes per output channel split the rows of the two quadratic forms (fp64 chains are the critical path here)
+  for (int o4 = tid; o4 < p.Cout * 4; o4 += blockDim.x) {
+    const int o = o4 >> 2, part = o4 & 3;
     double w[NR];
     double b = 0.0;
     for (int i = 0; i < 3; ++i) {
@@ -130,15 +131,30 @@ __device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm 
       b += p.bd[i][o];
     }
     for (int a = 0; a < 3; ++a) w[9 + a] = p.Wdn[o * 3 + a];
-    double mean_h = b, mean_d = p.bdn[o], var_h = 0.0, var_d = 0.0;
-    for (int j = 0; j < 9; ++j) {
+    double mean_h = 0.0, mean_d = 0.0, var_h = 0.0, var_d = 0.0;
+    for (int j = part; j < 9; j += 4) {
       mean_h += w[j] * E[j];
-      for (int k = 0; k < 9; ++k) var_h += w[j] * Cov[j * NR + k] * w[k];
+      double row = 0.0;
+      for (int k = 0; k < 9; ++k) row += Cov[j * NR + k] * w[k];
+      var_h += w[j] * row;
     }
-    for (int j = 9; j < 12; ++j) {
+    if (part < 3) {
+      const int j = 9 + part;
       mean_d += w[j] * E[j];
-      for (int k = 9; k < 12; ++k) var_d += w[j] * Cov[j * NR + k] * w[k];
+      double row = 0.0;
+      for (int k = 9; k < 12; ++k) row += Cov[j * NR + k] * w[k];
+      var_d += w[j] * row;
     }
+#pragma unroll
+    for (int off = 1; off < 4; off <<= 1) {   // the 4 lanes of a channel are adjacent; blockDim and Cout*4 are multiples of 32
+      mean_h += __shfl_xor_sync(0xffffffffu, mean_h, off);
+      mean_d += __shfl_xor_sync(0xffffffffu, mean_d, off);
+      var_h += __shfl_xor_sync(0xffffffffu, var_h, off);
+      var_d += __shfl_xor_sync(0xffffffffu, var_d, off);
+    }
+    if (part != 0) continue;
+    mean_h += b;
+    mean_d += p.bdn[o];
     if (var_h < 0.0) var_h = 0.0;
     if (var_d < 0.0) var_d = 0.0;
     const double ctr_h = mean_h, ctr_d = mean_d;  // pre-BN activations at the batch centre E[r]
@@ -176,45 +192,85 @@ __device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm 
   if (tid == 0) *p.counter = 0;
 }
 
-__global__ void __launch_bounds__(kThreads) gcn0_scores_kernel(const afb_gcn0_fwd_t p) {
+// One CTA of 512 threads per sample: the per-sample work (Gram matrix, 3 softmaxed mixing matrices, r vectors,
+// 90 moments) is a chain of small dependent phases, so the kernel is latency-bound -- a wide CTA shortens every
+// phase (only N CTAs exist, 256 for the benchmark batch, so wide CTAs also fill the SMs).
+constexpr int kScoreThreads = 512;    // 2 CTAs per SM: the benchmark's 256 samples run as one wave
+constexpr int kMomSegs = kScoreThreads / 90;   // position segments per moment (5 x 90 threads)
+
+// (__grid_constant__: gcn0_finalize takes the parameter block by reference; without it every thread would first
+// copy the 464-byte struct to local memory -- 120 MB of local stores per launch, the top stall in the r01 profile)
+__global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __grid_constant__ afb_gcn0_fwd_t p) {
   extern __shared__ __align__(16) float sm[];
   const int T = p.T, V = p.V, n = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
   float* xs = sm;                        // [T*V*3]
   float* Ms = xs + a4(T * V * 3);        // [3][V][V]
   float* rs = Ms + a4(3 * V * V);        // [kPosChunk][12]   r vectors of one chunk of positions
-  float* part = rs + kPosChunk * NR;     // [2][NMOM]
+  float* part = rs + kPosChunk * NR;     // [kMomSegs][NMOM]
   __shared__ float coef[3][16];
   __shared__ int is_last;
   const float* xg = p.x + (int64_t)n * T * V * 3;
-  for (int i = threadIdx.x; i < T * V * 3; i += blockDim.x) xs[i] = xg[i];
+  if ((T * V * 3) % 4 == 0) {            // sample base is 16-byte aligned then: one float4 per thread, all in flight
+    const float4* x4 = reinterpret_cast<const float4*>(xg);
+    for (int i = tid; i < T * V * 3 / 4; i += nthr) reinterpret_cast<float4*>(xs)[i] = x4[i];
+  } else {
+    for (int i = tid; i < T * V * 3; i += nthr) xs[i] = xg[i];
+  }
   compute_coef(p, coef);
   __syncthreads();
   const float inv = 1.0f / (float)(p.IC * T);
-  for (int pr = threadIdx.x; pr < V * V; pr += blockDim.x) {
-    const int u = pr / V, v = pr % V;
-    float g[9], su[3], sv[3];
-    gram_pair(xs, T, V, u, v, g, su, sv);
+  // Gram form of the scores: two threads per (u, v) pair, each over half of the frames, combined by one shuffle
+  for (int it = tid; it < ((V * V * 2 + 31) & ~31); it += nthr) {
+    const int pr = it >> 1, half = it & 1;
+    const bool live = pr < V * V;
+    const int u = live ? pr / V : 0, v = live ? pr % V : 0;
+    float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, su[3] = {0.f, 0.f, 0.f}, sv[3] = {0.f, 0.f, 0.f};
+    const int t0 = half ? (T + 1) / 2 : 0, t1 = half ? T : (T + 1) / 2;
+    for (int t = t0; t < t1; ++t) {
+      const float* xu = xs + (t * V + u) * 3;
+      const float* xv = xs + (t * V + v) * 3;
+      const float u0 = xu[0], u1 = xu[1], u2 = xu[2], v0 = xv[0], v1 = xv[1], v2 = xv[2];
+      g[0] += u0 * v0; g[1] += u0 * v1; g[2] += u0 * v2;
+      g[3] += u1 * v0; g[4] += u1 * v1; g[5] += u1 * v2;
+      g[6] += u2 * v0; g[7] += u2 * v1; g[8] += u2 * v2;
+      su[0] += u0; su[1] += u1; su[2] += u2;
+      sv[0] += v0; sv[1] += v1; sv[2] += v2;
+    }
+    float sc[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      float s = 0.f;
+    for (int i = 0; i < 3; ++i) {   // the score is linear in (g, su, sv): each half contributes its partial
+      float acc = 0.f;
 #pragma unroll
-      for (int q = 0; q < 9; ++q) s += coef[i][q] * g[q];
+      for (int q = 0; q < 9; ++q) acc += coef[i][q] * g[q];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) s += coef[i][9 + a] * su[a] + coef[i][12 + a] * sv[a];
-      Ms[(i * V + u) * V + v] = s * inv;
+      for (int a = 0; a < 3; ++a) acc += coef[i][9 + a] * su[a] + coef[i][12 + a] * sv[a];
+      sc[i] = acc + __shfl_xor_sync(0xffffffffu, acc, 1);
+    }
+    if (live && half == 0) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Ms[(i * V + u) * V + v] = sc[i] * inv;
     }
   }
   __syncthreads();
-  for (int col = threadIdx.x; col < 3 * V; col += blockDim.x) {  // softmax over u for fixed (i, v)
+  // softmax over u for fixed (i, v): one warp per column, lanes over u (V <= 64: two rows per lane)
+  for (int col = warp; col < 3 * V; col += nthr >> 5) {
     const int i = col / V, v = col % V;
-    float mx = -INFINITY;
-    for (int u = 0; u < V; ++u) mx = fmaxf(mx, Ms[(i * V + u) * V + v]);
-    float den = 0.f;
-    for (int u = 0; u < V; ++u) den += __expf(Ms[(i * V + u) * V + v] - mx);
-    const float rden = 1.0f / den;
-    for (int u = 0; u < V; ++u) {
-      const int idx = (i * V + u) * V + v;
-      const float m = __expf(Ms[idx] - mx) * rden + p.A[idx] + p.PA[idx];
+    const int u0 = lane, u1 = lane + 32;
+    const float s0 = u0 < V ? Ms[(i * V + u0) * V + v] : -INFINITY;
+    const float s1 = u1 < V ? Ms[(i * V + u1) * V + v] : -INFINITY;
+    const float mx = warp_max(fmaxf(s0, s1));
+    const float e0 = u0 < V ? __expf(s0 - mx) : 0.f, e1 = u1 < V ? __expf(s1 - mx) : 0.f;
+    const float rden = 1.0f / warp_sum(e0 + e1);
+    if (u0 < V) {
+      const int idx = (i * V + u0) * V + v;
+      const float m = e0 * rden + p.A[idx] + p.PA[idx];
+      Ms[idx] = m;
+      p.Mmat[(int64_t)n * 3 * V * V + idx] = m;
+    }
+    if (u1 < V) {
+      const int idx = (i * V + u1) * V + v;
+      const float m = e1 * rden + p.A[idx] + p.PA[idx];
       Ms[idx] = m;
       p.Mmat[(int64_t)n * 3 * V * V + idx] = m;
     }
@@ -223,11 +279,11 @@ __global__ void __launch_bounds__(kThreads) gcn0_scores_kernel(const afb_gcn0_fw
   if (p.Aop != nullptr) {   // operands of the tensor-core apply pass: A_i[v][u] = M_i[u][v] (bf16, zero padded) + colsum
     const int VP = p.V <= 16 ? 16 : (p.V <= 32 ? 32 : 48), AP = VP + 8;
     bf16* Ag = reinterpret_cast<bf16*>(p.Aop) + (int64_t)n * 3 * VP * AP;
-    for (int e = threadIdx.x; e < 3 * VP * AP; e += blockDim.x) {
+    for (int e = tid; e < 3 * VP * AP; e += nthr) {
       const int i = e / (VP * AP), r = e % (VP * AP), v = r / AP, u = r % AP;
       Ag[e] = __float2bfloat16_rn((v < V && u < V) ? Ms[(i * V + u) * V + v] : 0.f);
     }
-    for (int e = threadIdx.x; e < 3 * VP; e += blockDim.x) {
+    for (int e = tid; e < 3 * VP; e += nthr) {
       const int i = e / VP, v = e % VP;
       float cs = 0.f;
       if (v < V)
@@ -235,8 +291,8 @@ __global__ void __launch_bounds__(kThreads) gcn0_scores_kernel(const afb_gcn0_fw
       p.colsum[(int64_t)n * 3 * VP + e] = cs;
     }
   }
-  // moments: thread (j, seg) owns moment j (12 first + 78 second) over every other position -- no shuffles
-  const int mj = threadIdx.x % 90, seg = threadIdx.x / 90;
+  // moments: thread (j, seg) owns moment j (12 first + 78 second) over every kMomSegs-th position -- no shuffles
+  const int mj = tid % 90, seg = tid / 90;
   int pa = 0, pb = 0;
   if (mj >= NR) {
     int rem = mj - NR;
@@ -247,7 +303,7 @@ __global__ void __launch_bounds__(kThreads) gcn0_scores_kernel(const afb_gcn0_fw
   float macc = 0.f;
   for (int c0 = 0; c0 < T * V; c0 += kPosChunk) {
     const int np = min(kPosChunk, T * V - c0);
-    for (int it = threadIdx.x; it < np * 4; it += blockDim.x) {  // r vectors of this chunk: (position, subset | x)
+    for (int it = tid; it < np * 4; it += nthr) {  // r vectors of this chunk: (position, subset | x)
       const int pl = it >> 2, i = it & 3, pos = c0 + pl;
       const int t = pos / V, v = pos % V;
       const float* xt = xs + t * V * 3;
@@ -264,23 +320,27 @@ __global__ void __launch_bounds__(kThreads) gcn0_scores_kernel(const afb_gcn0_fw
       }
     }
     __syncthreads();
-    if (seg < 2) {
+    if (seg < kMomSegs) {
       if (mj < NR) {
-        for (int pl = seg; pl < np; pl += 2) macc += rs[pl * NR + mj];
+        for (int pl = seg; pl < np; pl += kMomSegs) macc += rs[pl * NR + mj];
       } else {
-        for (int pl = seg; pl < np; pl += 2) macc += rs[pl * NR + pa] * rs[pl * NR + pb];
+        for (int pl = seg; pl < np; pl += kMomSegs) macc += rs[pl * NR + pa] * rs[pl * NR + pb];
       }
     }
     __syncthreads();
   }
-  if (seg < 2) part[seg * NMOM + mj] = macc;
+  if (seg < kMomSegs) part[seg * NMOM + mj] = macc;
   __syncthreads();
-  if (threadIdx.x < 90)
-    atomicAdd(p.moments + (blockIdx.x % kSlots) * NMOM + threadIdx.x, (double)part[threadIdx.x] + (double)part[NMOM + threadIdx.x]);
+  if (tid < 90) {
+    double tot = 0.0;
+#pragma unroll
+    for (int sg = 0; sg < kMomSegs; ++sg) tot += (double)part[sg * NMOM + tid];
+    atomicAdd(p.moments + (blockIdx.x % kSlots) * NMOM + tid, tot);
+  }
   // last CTA to finish turns the accumulated moments into statistics and folded weights
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(p.counter, 1) == (int)gridDim.x - 1;
+  if (tid == 0) is_last = atomicAdd(p.counter, 1) == (int)gridDim.x - 1;
   __syncthreads();
   if (is_last) {
     __threadfence();
@@ -438,13 +498,16 @@ __global__ void __launch_bounds__(kThreads) gcn0_apply_mma_kernel(const afb_gcn0
   bf16* stage = Asm + 3 * VP * AP;                             // [8 warps][VP][OP]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
 
-  {
+  {  // operand staging with cp.async: every 16-byte (A) / 4-byte (x) piece is in flight at once
     const uint4* Ag = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.Aop) + (int64_t)n * 3 * VP * AP);
     uint4* As4 = reinterpret_cast<uint4*>(Asm);
-    for (int i = threadIdx.x; i < 3 * VP * AP / 8; i += blockDim.x) As4[i] = Ag[i];
+    for (int i = threadIdx.x; i < 3 * VP * AP / 8; i += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(As4 + i)), "l"(Ag + i) : "memory");
+    const float* xg = p.x + ((int64_t)n * T + t0) * V * 3;
+    for (int i = threadIdx.x; i < tt * V * 3; i += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(xs + i)), "l"(xg + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  const float* xg = p.x + ((int64_t)n * T + t0) * V * 3;
-  for (int i = threadIdx.x; i < tt * V * 3; i += blockDim.x) xs[i] = xg[i];
   if (threadIdx.x < 16) ctr[threadIdx.x] = threadIdx.x < NR ? p.stats[threadIdx.x] : 0.f;
   if (threadIdx.x < 3 * VP) colsum[threadIdx.x] = p.colsum[(int64_t)n * 3 * VP + threadIdx.x];
   uint32_t bfrag[COUT / 8][2];
@@ -454,6 +517,7 @@ __global__ void __launch_bounds__(kThreads) gcn0_apply_mma_kernel(const afb_gcn0
     bfrag[nt][0] = f.x;
     bfrag[nt][1] = f.y;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   for (int e = threadIdx.x; e < 9 * VP; e += blockDim.x) {
     const int slot = e / VP, v = e % VP;
@@ -851,11 +915,11 @@ extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
   cudaStream_t st = as_stream(s);
   const int T = p->T, V = p->V;
   {
-    size_t smem = ((size_t)a4(T * V * 3) + a4(3 * V * V) + (size_t)kPosChunk * NR + 2 * NMOM) * sizeof(float);
+    size_t smem = ((size_t)a4(T * V * 3) + a4(3 * V * V) + (size_t)kPosChunk * NR + kMomSegs * NMOM) * sizeof(float);
     if (smem < 2048 + 8) smem = 2048 + 8;   // the finalize step reuses the buffer for ~252 doubles
     AFB_REQUIRE(smem <= 220 * 1024, "gcn0: T*V too large for the per-sample shared-memory stage (%zu B)", smem);
     if ((rc = set_smem(gcn0_scores_kernel, smem, "gcn0_scores"))) return rc;
-    gcn0_scores_kernel<<<p->N, kThreads, smem, st>>>(*p);
+    gcn0_scores_kernel<<<p->N, kScoreThreads, smem, st>>>(*p);
     if ((rc = check_launch("gcn0_scores"))) return rc;
   }
   const int TT = pick_tt(T, V), chunks = ceil_div(T, TT);
@@ -864,7 +928,7 @@ extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
   const bool mma = !p->precise && p->y_dtype == AFB_BF16 && p->Cout == 128;
   static const bool old_apply = getenv("AFB_GCN0_APPLY_V1") != nullptr;
   if (mma && !old_apply && V <= 48 && p->Aop != nullptr && p->colsum != nullptr && p->Wfrag != nullptr) {
-    const int TT2 = T < 16 ? T : 16, chunks2 = ceil_div(T, TT2);
+    const int TT2 = T < 8 ? T : 8, chunks2 = ceil_div(T, TT2);   // one frame per warp; 2 CTAs per SM overlap each other's setup
     const int VP = V <= 16 ? 16 : (V <= 32 ? 32 : 48);
     const size_t smem2 = ((size_t)a4(TT2 * V * 3) + 12 * VP + 16) * sizeof(float) + (size_t)3 * VP * (VP + 8) * 2 +
                          (size_t)(kThreads / 32) * VP * (128 + 8) * 2;
