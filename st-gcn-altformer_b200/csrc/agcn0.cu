@@ -58,6 +58,17 @@ __device__ void compute_coef(const afb_gcn0_fwd_t& p, float (*coef)[16]) {
   }
 }
 
+// two adjacent elements (even index) as floats
+template <typename T> __device__ __forceinline__ void ld2f(const T* p, float& a, float& b);
+template <> __device__ __forceinline__ void ld2f<float>(const float* p, float& a, float& b) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  a = v.x; b = v.y;
+}
+template <> __device__ __forceinline__ void ld2f<bf16>(const bf16* p, float& a, float& b) {
+  const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+  a = __uint_as_float(v << 16); b = __uint_as_float(v & 0xffff0000u);
+}
+
 // g[a][b] = sum_t x[t,u,a] x[t,v,b], su[a] = sum_t x[t,u,a], sv[b] = sum_t x[t,v,b]
 __device__ __forceinline__ void gram_pair(const float* xs, int T, int V, int u, int v, float (&g)[9], float (&su)[3], float (&sv)[3]) {
 #pragma unroll
@@ -617,7 +628,7 @@ __global__ void __launch_bounds__(kThreads) gcn0_bwd_q_kernel(const afb_gcn0_bwd
   float* xs = Ms + 3 * V * V;
   float* ctr = xs + TT * V * 3;
   float* Aop = ctr + 16;             // [TT*V][13]
-  float* part = Aop + TT * V * 13;   // [kThreads][13]
+  float* part = Aop + TT * V * 13;   // [parts][Cout][13]  (parts * Cout = 2 * kThreads)
   const float* Mg = p.Mmat + (int64_t)n * 3 * V * V;
   for (int i = threadIdx.x; i < 3 * V * V; i += blockDim.x) Ms[i] = Mg[i];
   const float* xg = p.x + ((int64_t)n * T + t0) * V * 3;
@@ -635,22 +646,46 @@ __global__ void __launch_bounds__(kThreads) gcn0_bwd_q_kernel(const afb_gcn0_bwd
   const int64_t row0 = ((int64_t)n * T + t0) * V;
   const TY* dy = reinterpret_cast<const TY*>(b.dy) + row0 * Cout;
   const TY* y = reinterpret_cast<const TY*>(p.y) + row0 * Cout;
-  const int o = threadIdx.x % Cout, part_id = threadIdx.x / Cout, nparts = kThreads / Cout;
-  float acc[13];
+  // thread = 2 adjacent channels x one slice of the positions; the y / dy loads of 4 positions are issued
+  // before any of them is used (the old one-position-at-a-time loop with the dy load behind the ReLU test was
+  // a chain of dependent global loads)
+  const int half_c = Cout / 2;
+  const int o2 = (threadIdx.x % half_c) * 2, part_id = threadIdx.x / half_c, nparts = kThreads / half_c;
+  float acc0[13], acc1[13];
 #pragma unroll
-  for (int j = 0; j < 13; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 13; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
   if (part_id < nparts) {
-    for (int pos = part_id; pos < P; pos += nparts) {
-      const float yv = ldf<TY>(y + (int64_t)pos * Cout + o);
-      if (yv > 0.f) {
-        const float g1 = ldf<TY>(dy + (int64_t)pos * Cout + o);
+    for (int pos0 = part_id; pos0 < P; pos0 += 4 * nparts) {
+      float ya[4], yb[4], ga[4], gb[4];
 #pragma unroll
-        for (int j = 0; j < 13; ++j) acc[j] += g1 * Aop[pos * 13 + j];
+      for (int u = 0; u < 4; ++u) {
+        const int pos = pos0 + u * nparts;
+        ya[u] = yb[u] = ga[u] = gb[u] = 0.f;
+        if (pos < P) {
+          ld2f<TY>(y + (int64_t)pos * Cout + o2, ya[u], yb[u]);
+          ld2f<TY>(dy + (int64_t)pos * Cout + o2, ga[u], gb[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pos = pos0 + u * nparts;
+        if (pos < P) {
+          const float g0 = ya[u] > 0.f ? ga[u] : 0.f, g1 = yb[u] > 0.f ? gb[u] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 13; ++j) {
+            const float a = Aop[pos * 13 + j];
+            acc0[j] = fmaf(g0, a, acc0[j]);
+            acc1[j] = fmaf(g1, a, acc1[j]);
+          }
+        }
       }
     }
-  }
 #pragma unroll
-  for (int j = 0; j < 13; ++j) part[threadIdx.x * 13 + j] = acc[j];
+    for (int j = 0; j < 13; ++j) {
+      part[(part_id * Cout + o2) * 13 + j] = acc0[j];
+      part[(part_id * Cout + o2 + 1) * 13 + j] = acc1[j];
+    }
+  }
   __syncthreads();
   for (int e = threadIdx.x; e < Cout * 13; e += blockDim.x) {
     const int oo = e / 13, j = e % 13;
@@ -753,40 +788,59 @@ __global__ void __launch_bounds__(kThreads) gcn0_bwd_dz_kernel(const afb_gcn0_bw
   __syncthreads();
   const TY* dy = reinterpret_cast<const TY*>(b.dy) + (int64_t)n * T * V * Cout;
   const TY* y = reinterpret_cast<const TY*>(p.y) + (int64_t)n * T * V * Cout;
-  for (int pos = warp; pos < T * V; pos += kThreads / 32) {
-    float part[9];
+  // centred z of every position, all threads (the old per-position recompute ran on 9 lanes, 22 serial steps each);
+  // it is parked in dz[] and replaced by the finished dz below
+  for (int it = threadIdx.x; it < T * V * 3; it += blockDim.x) {
+    const int pos = it / 3, i = it % 3, tl = pos / V, v = pos % V;
+    const float* xt = xs + tl * V * 3;
+    float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+    for (int u = 0; u < V; ++u) {
+      const float m = Ms[(i * V + u) * V + v];
+      z0 += xt[u * 3] * m; z1 += xt[u * 3 + 1] * m; z2 += xt[u * 3 + 2] * m;
+    }
+    dz[pos * 9 + i * 3] = z0 - E[i * 3]; dz[pos * 9 + i * 3 + 1] = z1 - E[i * 3 + 1]; dz[pos * 9 + i * 3 + 2] = z2 - E[i * 3 + 2];
+  }
+  __syncthreads();
+  // dz[pos][j] = sum_c relu'(y) dy[pos][c] U[c][j] - c_j - sum_k zc_k K[k][j]; two positions per warp step so both
+  // rows' loads are in flight together
+  for (int pos0 = warp * 2; pos0 < T * V; pos0 += 2 * (kThreads / 32)) {
+    float part[2][9];
+    float yv[2][CPL], gv[2][CPL];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) part[j] = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const int pos = min(pos0 + h, T * V - 1);
 #pragma unroll
-    for (int q = 0; q < CPL; ++q) {
-      const int c = lane * CPL + q;
-      const float yv = ldf<TY>(y + (int64_t)pos * Cout + c);
-      const float g1 = yv > 0.f ? ldf<TY>(dy + (int64_t)pos * Cout + c) : 0.f;
-#pragma unroll
-      for (int j = 0; j < 9; ++j) part[j] += g1 * U[q][j];
+      for (int q = 0; q < CPL; q += 2) {
+        ld2f<TY>(y + (int64_t)pos * Cout + lane * CPL + q, yv[h][q], yv[h][q + 1]);
+        ld2f<TY>(dy + (int64_t)pos * Cout + lane * CPL + q, gv[h][q], gv[h][q + 1]);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 9; ++j) part[j] = warp_sum(part[j]);
-    // lane k < 9 computes the centred z_k of this position
-    const int tl = pos / V, v = pos % V;
-    float rc = 0.f;
-    if (lane < 9) {
-      const int i = lane / 3, a = lane % 3;
-      const float* xt = xs + tl * V * 3;
-      for (int u = 0; u < V; ++u) rc += xt[u * 3 + a] * Ms[(i * V + u) * V + v];
-      rc -= E[lane];
-    }
-    float corr = 0.f;
+    for (int h = 0; h < 2; ++h) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const float rk = __shfl_sync(0xffffffffu, rc, k);
-      if (lane < 9) corr += rk * Kmat[k * 9 + lane];
-    }
-    if (lane < 9) {
-      float mine = part[0];
+      for (int j = 0; j < 9; ++j) part[h][j] = 0.f;
 #pragma unroll
-      for (int j = 1; j < 9; ++j) mine = lane == j ? part[j] : mine;
-      dz[pos * 9 + lane] = mine - cvec[lane] - corr;
+      for (int q = 0; q < CPL; ++q) {
+        const float g1 = yv[h][q] > 0.f ? gv[h][q] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) part[h][j] = fmaf(g1, U[q][j], part[h][j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 9; ++j) part[h][j] = warp_sum(part[h][j]);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pos = pos0 + h;
+      if (pos < T * V && lane < 9) {
+        float corr = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) corr = fmaf(dz[pos * 9 + k], Kmat[k * 9 + lane], corr);
+        float mine = part[h][0];
+#pragma unroll
+        for (int j = 1; j < 9; ++j) mine = lane == j ? part[h][j] : mine;
+        __syncwarp(0x1ffu);   // all 9 lanes have read the parked z of this position before it is overwritten
+        dz[pos * 9 + lane] = mine - cvec[lane] - corr;
+      }
     }
   }
   __syncthreads();
@@ -971,7 +1025,7 @@ extern "C" int afb_gcn0_bwd(const afb_gcn0_bwd_t* b, afb_stream s) {
   if (e != cudaSuccess) { set_error("gcn0_bwd: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
   const int TT = pick_tt(T, V), chunks = ceil_div(T, TT);
   {
-    const size_t smem = ((size_t)3 * V * V + TT * V * 3 + 16 + (size_t)TT * V * 13 + kThreads * 13) * sizeof(float);
+    const size_t smem = ((size_t)3 * V * V + TT * V * 3 + 16 + (size_t)TT * V * 13 + 2 * kThreads * 13) * sizeof(float);
     if (p->y_dtype == AFB_BF16) {
       if ((rc = set_smem(gcn0_bwd_q_kernel<bf16>, smem, "gcn0_bwd_q"))) return rc;
       gcn0_bwd_q_kernel<bf16><<<p->N * chunks, kThreads, smem, st>>>(*b, TT, chunks);
@@ -992,11 +1046,11 @@ extern "C" int afb_gcn0_bwd(const afb_gcn0_bwd_t* b, afb_stream s) {
     gcn0_bwd_dz_kernel<TYPE, CPL_><<<p->N, kThreads, smem, st>>>(*b);                      \
   } while (0)
     const int cpl = Cout / 32;
-    AFB_REQUIRE(cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8, "gcn0_bwd: Cout=%d unsupported", Cout);
+    AFB_REQUIRE(cpl == 2 || cpl == 4 || cpl == 8, "gcn0_bwd: Cout=%d unsupported (64, 128 or 256)", Cout);
     if (p->y_dtype == AFB_BF16) {
-      if (cpl == 1) LAUNCH_DZ(bf16, 1); else if (cpl == 2) LAUNCH_DZ(bf16, 2); else if (cpl == 4) LAUNCH_DZ(bf16, 4); else LAUNCH_DZ(bf16, 8);
+      if (cpl == 2) LAUNCH_DZ(bf16, 2); else if (cpl == 4) LAUNCH_DZ(bf16, 4); else LAUNCH_DZ(bf16, 8);
     } else {
-      if (cpl == 1) LAUNCH_DZ(float, 1); else if (cpl == 2) LAUNCH_DZ(float, 2); else if (cpl == 4) LAUNCH_DZ(float, 4); else LAUNCH_DZ(float, 8);
+      if (cpl == 2) LAUNCH_DZ(float, 2); else if (cpl == 4) LAUNCH_DZ(float, 4); else LAUNCH_DZ(float, 8);
     }
 #undef LAUNCH_DZ
     if ((rc = check_launch("gcn0_bwd_dz"))) return rc;
