@@ -123,7 +123,7 @@ def run_reference(args):
     val = B / (ms / 1e3)
     cores = torch.get_num_threads()
     sample = f"batch {B} of the 256-sample step (fwd+CE+bwd+AdamW), fp32, {cores} threads"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "seq/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -208,7 +208,30 @@ def cpu_baseline(budget_s=20.0):
             "sample": f"{len(times) - 1} train steps of batch {B} (of the 256-sample step), oracle port, fp32, {cores} threads"}
 
 
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """stdout must carry exactly ONE JSON line: libraries (NCCL's version banner, torchrun notices) also write to
+    fd 1, so fd 1 is pointed at stderr for the run and the JSON line goes to a saved copy of the original."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -303,7 +326,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(out))
+        emit(out)
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()
