@@ -40,6 +40,13 @@ __device__ __forceinline__ float quad_max(float v) {
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
 }
 
+// 2^x on the SFU without the libm range fix-ups (arguments are <= 0 here; -inf -> 0, denormal results flush)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Geometry of one CTA's shared memory (all pitches are an odd number of 16-byte chunks => conflict-free
 // ldmatrix and 16-byte row copies).
 template <int DH, int LP, int HG> struct Geo {
@@ -126,12 +133,13 @@ __device__ __forceinline__ void scores_softmax(const bf16* sq, int qcol, int kco
   mx0 = quad_max(mx0);
   mx1 = quad_max(mx1);
   float sum0 = 0.f, sum1 = 0.f;
+  const float nm0 = -mx0 * scale_log2, nm1 = -mx1 * scale_log2;   // one FFMA + one MUFU.EX2 per element
 #pragma unroll
   for (int nj = 0; nj < LP / 8; ++nj) {
-    s[nj][0] = exp2f((s[nj][0] - mx0) * scale_log2);
-    s[nj][1] = exp2f((s[nj][1] - mx0) * scale_log2);
-    s[nj][2] = exp2f((s[nj][2] - mx1) * scale_log2);
-    s[nj][3] = exp2f((s[nj][3] - mx1) * scale_log2);
+    s[nj][0] = ex2_fast(fmaf(s[nj][0], scale_log2, nm0));
+    s[nj][1] = ex2_fast(fmaf(s[nj][1], scale_log2, nm0));
+    s[nj][2] = ex2_fast(fmaf(s[nj][2], scale_log2, nm1));
+    s[nj][3] = ex2_fast(fmaf(s[nj][3], scale_log2, nm1));
     sum0 += s[nj][0] + s[nj][1];
     sum1 += s[nj][2] + s[nj][3];
   }
@@ -192,8 +200,8 @@ __global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __res
   const int hw = threadIdx.x >> 5;
   const int qcol = hw * DH, kcol = G::W + hw * DH, vcol = 2 * G::W + hw * DH;
   const float scale_log2 = scale * 1.4426950408889634f;
-#pragma unroll 1
-  for (int mi = 0; mi < LP / 16; ++mi) {
+#pragma unroll
+  for (int mi = 0; mi < LP / 16; ++mi) {   // unrolled: every ldmatrix / store address becomes base + immediate
     if (mi * 16 >= L) break;
     float s[LP / 8][4];
     scores_softmax<DH, LP, G::QKV_PITCH>(sq, qcol, kcol, mi, L, scale_log2, s);
