@@ -108,6 +108,9 @@ typedef struct {
   float alpha;
   float* dbias; /* optional: dbias[n1] += alpha * sum_m G[m, n1] (bias gradient: column sums of the G tiles taken
                    from shared memory while the MMAs run, or one extra N=16 MMA against an all-ones operand) */
+  int32_t taps;           /* > 1 (<= 3, needs N1 <= 128 and N2 <= 128): one launch produces `taps` gradients that share G:  */
+  int32_t tap_row_stride; /*   dW[t * tap_dw_stride + ...] uses X rows shifted by x_row_shift + t * tap_row_stride          */
+  int64_t tap_dw_stride;  /*   (the k x 1 temporal conv: taps of one weight read the same dY tile). 0 / 1 = single tap.     */
   const float* dbias_row_scale; /* optional (needs N1 % 256 == 0): dbias[n1] += alpha * sum_m rs[m / row_scale_div] * G[m, n1]
                                    -- the DropPath keep factor of the bias path; dW itself is NOT scaled */
   int32_t row_scale_div;
@@ -140,6 +143,9 @@ int afb_cast_transpose(const float* src, void* dst_bf16, int rows, int cols, afb
 /* Conv2d weight (co, ci, k, 1) fp32 -> fwd bf16 [co][k][ci] and bwd bf16 [ci][k'][co] with k' = k-1-tap
  * (the flipped kernel of the transposed conv that yields dX).  Either output may be NULL. */
 int afb_conv_weight_pack(const float* w, void* fwd_bf16, void* bwd_bf16, int co, int ci, int k, afb_stream s);
+/* dW (co, ci, k) += tap-major weight gradient tmp [k][co][ci] (what afb_gemm_dw with taps > 1 produces with contiguous
+ * rows, so its epilogue can use 16-byte vector reductions); Conv2d weight gradient of model/net.py:50. */
+int afb_conv_dw_unpack(const float* tmp, float* dW, int co, int ci, int k, afb_stream s);
 /* hi/lo bf16 split of an fp32 matrix for the 3-pass fp32-parity GEMM: dst is [rows][3*cols] holding
  * (hi | lo | hi) when which == 0 (A side) or (hi | hi | lo) when which == 1 (B side); which == 2 stacks
  * (hi ; hi ; lo) along rows instead ([3*rows][cols], the MN-major B operand of dX = dY * W). */

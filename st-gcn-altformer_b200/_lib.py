@@ -29,6 +29,7 @@ class GemmTn(C.Structure):
 class GemmDw(C.Structure):
     _fields_ = [("G", vp), ("X", vp), ("dW", vp), ("rows_per_batch", i64), ("batches", i32), ("N1", i32), ("N2", i32),
                 ("ldg", i32), ("ldx", i32), ("ld1", i64), ("ld2", i64), ("x_row_shift", i32), ("alpha", f32), ("dbias", vp),
+                ("taps", i32), ("tap_row_stride", i32), ("tap_dw_stride", i64),
                 ("dbias_row_scale", vp), ("row_scale_div", i32)]
 
 
@@ -81,6 +82,7 @@ def _declare(L):
         "afb_copy2d": [vp, i32, i64, vp, i32, i64, i64, i32, vp],
         "afb_cast_transpose": [vp, vp, i32, i32, vp],
         "afb_conv_weight_pack": [vp, vp, vp, i32, i32, i32, vp],
+        "afb_conv_dw_unpack": [vp, vp, i32, i32, i32, vp],
         "afb_split3": [vp, vp, i64, i32, i32, vp],
         "afb_layernorm_fwd": [vp, i32, vp, vp, vp, i32, vp, vp, i64, i32, f32, vp],
         "afb_layernorm_bwd": [vp, i32, vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, i64, i32, vp],

@@ -54,6 +54,16 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, bf16* __restrict__
   }
 }
 
+// dW (co, ci, k) += tmp [k][co][ci]
+__global__ void conv_dw_unpack_kernel(const float* __restrict__ tmp, float* __restrict__ dW, int co, int ci, int k) {
+  const int64_t total = (int64_t)co * ci * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % k);
+    const int64_t oc = i / k;   // c_out * ci + c_in
+    dW[i] += tmp[(int64_t)tap * co * ci + oc];
+  }
+}
+
 template <typename S, typename D>
 __global__ void copy2d_kernel(const S* __restrict__ src, int64_t lds, D* __restrict__ dst, int64_t ldd, int64_t rows, int cols) {
   const int64_t total = rows * cols;
@@ -626,6 +636,12 @@ extern "C" int afb_conv_weight_pack(const float* w, void* fwd, void* bwd, int co
   AFB_REQUIRE(w && (fwd || bwd), "conv_weight_pack: bad args");
   conv_pack_kernel<<<grid_for((int64_t)co * ci * k, kBlock), kBlock, 0, as_stream(s)>>>(w, (bf16*)fwd, (bf16*)bwd, co, ci, k);
   return check_launch("conv_weight_pack");
+}
+
+extern "C" int afb_conv_dw_unpack(const float* tmp, float* dW, int co, int ci, int k, afb_stream s) {
+  AFB_REQUIRE(tmp && dW && co > 0 && ci > 0 && k > 0, "conv_dw_unpack: bad args");
+  conv_dw_unpack_kernel<<<grid_for((int64_t)co * ci * k, kBlock), kBlock, 0, as_stream(s)>>>(tmp, dW, co, ci, k);
+  return check_launch("conv_dw_unpack");
 }
 
 extern "C" int afb_copy2d(const void* src, int sd, int64_t lds, void* dst, int dd, int64_t ldd, int64_t rows, int cols, afb_stream s) {

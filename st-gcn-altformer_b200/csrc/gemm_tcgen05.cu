@@ -801,14 +801,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   otherwise idle epilogue warps straight from the G tiles in shared memory.
 //   BN1 = 128: one accumulator; the bias gradient rides on one extra N=16 MMA against an all-ones tile.
 // ---------------------------------------------------------------------------------------------
-template <int BN1, int BN2> struct DwCfg {
+template <int BN1, int BN2, int TAPS> struct DwCfg {
   static constexpr int kABytes = 64 * BN1 * 2;      // 64 rows x BN1 n1
-  static constexpr int kBBytes = 64 * BN2 * 2;      // 64 rows x BN2 n2
+  static constexpr int kTapBytes = 64 * BN2 * 2;    // 64 rows x BN2 n2 of one tap
+  static constexpr int kBBytes = TAPS * kTapBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;
   static constexpr bool kOnesTrick = BN1 == 128;
   // BN1 == 128: accumulator columns [0, BN2) hold dW, [BN2, BN2 + 16) hold G^T * ones (the bias gradient)
-  static constexpr int kUsedCols = kOnesTrick ? BN2 + 16 : 2 * BN2;
+  static constexpr int kUsedCols = kOnesTrick ? TAPS * BN2 + 16 : 2 * BN2;
   static constexpr int kTmemCols = kUsedCols > 256 ? 512 : (kUsedCols > 128 ? 256 : 128);
   static constexpr int kScratchBytes = kEpiWarps * 32 * kScratchStride * 4;
   static constexpr int kOnesBytes = 8192;           // one all-ones [64 x 64] bf16 tile (MN-major B operand)
@@ -824,16 +825,18 @@ struct DwArgs {
   long long ld1, ld2;
   float alpha;
   float* dbias;   // optional: dbias[n1] += alpha * sum_m G[m, n1]
+  int tap_row_stride;        // TAPS > 1: tap t reads X rows shifted by x_row_shift + t * tap_row_stride ...
+  long long tap_dw_stride;   // ... and accumulates into dW + t * tap_dw_stride
   int vec4;       // ld2 == 1 and 16-byte aligned rows: the epilogue uses red.global.add.v4.f32
   const float* dbias_rs;   // optional per-row factor of the bias gradient (smem column-sum path only)
   int rs_div;
   long long rows_per_batch;
 };
 
-template <int BN1, int BN2>
+template <int BN1, int BN2, int TAPS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const DwArgs p) {
-  using Cfg = DwCfg<BN1, BN2>;
+  using Cfg = DwCfg<BN1, BN2, TAPS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -901,8 +904,11 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           for (int j = 0; j < BN1 / 64; ++j)
             tma_load_3d(&tmG, full_bar(stage), sA + stage * Cfg::kABytes + j * 8192, n1_blk * BN1 + j * 64, r0, batch);
 #pragma unroll
-          for (int j = 0; j < BN2 / 64; ++j)
-            tma_load_3d(&tmX, full_bar(stage), sB + stage * Cfg::kBBytes + j * 8192, n2_blk * BN2 + j * 64, r0 + p.x_row_shift, batch);
+          for (int tap = 0; tap < TAPS; ++tap)
+#pragma unroll
+            for (int j = 0; j < BN2 / 64; ++j)
+              tma_load_3d(&tmX, full_bar(stage), sB + stage * Cfg::kBBytes + tap * Cfg::kTapBytes + j * 8192, n2_blk * BN2 + j * 64,
+                          r0 + p.x_row_shift + tap * p.tap_row_stride, batch);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -919,13 +925,16 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           const uint32_t b_addr = sB + stage * Cfg::kBBytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 16 contraction rows per MMA = two 8-row atoms
-            const uint64_t bdesc = make_desc(b_addr + k * 2048, 8192, 1024);
 #pragma unroll
             for (int h = 0; h < BN1 / 128; ++h) {   // 128 n1 columns = two 64-column boxes per accumulator
               const uint64_t adesc = make_desc(a_addr + h * 16384 + k * 2048, 8192, 1024);
-              umma_bf16(tmem_base + (uint32_t)(h * BN2), adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+#pragma unroll
+              for (int tap = 0; tap < TAPS; ++tap) {   // the taps of a k x 1 conv share the G tile
+                const uint64_t bdesc = make_desc(b_addr + tap * Cfg::kTapBytes + k * 2048, 8192, 1024);
+                umma_bf16(tmem_base + (uint32_t)((h * TAPS + tap) * BN2), adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+              }
               if (Cfg::kOnesTrick && do_bias)
-                umma_bf16(tmem_base + BN2, adesc, make_desc(sOnes, 8192, 1024), idesc_ones, (i | k) != 0 ? 1u : 0u);
+                umma_bf16(tmem_base + TAPS * BN2, adesc, make_desc(sOnes, 8192, 1024), idesc_ones, (i | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(empty_bar(stage));
@@ -984,10 +993,12 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
 #pragma unroll 1
-      for (int h = 0; h < BN1 / 128; ++h) {
+      for (int acc = 0; acc < (BN1 / 128) * TAPS; ++acc) {
+        const int h = acc / TAPS;
+        float* dWt = p.dW + (acc % TAPS) * p.tap_dw_stride;
         for (int ch = 0; ch < BN2 / 32; ++ch) {
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(h * BN2 + ch * 32), v);
+          tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN2 + ch * 32), v);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(my + lane * kScratchStride + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -1001,7 +1012,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
               const int n1 = n1_blk * BN1 + h * 128 + lane_grp * 32 + r;
               const float4 v4 = *reinterpret_cast<const float4*>(my + r * kScratchStride + c4);
               if (n1 < p.N1)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dW + n1 * p.ld1 + n2), "f"(p.alpha * v4.x),
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dWt + n1 * p.ld1 + n2), "f"(p.alpha * v4.x),
                              "f"(p.alpha * v4.y), "f"(p.alpha * v4.z), "f"(p.alpha * v4.w)
                              : "memory");
             }
@@ -1010,7 +1021,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
 #pragma unroll 4
             for (int r = 0; r < 32; ++r) {
               const int n1 = n1_blk * BN1 + h * 128 + lane_grp * 32 + r;
-              if (n1 < p.N1 && n2 < p.N2) atomicAdd(p.dW + n1 * p.ld1 + n2 * p.ld2, p.alpha * my[r * kScratchStride + lane]);
+              if (n1 < p.N1 && n2 < p.N2) atomicAdd(dWt + n1 * p.ld1 + n2 * p.ld2, p.alpha * my[r * kScratchStride + lane]);
             }
           }
           __syncwarp();
@@ -1018,7 +1029,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
       }
       if (Cfg::kOnesTrick && do_bias) {   // column BN2 of the accumulator = sum over this CTA's rows of G[:, n1]
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)BN2, v);
+        tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(TAPS * BN2), v);
         const int n1 = n1_blk * BN1 + lane_grp * 32 + lane;
         if (n1 < p.N1) atomicAdd(p.dbias + n1, p.alpha * v[0]);
       }
@@ -1116,12 +1127,12 @@ int launch_tn_stat(bool stat, const CUtensorMap& tmA, const CUtensorMap& tmB, co
   return stat ? launch_tn<BN, B_MN, true>(tmA, tmB, tmC, tmC2, a, st) : launch_tn<BN, B_MN, false>(tmA, tmB, tmC, tmC2, a, st);
 }
 
-template <int BN1, int BN2>
+template <int BN1, int BN2, int TAPS = 1>
 int launch_dw(const CUtensorMap& tmG, const CUtensorMap& tmX, const DwArgs& a, cudaStream_t st) {
-  using Cfg = DwCfg<BN1, BN2>;
+  using Cfg = DwCfg<BN1, BN2, TAPS>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_dw_kernel<BN1, BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_dw_kernel<BN1, BN2, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("gemm_dw: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
@@ -1129,7 +1140,7 @@ int launch_dw(const CUtensorMap& tmG, const CUtensorMap& tmX, const DwArgs& a, c
     configured = true;
   }
   const int grid = a.n1_tiles * a.n2_tiles * a.splits;
-  gemm_dw_kernel<BN1, BN2><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmG, tmX, a);
+  gemm_dw_kernel<BN1, BN2, TAPS><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmG, tmX, a);
   return check_launch("gemm_dw");
 }
 
@@ -1253,7 +1264,9 @@ extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
   AFB_REQUIRE(((uintptr_t)p->G & 15) == 0 && ((uintptr_t)p->X & 15) == 0, "gemm_dw: operands must be 16-byte aligned");
   const int BN2 = (p->N2 % 256 == 0) ? 256 : (p->N2 % 128 == 0 ? 128 : 64);
   static const bool no_wide = getenv("AFB_DW_BN1_128") != nullptr;
-  const int BN1 = (!no_wide && p->N1 % 256 == 0) ? 256 : 128;
+  const int taps = p->taps > 1 ? p->taps : 1;
+  AFB_REQUIRE(taps <= 3 && (taps == 1 || (p->N1 <= 128 && p->N2 <= 128)), "gemm_dw: taps=%d needs taps <= 3, N1 <= 128, N2 <= 128", taps);
+  const int BN1 = (!no_wide && taps == 1 && p->N1 % 256 == 0) ? 256 : 128;
   DwArgs a;
   a.n1_tiles = ceil_div(p->N1, BN1);
   a.n2_tiles = p->N2 / BN2;
@@ -1262,7 +1275,7 @@ extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
   const int tiles = a.n1_tiles * a.n2_tiles;
   // one CTA per SM (the smem ring takes ~200 KB): 256-wide tiles run as ONE wave, each CTA paying the pipeline
   // fill and the atomic epilogue once; the narrower tiles keep two waves (shorter tails for the conv shapes)
-  int splits = ((BN1 == 256 ? 1 : 2) * num_sms()) / tiles;
+  int splits = (((BN1 == 256 || taps > 1) ? 1 : 2) * num_sms()) / tiles;
   if (splits < 1) splits = 1;
   if (splits > a.total_row_blocks) splits = a.total_row_blocks;
   // keep at least 8 row blocks per split so the atomic epilogue is amortised
@@ -1271,7 +1284,8 @@ extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
   a.splits = splits;
   a.N1 = p->N1; a.N2 = p->N2; a.x_row_shift = p->x_row_shift;
   a.dW = p->dW; a.ld1 = p->ld1; a.ld2 = p->ld2; a.alpha = p->alpha; a.dbias = p->dbias;
-  a.vec4 = (p->ld2 == 1 && p->ld1 % 4 == 0 && ((uintptr_t)p->dW & 15) == 0) ? 1 : 0;
+  a.tap_row_stride = p->tap_row_stride; a.tap_dw_stride = p->tap_dw_stride;
+  a.vec4 = (p->ld2 == 1 && p->ld1 % 4 == 0 && ((uintptr_t)p->dW & 15) == 0 && (taps == 1 || p->tap_dw_stride % 4 == 0)) ? 1 : 0;
   a.dbias_rs = p->dbias != nullptr ? p->dbias_row_scale : nullptr;
   a.rs_div = p->row_scale_div > 0 ? p->row_scale_div : 1;
   a.rows_per_batch = p->rows_per_batch;
@@ -1284,6 +1298,10 @@ extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
                 (uint64_t)p->rows_per_batch * p->ldx, 64, 64, 3);
   if (rc) return rc;
   cudaStream_t st = as_stream(s);
+  if (taps > 1) {   // N2 <= 128: BN2 is 128 or 64
+    if (BN2 == 128) return taps == 3 ? launch_dw<128, 128, 3>(tmG, tmX, a, st) : launch_dw<128, 128, 2>(tmG, tmX, a, st);
+    return taps == 3 ? launch_dw<128, 64, 3>(tmG, tmX, a, st) : launch_dw<128, 64, 2>(tmG, tmX, a, st);
+  }
   if (BN1 == 256) {
     if (BN2 == 256) return launch_dw<256, 256>(tmG, tmX, a, st);
     if (BN2 == 128) return launch_dw<256, 128>(tmG, tmX, a, st);

@@ -489,17 +489,29 @@ class Unit2DFn(torch.autograd.Function):
         dy2 = None if dy2 is None else _as_act(dy2.contiguous())
         sg, sb = _grad_sink(bn_w), _grad_sink(bn_b)
         draw, _ = ops.bn_bwd(dy, dy2, raw, stats, bn_w.detach(), bn_b.detach(), True, training, sg[0], sb[0], T=T, V=V)
-        gcb = None
-        if conv_b is not None:
+        gcb, scb = None, None
+        if conv_b is not None:   # bias gradient = column sums of draw: rides on the first weight-gradient launch
             scb = _grad_sink(conv_b)
-            ops.colsum(draw, scb[0])
             gcb = _ret(scb)
+        db = None if scb is None else scb[0]
         sw = _grad_sink(conv_w)
         flat = sw[0].view(-1)
         pad = (k - 1) // 2
-        for tap in range(k):  # dW[co, ci, tap] = sum_rows draw[row, co] * x[row + (tap - pad) V, ci]
-            mm_dw(draw, x, flat[tap:], N1=co, N2=ci, rows_per_batch=T * V, batches=N, ld1=ci * k, ld2=k,
-                  x_row_shift=(tap - pad) * V)
+        # dW[co, ci, tap] = sum_rows draw[row, co] * x[row + (tap - pad) V, ci]
+        if co <= 128 and ci <= 128 and ci % 64 == 0:
+            # three taps per launch share every dY tile; the tap-major scratch keeps gradient rows contiguous
+            # (16-byte vector reductions) and is folded into the (co, ci, k) gradient by one small kernel
+            tmp = torch.zeros((k, co, ci), device=x.device, dtype=torch.float32)
+            tflat = tmp.view(-1)
+            for t0 in range(0, k, 3):
+                mm_dw(draw, x, tflat[t0 * co * ci:], N1=co, N2=ci, rows_per_batch=T * V, batches=N, ld1=ci, ld2=1,
+                      x_row_shift=(t0 - pad) * V, taps=min(3, k - t0), tap_row_stride=V, tap_dw_stride=co * ci,
+                      dbias=db if t0 == 0 else None)
+            ops.conv_dw_unpack(tmp, flat, co, ci, k)
+        else:
+            for tap in range(k):
+                mm_dw(draw, x, flat[tap:], N1=co, N2=ci, rows_per_batch=T * V, batches=N, ld1=ci * k, ld2=k,
+                      x_row_shift=(tap - pad) * V, dbias=db if tap == 0 else None)
         dx = None
         if ctx.needs_input_grad[0]:
             _, bwd_w = conv_packs(conv_w)

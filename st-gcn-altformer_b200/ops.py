@@ -91,9 +91,11 @@ def gemm_tn(a, b, N, *, k_per_tap=None, taps=1, tap_row_stride=0, tap_pad=0, row
 
 
 def gemm_dw(g, x, dW, *, N1=None, N2=None, rows_per_batch=None, batches=1, ld1=None, ld2=1, x_row_shift=0, alpha=1.0,
-            g_col0=0, x_col0=0, dbias=None, dbias_row_scale=None, row_scale_div=1):
+            g_col0=0, x_col0=0, dbias=None, dbias_row_scale=None, row_scale_div=1, taps=1, tap_row_stride=0, tap_dw_stride=0):
     """dW[n1*ld1 + n2*ld2] += alpha * sum_m g[m, g_col0 + n1] * x[m + shift, x_col0 + n2]  (fp32 atomics);
-    dbias[n1] += alpha * sum_m (rs[m // row_scale_div]) * g[m, g_col0 + n1] when given (rs = dbias_row_scale or 1)."""
+    dbias[n1] += alpha * sum_m (rs[m // row_scale_div]) * g[m, g_col0 + n1] when given (rs = dbias_row_scale or 1).
+    taps in (2, 3): the launch produces `taps` gradients sharing g -- tap t reads x rows shifted by a further
+    t * tap_row_stride and accumulates into dW.view(-1)[t * tap_dw_stride:] (k x 1 temporal conv)."""
     need_cuda(g, x, dW, dbias, dbias_row_scale)
     if g.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dW.dtype != torch.float32:
         raise RuntimeError("gemm_dw: g, x must be bfloat16 and dW float32")
@@ -105,6 +107,7 @@ def gemm_dw(g, x, dW, *, N1=None, N2=None, rows_per_batch=None, batches=1, ld1=N
     p = _lib.GemmDw(G=ptr(g) + 2 * g_col0, X=ptr(x) + 2 * x_col0, dW=ptr(dW), rows_per_batch=rows_per_batch,
                     batches=batches, N1=N1, N2=N2, ldg=g.shape[1], ldx=x.shape[1],
                     ld1=N2 if ld1 is None else ld1, ld2=ld2, x_row_shift=x_row_shift, alpha=alpha, dbias=ptr(dbias),
+                    taps=taps, tap_row_stride=tap_row_stride, tap_dw_stride=tap_dw_stride,
                     dbias_row_scale=ptr(dbias_row_scale), row_scale_div=row_scale_div)
     _call("afb_gemm_dw", C.byref(p), stream())
     return dW
@@ -150,6 +153,13 @@ def cast_transpose(w):
     y = torch.empty((cols, rows), device=w.device, dtype=torch.bfloat16)
     _call("afb_cast_transpose", ptr(w), ptr(y), rows, cols, stream())
     return y
+
+
+def conv_dw_unpack(tmp, dW, co, ci, k):
+    """dW (co, ci, k) += tmp [k][co][ci] (tap-major gradient produced by gemm_dw(taps=...))."""
+    need_cuda(tmp, dW)
+    _call("afb_conv_dw_unpack", ptr(tmp), ptr(dW), co, ci, k, stream())
+    return dW
 
 
 def conv_weight_pack(w, fwd=None, bwd=None):

@@ -400,6 +400,20 @@ def grp_gemm_dw():
         for tap in range(9):
             ops.gemm_dw(dtok, tok, flat[tap:], N1=Co, N2=Cc, rows_per_batch=T * V, batches=Nb, ld1=Cc * 9, ld2=9, x_row_shift=(tap - 4) * V)
         report("conv9x1 dW via 9 shifted gemm_dw", dW, w.grad[..., 0], 3e-3)
+        # three taps per launch (shared dY tile), tap-major scratch, bias gradient from the first group
+        tmp = torch.zeros(9, Co, Cc, device=DEV)
+        db = torch.zeros(Co, device=DEV)
+        for t0 in range(0, 9, 3):
+            ops.gemm_dw(dtok, tok, tmp.view(-1)[t0 * Co * Cc:], N1=Co, N2=Cc, rows_per_batch=T * V, batches=Nb, ld1=Cc, ld2=1,
+                        x_row_shift=(t0 - 4) * V, taps=3, tap_row_stride=V, tap_dw_stride=Co * Cc, dbias=db if t0 == 0 else None)
+        dW2 = torch.full((Co, Cc, 9), 0.5, device=DEV)
+        ops.conv_dw_unpack(tmp, dW2, Co, Cc, 9)
+        report("conv9x1 dW via 3 x 3-tap gemm_dw + unpack", dW2 - 0.5, w.grad[..., 0], 3e-3)
+        report("conv9x1 dbias from the first tap group", db, dtok.float().sum(0), 3e-3)
+        tmp2 = torch.zeros(2, Co, Cc, device=DEV)
+        ops.gemm_dw(dtok, tok, tmp2.view(-1), N1=Co, N2=Cc, rows_per_batch=T * V, batches=Nb, ld1=Cc, ld2=1, x_row_shift=-V, taps=2,
+                    tap_row_stride=V, tap_dw_stride=Co * Cc)
+        report("gemm_dw taps=2", tmp2, w.grad[..., 0].permute(2, 0, 1)[3:5], 3e-3)
     check(conv_dw)
 
 
