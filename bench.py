@@ -184,7 +184,12 @@ def gcn0_roofline(model, x, dev, pk, iters=20):
     achieved = alg_bytes / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "gcn0 = unit_agcn(3->128) forward (gcn0_scores [+finalize in its last CTA] + gcn0_apply)",
             "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"], "frac_of_8TBps_nominal": achieved / 8000.0,
-            "peak_source": pk["src"], "traffic": None, "alg_bytes_per_launch": alg_bytes, "ms_per_launch": ms}
+            "peak_source": pk["src"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of the two kernels, ncu --set full at this batch
+            # (profiles/r01_ncu_gcn0_v3.txt): 6.5 MB read; the 46 MB output lands in L2 and is written back while the
+            # next kernel runs (45.1 MB of write-back observed there).  Only meaningful for the default batch of 256.
+            "traffic": 51.6e6 if N == 256 and T == 32 and V == 22 else None,
+            "alg_bytes_per_launch": alg_bytes, "ms_per_launch": ms}
 
 
 def cpu_baseline(budget_s=20.0):

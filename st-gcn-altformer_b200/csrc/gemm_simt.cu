@@ -7,6 +7,9 @@ namespace {
 
 constexpr int TS = 32;  // tile edge; 256 threads, each computes a 2x2 micro-tile
 
+__device__ __forceinline__ void atomic_add_f32(float* p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add_f32(bf16*, float) {}   // split-K is never selected for bf16 outputs
+
 template <typename TA, typename TB, typename TC>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ B, TC* __restrict__ C,
                                                         const float* __restrict__ bias, int M, int N, int K, int64_t sai, int64_t sak,
@@ -16,7 +19,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int i0 = blockIdx.y * TS, j0 = blockIdx.x * TS;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = 0; k0 < K; k0 += TS) {
+  // split-K (gridDim.z > 1, fp32 C only): each z slice owns a range of 32-wide k-steps and adds its partial with
+  // atomics; the host has already applied beta (zeroed C when beta == 0), slice 0 adds the bias.
+  const int ksteps = (K + TS - 1) / TS, per = (ksteps + gridDim.z - 1) / gridDim.z;
+  const int kbeg = blockIdx.z * per * TS, kend = min(K, (int)(blockIdx.z + 1) * per * TS);
+  const bool split = gridDim.z > 1;
+  for (int k0 = kbeg; k0 < kend; k0 += TS) {
     for (int e = threadIdx.x; e < TS * TS; e += 256) {
       // pick the faster-varying index along whichever stride is 1 so loads coalesce
       int r, c;
@@ -46,10 +54,14 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
     for (int w = 0; w < 2; ++w) {
       const int i = i0 + ty + 16 * u, j = j0 + tx + 16 * w;
       if (i < M && j < N) {
-        float v = alpha * acc[u][w] + (bias ? bias[j] : 0.f);
+        float v = alpha * acc[u][w] + ((bias && blockIdx.z == 0) ? bias[j] : 0.f);
         TC* dst = C + i * sci + j * scj;
-        if (beta != 0.f) v += beta * ldf<TC>(dst);
-        stf<TC>(dst, v);
+        if (split) {
+          atomic_add_f32(dst, v);
+        } else {
+          if (beta != 0.f) v += beta * ldf<TC>(dst);
+          stf<TC>(dst, v);
+        }
       }
     }
 }
@@ -57,6 +69,18 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
 template <typename TA, typename TB>
 int launch_c(const afb_gemm_simt_t* p, cudaStream_t st) {
   dim3 grid(ceil_div(p->N, TS), ceil_div(p->M, TS));
+  // The classifier-head shapes give 1-16 tiles with 8-16 serial k-steps each: split K over gridDim.z until ~64 CTAs
+  // exist.  Needs an fp32, contiguous-or-strided but non-aliased C and beta in {0, 1} (beta = 0: C is zeroed first).
+  const int ksteps = ceil_div(p->K, TS);
+  int splits = 1;
+  const bool dense = p->scj == 1 && p->sci == p->N;
+  if (p->c_dtype == AFB_F32 && (p->beta == 1.f || (p->beta == 0.f && dense)) && ksteps >= 4) {
+    while (splits * 2 <= ksteps / 2 && (int)(grid.x * grid.y) * splits < 64) splits *= 2;
+  }
+  if (splits > 1) {
+    grid.z = splits;
+    if (p->beta == 0.f) cudaMemsetAsync(p->C, 0, (size_t)p->M * p->N * sizeof(float), st);
+  }
   if (p->c_dtype == AFB_BF16)
     gemm_simt_kernel<TA, TB, bf16><<<grid, 256, 0, st>>>((const TA*)p->A, (const TB*)p->B, (bf16*)p->C, p->bias, p->M, p->N, p->K, p->sai,
                                                          p->sak, p->sbj, p->sbk, p->sci, p->scj, p->alpha, p->beta);
