@@ -59,6 +59,8 @@ template <int DH, int LP, int HG> struct Geo {
   static constexpr size_t bwd_bytes = ((size_t)LP * QKV_PITCH + (size_t)LP * O_PITCH + (size_t)HG * 2 * LP * S_PITCH) * 2;
 };
 
+__host__ __device__ constexpr int bwd_wph(int LP) { return LP >= 32 ? 2 : 1; }   // backward: warps per head
+
 // rows [0, L) of PARTS W-wide column windows of a [.., ld] matrix -> smem tile; rows [L, LP) zeroed.
 // One warp per (row, part): the pair index is warp-uniform, so the address arithmetic is a handful of uniform
 // instructions per 512 contiguous bytes (the previous per-16-byte-chunk div/mod made the copy loop the top
@@ -227,22 +229,31 @@ __global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two warps per head (LP >= 32): each warp owns every other 16-row tile of every phase, so a CTA carries twice the
+// warps for the same shared memory (the kernel is latency-bound at 2 CTAs x 8 warps per SM); the pair meets at a
+// named barrier wherever one phase overwrites an operand the partner may still be reading.
 template <int DH, int LP, int HG>
-__global__ void __launch_bounds__(HG * 32) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, bf16* __restrict__ dqkv,
+__global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, bf16* __restrict__ dqkv,
                                                                int L, int heads, float scale) {
   using G = Geo<DH, LP, HG>;
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* sq = reinterpret_cast<bf16*>(smraw);           // q | k | v   ->  q | dK | dV
   bf16* sdo = sq + LP * G::QKV_PITCH;                  // dO          ->  dQ
-  const int hw = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, id = lane >> 3;
+  constexpr int WPH = bwd_wph(LP), NT = HG * 32 * WPH;
+  const int hw = (threadIdx.x >> 5) / WPH, half = (threadIdx.x >> 5) % WPH;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, id = lane >> 3;
+  auto pair_sync = [&]() {
+    if (WPH == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + hw), "r"(32 * WPH) : "memory");
+  };
   bf16* sP = sdo + LP * G::O_PITCH + hw * 2 * LP * G::S_PITCH;   // per-warp staging of P and dS (bf16)
   bf16* sdS = sP + LP * G::S_PITCH;
   const int groups = heads / HG;
   const int64_t b = blockIdx.x / groups;
   const int h0 = (blockIdx.x % groups) * HG;
   const int D = heads * DH;
-  load_tile<G::W, G::QKV_PITCH, 3, LP, G::kThreads>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L);
-  load_tile<G::W, G::O_PITCH, 1, LP, G::kThreads>(sdo, dO + b * L * D + h0 * DH, D, 0, L);
+  load_tile<G::W, G::QKV_PITCH, 3, LP, NT>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L);
+  load_tile<G::W, G::O_PITCH, 1, LP, NT>(sdo, dO + b * L * D + h0 * DH, D, 0, L);
   cp_async_wait_all();
   __syncthreads();
   const int qcol = hw * DH, kcol = G::W + hw * DH, vcol = 2 * G::W + hw * DH, ocol = hw * DH;
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(HG * 32) attn_bwd_mma_kernel(const bf16* __res
 
   // ---- phase A: P and dS = P * (dP - delta) * scale for every query tile -> staging ----
 #pragma unroll 1
-  for (int mi = 0; mi < LP / 16; ++mi) {
+  for (int mi = half; mi < LP / 16; mi += WPH) {
     float s[LP / 8][4];
     scores_softmax<DH, LP, G::QKV_PITCH>(sq, qcol, kcol, mi, L, scale_log2, s);
     uint32_t da[DH / 16][4];
@@ -295,11 +306,11 @@ __global__ void __launch_bounds__(HG * 32) attn_bwd_mma_kernel(const bf16* __res
       *reinterpret_cast<uint32_t*>(q1) = pack2(s[nj][2] * (dp[nj][2] - d1) * scale, s[nj][3] * (dp[nj][3] - d1) * scale);
     }
   }
-  __syncwarp();
+  pair_sync();
 
   // ---- phase B1: dV = P^T dO  (A = P^T via transposed loads of the staged P) -> v columns ----
 #pragma unroll 1
-  for (int mj = 0; mj < LP / 16; ++mj) {
+  for (int mj = half; mj < LP / 16; mj += WPH) {
     uint32_t a[LP / 16][4];
 #pragma unroll
     for (int kk = 0; kk < LP / 16; ++kk)  // a0:(key 0-7, q 0-7) a1:(key 8-15, q 0-7) a2:(key 0-7, q 8-15) a3:(key 8-15, q 8-15)
@@ -312,10 +323,10 @@ __global__ void __launch_bounds__(HG * 32) attn_bwd_mma_kernel(const bf16* __res
     mma_a_regs_bt<LP / 16, DH / 8, G::O_PITCH>(a, sdo, ocol, acc);
     store_acc<DH / 8, G::QKV_PITCH>(sq, mj * 16, vcol, acc, 1.f, 1.f);
   }
-  __syncwarp();
+  pair_sync();
   // ---- phase B2: dQ = dS K  -> the (now free) dO columns of this head ----
 #pragma unroll 1
-  for (int mi = 0; mi < LP / 16; ++mi) {
+  for (int mi = half; mi < LP / 16; mi += WPH) {
     uint32_t a[LP / 16][4];
 #pragma unroll
     for (int kk = 0; kk < LP / 16; ++kk)
@@ -328,10 +339,10 @@ __global__ void __launch_bounds__(HG * 32) attn_bwd_mma_kernel(const bf16* __res
     mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(a, sq, kcol, acc);
     store_acc<DH / 8, G::O_PITCH>(sdo, mi * 16, ocol, acc, 1.f, 1.f);
   }
-  __syncwarp();
+  pair_sync();
   // ---- phase B3: dK = dS^T Q  -> k columns (K is no longer needed by this warp) ----
 #pragma unroll 1
-  for (int mj = 0; mj < LP / 16; ++mj) {
+  for (int mj = half; mj < LP / 16; mj += WPH) {
     uint32_t a[LP / 16][4];
 #pragma unroll
     for (int kk = 0; kk < LP / 16; ++kk)
@@ -346,9 +357,9 @@ __global__ void __launch_bounds__(HG * 32) attn_bwd_mma_kernel(const bf16* __res
   }
   __syncthreads();
   bf16* out = dqkv + b * L * 3 * D + h0 * DH;
-  store_tile<G::W, G::O_PITCH>(out, 3 * D, sdo, L, G::kThreads);                      // dQ
-  store_tile<G::W, G::QKV_PITCH>(out + D, 3 * D, sq + G::W, L, G::kThreads);          // dK
-  store_tile<G::W, G::QKV_PITCH>(out + 2 * D, 3 * D, sq + 2 * G::W, L, G::kThreads);  // dV
+  store_tile<G::W, G::O_PITCH>(out, 3 * D, sdo, L, NT);                      // dQ
+  store_tile<G::W, G::QKV_PITCH>(out + D, 3 * D, sq + G::W, L, NT);          // dK
+  store_tile<G::W, G::QKV_PITCH>(out + 2 * D, 3 * D, sq + 2 * G::W, L, NT);  // dV
 }
 
 template <typename K>
@@ -376,7 +387,7 @@ int launch_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, in
   using G = Geo<DH, LP, HG>;
   int rc = set_smem(attn_bwd_mma_kernel<DH, LP, HG>, G::bwd_bytes);
   if (rc) return rc;
-  attn_bwd_mma_kernel<DH, LP, HG><<<(unsigned)(B * (heads / HG)), G::kThreads, G::bwd_bytes, st>>>((const bf16*)qkv, (const bf16*)dO, (bf16*)dqkv, L, heads,
+  attn_bwd_mma_kernel<DH, LP, HG><<<(unsigned)(B * (heads / HG)), G::kThreads * bwd_wph(LP), G::bwd_bytes, st>>>((const bf16*)qkv, (const bf16*)dO, (bf16*)dqkv, L, heads,
                                                                                                     scale);
   return check_launch("attention_bwd_mma");
 }
