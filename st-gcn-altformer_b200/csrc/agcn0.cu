@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
   } else {
     for (int i = tid; i < T * V * 3; i += nthr) xs[i] = xg[i];
   }
+  float* APs = part + kMomSegs * NMOM;   // [3][V][V]  A + PA (same for every sample; staged while x arrives)
+  for (int i = tid; i < 3 * V * V; i += nthr) APs[i] = p.A[i] + p.PA[i];
   compute_coef(p, coef);
   __syncthreads();
   const float inv = 1.0f / (float)(p.IC * T);
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
     const int u = live ? pr / V : 0, v = live ? pr % V : 0;
     float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, su[3] = {0.f, 0.f, 0.f}, sv[3] = {0.f, 0.f, 0.f};
     const int t0 = half ? (T + 1) / 2 : 0, t1 = half ? T : (T + 1) / 2;
+#pragma unroll 4
     for (int t = t0; t < t1; ++t) {
       const float* xu = xs + (t * V + u) * 3;
       const float* xv = xs + (t * V + v) * 3;
@@ -275,13 +278,13 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
     const float rden = 1.0f / warp_sum(e0 + e1);
     if (u0 < V) {
       const int idx = (i * V + u0) * V + v;
-      const float m = e0 * rden + p.A[idx] + p.PA[idx];
+      const float m = e0 * rden + APs[idx];
       Ms[idx] = m;
       p.Mmat[(int64_t)n * 3 * V * V + idx] = m;
     }
     if (u1 < V) {
       const int idx = (i * V + u1) * V + v;
-      const float m = e1 * rden + p.A[idx] + p.PA[idx];
+      const float m = e1 * rden + APs[idx];
       Ms[idx] = m;
       p.Mmat[(int64_t)n * 3 * V * V + idx] = m;
     }
@@ -321,6 +324,7 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
       float* dst = rs + pl * NR;
       if (i < 3) {
         float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+#pragma unroll 4
         for (int u = 0; u < V; ++u) {
           const float m = Ms[(i * V + u) * V + v];
           z0 += xt[u * 3] * m; z1 += xt[u * 3 + 1] * m; z2 += xt[u * 3 + 2] * m;
@@ -333,9 +337,11 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
     __syncthreads();
     if (seg < kMomSegs) {
       if (mj < NR) {
+#pragma unroll 8
         for (int pl = seg; pl < np; pl += kMomSegs) macc += rs[pl * NR + mj];
       } else {
-        for (int pl = seg; pl < np; pl += kMomSegs) macc += rs[pl * NR + pa] * rs[pl * NR + pb];
+#pragma unroll 8
+        for (int pl = seg; pl < np; pl += kMomSegs) macc = fmaf(rs[pl * NR + pa], rs[pl * NR + pb], macc);
       }
     }
     __syncthreads();
@@ -969,7 +975,7 @@ extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
   cudaStream_t st = as_stream(s);
   const int T = p->T, V = p->V;
   {
-    size_t smem = ((size_t)a4(T * V * 3) + a4(3 * V * V) + (size_t)kPosChunk * NR + kMomSegs * NMOM) * sizeof(float);
+    size_t smem = ((size_t)a4(T * V * 3) + 2 * a4(3 * V * V) + (size_t)kPosChunk * NR + kMomSegs * NMOM) * sizeof(float);
     if (smem < 2048 + 8) smem = 2048 + 8;   // the finalize step reuses the buffer for ~252 doubles
     AFB_REQUIRE(smem <= 220 * 1024, "gcn0: T*V too large for the per-sample shared-memory stage (%zu B)", smem);
     if ((rc = set_smem(gcn0_scores_kernel, smem, "gcn0_scores"))) return rc;
