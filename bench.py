@@ -91,6 +91,16 @@ def flops_per_sample_fwd(T, V, cls):
     return f
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline is meant to use every core it may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(n, 1))
+    return n
+
+
 def run_reference(args):
     """CPU oracle port of the reference train step (train_sttran.py:89-102,185-191), all host threads."""
     from oracle import altformer_oracle as O
@@ -99,6 +109,7 @@ def run_reference(args):
         return
     T, V, cls = CFG["T"], CFG["V"], CFG["cls"]
     B = 32  # bounded sample of the 256-sample step: seq/s on CPU is batch-insensitive
+    use_all_host_threads()
     torch.manual_seed(0)
     model = O.OracleModel(O.random_state(O.model_spec(3, cls, T, V), 0), O.spatial_graph(V), CFG["style"]).train()
     opt = torch.optim.AdamW(model.parameters(), lr=2e-4, weight_decay=0.1)
@@ -194,6 +205,7 @@ def gcn0_roofline(model, x, dev, pk, iters=20):
 
 def cpu_baseline(budget_s=20.0):
     from oracle import altformer_oracle as O
+    use_all_host_threads()
     T, V, cls, B = CFG["T"], CFG["V"], CFG["cls"], 32
     model = O.OracleModel(O.random_state(O.model_spec(3, cls, T, V), 0), O.spatial_graph(V), CFG["style"]).train()
     opt = torch.optim.AdamW(model.parameters(), lr=2e-4, weight_decay=0.1)
