@@ -91,3 +91,67 @@ def test_full_model_against_reference_golden(name, style, cls, seed):
                 assert abs(got - n) / n < 5e-3, (k, got, n)
     finally:
         ab.set_precision("bf16")
+
+
+def _cfg2_model(cls=28, T=32, V=22, seed=5):
+    import altformer_b200 as ab
+    from oracle import altformer_oracle as O
+    st = O.random_state(O.model_spec(3, cls, T, V), seed)
+    mod = ab.ST_GCN_AltFormer(3, cls, num_frame=T, num_joints=V, style="ST", graph="graph.SHRE", graph_args={"labeling_mode": "spatial"})
+    mod.load_state_dict(st)
+    return mod.cuda()
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_full_size_eval_is_batch_split_invariant(mode, tol):
+    """BASELINE cfg2 size (256 sequences): in eval mode every sequence is independent, so the logits of the full
+    batch must equal the logits of its 32-sequence slices -- a size-independent property checked where the oracle
+    is too slow to run (tile walks, persistent-CTA schedules and split reductions all change with the batch).
+    fp32 mode: to the parity tolerance.  bf16 mode: to bf16 noise only -- gcn0 centres its operands by the batch
+    mean before rounding them to bf16 (exact in real arithmetic), so the rounding pattern depends on the batch."""
+    import altformer_b200 as ab
+    from oracle import altformer_oracle as O
+    ab.set_precision(mode)
+    try:
+        mod = _cfg2_model().eval()
+        x, _ = O.synthetic_batch(256, 32, 22, 28, 99)
+        x = x.cuda()
+        with torch.no_grad():
+            full = mod(x).float()
+            parts = torch.cat([mod(x[i:i + 32]).float() for i in range(0, 256, 32)])
+        assert torch.isfinite(full).all()
+        err = float((full - parts).norm() / full.norm())
+        assert err < tol, err
+    finally:
+        ab.set_precision("bf16")
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("bf16", 5e-2)])
+def test_full_size_gradient_is_additive_over_shards(mode, tol):
+    """cfg2 size: with BatchNorm on running statistics and DropPath off the loss is a plain sum over sequences, so the
+    gradient of the full batch equals the sum of the gradients of its two halves -- linearity of the backward kernels
+    (dW split reductions, attention / LayerNorm backward, conv taps) at full size.  fp32 mode checks the kernels'
+    arithmetic; bf16 mode can only agree to the noise of independently rounded activations / gradients."""
+    import altformer_b200 as ab
+    from altformer_b200 import functional as AF
+    from oracle import altformer_oracle as O
+    ab.set_precision(mode)
+    try:
+        mod = _cfg2_model().eval()            # running-stat BN and no DropPath
+        for prm in mod.gcn0.parameters():     # gcn0's backward exists for batch-statistics BatchNorm only (training)
+            prm.requires_grad_(False)
+        x, y = O.synthetic_batch(256, 32, 22, 28, 123)
+        x, y = x.cuda(), y.cuda()
+
+        def grads(xs, ys, scale):
+            mod.zero_grad(set_to_none=True)
+            loss = AF.cross_entropy(mod(xs), ys) * scale   # cross_entropy averages: undo it so the pieces add up
+            loss.backward()
+            return torch.cat([p.grad.flatten().double() for _, p in mod.live_parameters() if p.grad is not None])
+
+        g_full = grads(x, y, 256.0)
+        g_a, g_b = grads(x[:128], y[:128], 128.0), grads(x[128:], y[128:], 128.0)
+        err = float((g_full - (g_a + g_b)).norm() / g_full.norm())
+        assert torch.isfinite(g_full).all() and err < tol, err
+    finally:
+        ab.set_precision("bf16")
