@@ -66,46 +66,68 @@ __host__ __device__ constexpr int bwd_wph(int LP) { return LP >= 32 ? 2 : 1; }  
 // instructions per 512 contiguous bytes (the previous per-16-byte-chunk div/mod made the copy loop the top
 // issue-slot consumer of the forward kernel, ncu r01).
 template <int W, int PITCH, int PARTS, int LP, int NT>
-__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t ld, int64_t part_stride, int L) {
+__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int ld, int part_stride, int L) {
   constexpr int C16 = W / 8;  // 16-byte chunks per part row
   constexpr int NW = NT / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 32-bit offsets from two bases (a tile spans < 2^31 elements): one 64-bit add per copy instead of 64-bit multiplies
+  const uint32_t d0 = smem_u32(dst) + (uint32_t)lane * 16u;
+  const bf16* s0 = src + lane * 8;
 #pragma unroll
   for (int j0 = 0; j0 < LP * PARTS; j0 += NW) {
     const int j = j0 + warp;
     if ((LP * PARTS) % NW != 0 && j >= LP * PARTS) break;
     const int row = j / PARTS, part = j - row * PARTS;
-    bf16* d = dst + row * PITCH + part * W;
-    const bf16* sp = src + row * ld + part * part_stride;
+    const uint32_t d = d0 + (uint32_t)((row * PITCH + part * W) * 2);
+    const int soff = row * ld + part * part_stride;
 #pragma unroll
-    for (int c = lane; c < C16; c += 32) {
+    for (int c = 0; c < C16; c += 32) {
+      if (C16 % 32 != 0 && lane + c >= C16) break;
       if (row < L)   // asynchronous 16-byte copies: every chunk of the tile is in flight at once (cp_async_wait_all below)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d + c * 8)), "l"(sp + c * 8)
-                     : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + c * 16), "l"(s0 + soff + c * 8) : "memory");
       else
-        *reinterpret_cast<uint4*>(d + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(d + c * 16), "r"(0) : "memory");
     }
   }
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 template <int W, int PITCH>
-__device__ __forceinline__ void store_tile(bf16* dst, int64_t ld, const bf16* src, int L, int nthreads) {
+__device__ __forceinline__ void store_tile(bf16* dst, int ld, const bf16* src, int L, int nthreads) {
   constexpr int C16 = W / 8;
   for (int idx = threadIdx.x; idx < L * C16; idx += nthreads) {
     const int row = idx / C16, c = idx % C16;
-    *reinterpret_cast<uint4*>(dst + row * ld + c * 8) = *reinterpret_cast<const uint4*>(src + row * PITCH + c * 8);
+    *reinterpret_cast<uint4*>(dst + (row * ld + c * 8)) = *reinterpret_cast<const uint4*>(src + (row * PITCH + c * 8));
   }
 }
 
+// Lane-dependent shared-memory byte offsets of the four access patterns, computed ONCE per thread; every ldmatrix /
+// store below is then base + lane offset + compile-time constant (the per-call pointer arithmetic used to be ~40 % of
+// the forward kernel's instructions, ncu r01).
+//   a : A operand, non-transposed   rows r0 + (lane & 15),                 cols c0 + (lane >> 4) * 8
+//   k : B operand from [n][k] rows  rows n0 + (lane & 7) + (id >> 1) * 8,  cols c0 + (id & 1) * 8        (id = lane >> 3)
+//   bt: B operand from [k][n] rows (transposed load)  rows k0 + (lane & 7) + (id & 1) * 8, cols c0 + (id >> 1) * 8
+//   c : C fragment element (g, 2t)   rows r0 + g (+8), cols c0 + 2t
+template <int PITCH> struct LaneOff {
+  uint32_t a, k, bt, c;
+  __device__ __forceinline__ LaneOff() {
+    const int lane = threadIdx.x & 31, id = lane >> 3;
+    a = (uint32_t)(((lane & 15) * PITCH + (lane >> 4) * 8) * 2);
+    k = (uint32_t)((((lane & 7) + (id >> 1) * 8) * PITCH + (id & 1) * 8) * 2);
+    bt = (uint32_t)((((lane & 7) + (id & 1) * 8) * PITCH + (id >> 1) * 8) * 2);
+    c = (uint32_t)(((lane >> 2) * PITCH + 2 * (lane & 3)) * 2);
+  }
+};
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
 // S tile for query rows [mi*16, mi*16+16): s[nj][0..3] = (Q K^T) for key tile nj, then masked softmax.
 // Returns the normalised probabilities in s (fp32), columns >= L are exactly 0.
+// qbase / kbase: shared-memory byte addresses of the head's Q / K columns with the lane offsets (a / k) already added.
 template <int DH, int LP, int PITCH>
-__device__ __forceinline__ void scores_softmax(const bf16* sq, int qcol, int kcol, int mi, int L, float scale_log2, float (&s)[LP / 8][4]) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ void scores_softmax(uint32_t qbase, uint32_t kbase, int mi, int L, float scale_log2, float (&s)[LP / 8][4]) {
+  const int t = threadIdx.x & 3;
   uint32_t qa[DH / 16][4];
 #pragma unroll
-  for (int kk = 0; kk < DH / 16; ++kk)
-    ldsm_x4(smem_u32(sq + (mi * 16 + (lane & 15)) * PITCH + qcol + kk * 16 + (lane >> 4) * 8), qa[kk]);
+  for (int kk = 0; kk < DH / 16; ++kk) ldsm_x4(qbase + (uint32_t)((mi * 16 * PITCH + kk * 16) * 2), qa[kk]);
 #pragma unroll
   for (int nj = 0; nj < LP / 8; ++nj)
 #pragma unroll
@@ -117,8 +139,7 @@ __device__ __forceinline__ void scores_softmax(const bf16* sq, int qcol, int kco
 #pragma unroll
     for (int kk = 0; kk < DH / 16; ++kk) {
       uint32_t kb[4];
-      const int id = lane >> 3;
-      ldsm_x4(smem_u32(sq + (n2 * 16 + (lane & 7) + (id >> 1) * 8) * PITCH + kcol + kk * 16 + (id & 1) * 8), kb);
+      ldsm_x4(kbase + (uint32_t)((n2 * 16 * PITCH + kk * 16) * 2), kb);
       mma(s[2 * n2], qa[kk], kb[0], kb[1]);
       if (2 * n2 + 1 < nt_valid) mma(s[2 * n2 + 1], qa[kk], kb[2], kb[3]);
     }
@@ -153,28 +174,28 @@ __device__ __forceinline__ void scores_softmax(const bf16* sq, int qcol, int kco
   }
 }
 
-// acc[nd][..] += A(16 x LPk) * Bt, where B[k][n] = src[krow0 + k][col + n] (row-major source, transposed load)
+// acc[nd][..] += A(16 x 16*NK16) * B, B[k][n] = rows k, cols n of a row-major tile (transposed load).
+// bbase: byte address of the tile's (row 0, first column) with the lane offset (bt) already added.
 template <int NK16, int ND8, int PITCH>
-__device__ __forceinline__ void mma_a_regs_bt(const uint32_t (&a)[NK16][4], const bf16* src, int col, float (&acc)[ND8][4]) {
-  const int lane = threadIdx.x & 31, id = lane >> 3;
+__device__ __forceinline__ void mma_a_regs_bt(const uint32_t (&a)[NK16][4], uint32_t bbase, float (&acc)[ND8][4]) {
 #pragma unroll
   for (int kk = 0; kk < NK16; ++kk)
 #pragma unroll
     for (int n2 = 0; n2 < ND8 / 2; ++n2) {
       uint32_t b[4];
-      ldsm_x4_t(smem_u32(src + (kk * 16 + (lane & 7) + (id & 1) * 8) * PITCH + col + n2 * 16 + (id >> 1) * 8), b);
+      ldsm_x4_t(bbase + (uint32_t)((kk * 16 * PITCH + n2 * 16) * 2), b);
       mma(acc[2 * n2], a[kk], b[0], b[1]);
       mma(acc[2 * n2 + 1], a[kk], b[2], b[3]);
     }
 }
 
+// cbase: byte address of (row 0, first column) of the destination with the lane offset (c) already added
 template <int ND8, int PITCH>
-__device__ __forceinline__ void store_acc(bf16* dst, int row0, int col, const float (&acc)[ND8][4], float m0, float m1) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ void store_acc(uint32_t cbase, int row0, const float (&acc)[ND8][4], float m0, float m1) {
 #pragma unroll
   for (int nd = 0; nd < ND8; ++nd) {
-    *reinterpret_cast<uint32_t*>(dst + (row0 + g) * PITCH + col + nd * 8 + 2 * t) = pack2(acc[nd][0] * m0, acc[nd][1] * m0);
-    *reinterpret_cast<uint32_t*>(dst + (row0 + g + 8) * PITCH + col + nd * 8 + 2 * t) = pack2(acc[nd][2] * m1, acc[nd][3] * m1);
+    sts32(cbase + (uint32_t)((row0 * PITCH + nd * 8) * 2), pack2(acc[nd][0] * m0, acc[nd][1] * m0));
+    sts32(cbase + (uint32_t)(((row0 + 8) * PITCH + nd * 8) * 2), pack2(acc[nd][2] * m1, acc[nd][3] * m1));
   }
 }
 
@@ -202,11 +223,15 @@ __global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __res
   const int hw = threadIdx.x >> 5;
   const int qcol = hw * DH, kcol = G::W + hw * DH, vcol = 2 * G::W + hw * DH;
   const float scale_log2 = scale * 1.4426950408889634f;
+  const LaneOff<G::QKV_PITCH> lo;
+  const uint32_t sq32 = smem_u32(sq);
+  const uint32_t qbase = sq32 + lo.a + qcol * 2, kbase = sq32 + lo.k + kcol * 2, vbase = sq32 + lo.bt + vcol * 2;
+  const uint32_t obase = sq32 + lo.c + qcol * 2;
 #pragma unroll
   for (int mi = 0; mi < LP / 16; ++mi) {   // unrolled: every ldmatrix / store address becomes base + immediate
     if (mi * 16 >= L) break;
     float s[LP / 8][4];
-    scores_softmax<DH, LP, G::QKV_PITCH>(sq, qcol, kcol, mi, L, scale_log2, s);
+    scores_softmax<DH, LP, G::QKV_PITCH>(qbase, kbase, mi, L, scale_log2, s);
     uint32_t pa[LP / 16][4];
 #pragma unroll
     for (int kk = 0; kk < LP / 16; ++kk) {
@@ -220,9 +245,9 @@ __global__ void __launch_bounds__(HG * 32) attn_fwd_mma_kernel(const bf16* __res
     for (int nd = 0; nd < DH / 8; ++nd)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
-    mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(pa, sq, vcol, acc);
+    mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(pa, vbase, acc);
     __syncwarp();   // every lane has consumed this tile's Q fragments: the rows can take the output
-    store_acc<DH / 8, G::QKV_PITCH>(sq, mi * 16, qcol, acc, os, os);
+    store_acc<DH / 8, G::QKV_PITCH>(obase, mi * 16, acc, os, os);
   }
   __syncthreads();
   store_tile<G::W, G::QKV_PITCH>(o + b * L * D + h0 * DH, D, sq, L, G::kThreads);
@@ -241,7 +266,6 @@ __global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_m
   bf16* sdo = sq + LP * G::QKV_PITCH;                  // dO          ->  dQ
   constexpr int WPH = bwd_wph(LP), NT = HG * 32 * WPH;
   const int hw = (threadIdx.x >> 5) / WPH, half = (threadIdx.x >> 5) % WPH;
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, id = lane >> 3;
   auto pair_sync = [&]() {
     if (WPH == 1) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + hw), "r"(32 * WPH) : "memory");
@@ -258,16 +282,20 @@ __global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_m
   __syncthreads();
   const int qcol = hw * DH, kcol = G::W + hw * DH, vcol = 2 * G::W + hw * DH, ocol = hw * DH;
   const float scale_log2 = scale * 1.4426950408889634f;
+  const LaneOff<G::QKV_PITCH> lq;
+  const LaneOff<G::O_PITCH> ld;
+  const LaneOff<G::S_PITCH> ls;
+  const uint32_t sq32 = smem_u32(sq), sdo32 = smem_u32(sdo), sP32 = smem_u32(sP), sdS32 = smem_u32(sdS);
 
   // ---- phase A: P and dS = P * (dP - delta) * scale for every query tile -> staging ----
 #pragma unroll 1
   for (int mi = half; mi < LP / 16; mi += WPH) {
     float s[LP / 8][4];
-    scores_softmax<DH, LP, G::QKV_PITCH>(sq, qcol, kcol, mi, L, scale_log2, s);
+    scores_softmax<DH, LP, G::QKV_PITCH>(sq32 + lq.a + qcol * 2, sq32 + lq.k + kcol * 2, mi, L, scale_log2, s);
     uint32_t da[DH / 16][4];
 #pragma unroll
     for (int kk = 0; kk < DH / 16; ++kk)
-      ldsm_x4(smem_u32(sdo + (mi * 16 + (lane & 15)) * G::O_PITCH + ocol + kk * 16 + (lane >> 4) * 8), da[kk]);
+      ldsm_x4(sdo32 + ld.a + (uint32_t)((mi * 16 * G::O_PITCH + ocol + kk * 16) * 2), da[kk]);
     float dp[LP / 8][4];
 #pragma unroll
     for (int nj = 0; nj < LP / 8; ++nj)
@@ -280,7 +308,7 @@ __global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_m
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {  // dP = dO V^T : B[k = d][n = key] = V[key][d] (non-transposed load)
         uint32_t vb[4];
-        ldsm_x4(smem_u32(sq + (n2 * 16 + (lane & 7) + (id >> 1) * 8) * G::QKV_PITCH + vcol + kk * 16 + (id & 1) * 8), vb);
+        ldsm_x4(sq32 + lq.k + (uint32_t)((n2 * 16 * G::QKV_PITCH + vcol + kk * 16) * 2), vb);
         mma(dp[2 * n2], da[kk], vb[0], vb[1]);
         if (2 * n2 + 1 < nt_valid) mma(dp[2 * n2 + 1], da[kk], vb[2], vb[3]);
       }
@@ -295,15 +323,11 @@ __global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_m
     d1 = quad_sum(d1);
 #pragma unroll
     for (int nj = 0; nj < LP / 8; ++nj) {
-      const int c = nj * 8 + 2 * t;
-      bf16* p0 = sP + (mi * 16 + g) * G::S_PITCH + c;
-      bf16* p1 = sP + (mi * 16 + g + 8) * G::S_PITCH + c;
-      *reinterpret_cast<uint32_t*>(p0) = pack2(s[nj][0], s[nj][1]);
-      *reinterpret_cast<uint32_t*>(p1) = pack2(s[nj][2], s[nj][3]);
-      bf16* q0 = sdS + (mi * 16 + g) * G::S_PITCH + c;
-      bf16* q1 = sdS + (mi * 16 + g + 8) * G::S_PITCH + c;
-      *reinterpret_cast<uint32_t*>(q0) = pack2(s[nj][0] * (dp[nj][0] - d0) * scale, s[nj][1] * (dp[nj][1] - d0) * scale);
-      *reinterpret_cast<uint32_t*>(q1) = pack2(s[nj][2] * (dp[nj][2] - d1) * scale, s[nj][3] * (dp[nj][3] - d1) * scale);
+      const uint32_t off0 = ls.c + (uint32_t)((mi * 16 * G::S_PITCH + nj * 8) * 2), off1 = off0 + 8 * G::S_PITCH * 2;
+      sts32(sP32 + off0, pack2(s[nj][0], s[nj][1]));
+      sts32(sP32 + off1, pack2(s[nj][2], s[nj][3]));
+      sts32(sdS32 + off0, pack2(s[nj][0] * (dp[nj][0] - d0) * scale, s[nj][1] * (dp[nj][1] - d0) * scale));
+      sts32(sdS32 + off1, pack2(s[nj][2] * (dp[nj][2] - d1) * scale, s[nj][3] * (dp[nj][3] - d1) * scale));
     }
   }
   pair_sync();
@@ -314,14 +338,14 @@ __global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_m
     uint32_t a[LP / 16][4];
 #pragma unroll
     for (int kk = 0; kk < LP / 16; ++kk)  // a0:(key 0-7, q 0-7) a1:(key 8-15, q 0-7) a2:(key 0-7, q 8-15) a3:(key 8-15, q 8-15)
-      ldsm_x4_t(smem_u32(sP + (kk * 16 + (lane & 7) + (id >> 1) * 8) * G::S_PITCH + mj * 16 + (id & 1) * 8), a[kk]);
+      ldsm_x4_t(sP32 + ls.k + (uint32_t)((kk * 16 * G::S_PITCH + mj * 16) * 2), a[kk]);
     float acc[DH / 8][4];
 #pragma unroll
     for (int nd = 0; nd < DH / 8; ++nd)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
-    mma_a_regs_bt<LP / 16, DH / 8, G::O_PITCH>(a, sdo, ocol, acc);
-    store_acc<DH / 8, G::QKV_PITCH>(sq, mj * 16, vcol, acc, 1.f, 1.f);
+    mma_a_regs_bt<LP / 16, DH / 8, G::O_PITCH>(a, sdo32 + ld.bt + ocol * 2, acc);
+    store_acc<DH / 8, G::QKV_PITCH>(sq32 + lq.c + vcol * 2, mj * 16, acc, 1.f, 1.f);
   }
   pair_sync();
   // ---- phase B2: dQ = dS K  -> the (now free) dO columns of this head ----
@@ -330,14 +354,14 @@ __global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_m
     uint32_t a[LP / 16][4];
 #pragma unroll
     for (int kk = 0; kk < LP / 16; ++kk)
-      ldsm_x4(smem_u32(sdS + (mi * 16 + (lane & 15)) * G::S_PITCH + kk * 16 + (lane >> 4) * 8), a[kk]);
+      ldsm_x4(sdS32 + ls.a + (uint32_t)((mi * 16 * G::S_PITCH + kk * 16) * 2), a[kk]);
     float acc[DH / 8][4];
 #pragma unroll
     for (int nd = 0; nd < DH / 8; ++nd)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
-    mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(a, sq, kcol, acc);
-    store_acc<DH / 8, G::O_PITCH>(sdo, mi * 16, ocol, acc, 1.f, 1.f);
+    mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(a, sq32 + lq.bt + kcol * 2, acc);
+    store_acc<DH / 8, G::O_PITCH>(sdo32 + ld.c + ocol * 2, mi * 16, acc, 1.f, 1.f);
   }
   pair_sync();
   // ---- phase B3: dK = dS^T Q  -> k columns (K is no longer needed by this warp) ----
@@ -346,14 +370,14 @@ __global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_m
     uint32_t a[LP / 16][4];
 #pragma unroll
     for (int kk = 0; kk < LP / 16; ++kk)
-      ldsm_x4_t(smem_u32(sdS + (kk * 16 + (lane & 7) + (id >> 1) * 8) * G::S_PITCH + mj * 16 + (id & 1) * 8), a[kk]);
+      ldsm_x4_t(sdS32 + ls.k + (uint32_t)((kk * 16 * G::S_PITCH + mj * 16) * 2), a[kk]);
     float acc[DH / 8][4];
 #pragma unroll
     for (int nd = 0; nd < DH / 8; ++nd)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
-    mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(a, sq, qcol, acc);
-    store_acc<DH / 8, G::QKV_PITCH>(sq, mj * 16, kcol, acc, 1.f, 1.f);
+    mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(a, sq32 + lq.bt + qcol * 2, acc);
+    store_acc<DH / 8, G::QKV_PITCH>(sq32 + lq.c + kcol * 2, mj * 16, acc, 1.f, 1.f);
   }
   __syncthreads();
   bf16* out = dqkv + b * L * 3 * D + h0 * DH;
