@@ -286,16 +286,24 @@ __global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_m
   const LaneOff<G::O_PITCH> ld;
   const LaneOff<G::S_PITCH> ls;
   const uint32_t sq32 = smem_u32(sq), sdo32 = smem_u32(sdo), sP32 = smem_u32(sP), sdS32 = smem_u32(sdS);
+  // This warp's 16-row tiles are half, half + WPH, ...: the runtime part (half) is folded into the bases once, the
+  // loops below run over a compile-time index, so every shared-memory address is base + immediate.
+  constexpr int NTILE = (LP / 16 + WPH - 1) / WPH;
+  const uint32_t hq = (uint32_t)(half * 16 * G::QKV_PITCH * 2), ho = (uint32_t)(half * 16 * G::O_PITCH * 2);
+  const uint32_t hs = (uint32_t)(half * 16 * G::S_PITCH * 2), hc = (uint32_t)(half * 16 * 2);
+  auto live = [&](int i) { return (LP / 16) % WPH == 0 || half + i * WPH < LP / 16; };
 
   // ---- phase A: P and dS = P * (dP - delta) * scale for every query tile -> staging ----
-#pragma unroll 1
-  for (int mi = half; mi < LP / 16; mi += WPH) {
+#pragma unroll
+  for (int i = 0; i < NTILE; ++i) {
+    if (!live(i)) break;
+    const int mi = i * WPH;   // tile offset beyond `half` (compile-time after unrolling)
     float s[LP / 8][4];
-    scores_softmax<DH, LP, G::QKV_PITCH>(sq32 + lq.a + qcol * 2, sq32 + lq.k + kcol * 2, mi, L, scale_log2, s);
+    scores_softmax<DH, LP, G::QKV_PITCH>(sq32 + lq.a + qcol * 2 + hq, sq32 + lq.k + kcol * 2, mi, L, scale_log2, s);
     uint32_t da[DH / 16][4];
 #pragma unroll
     for (int kk = 0; kk < DH / 16; ++kk)
-      ldsm_x4(sdo32 + ld.a + (uint32_t)((mi * 16 * G::O_PITCH + ocol + kk * 16) * 2), da[kk]);
+      ldsm_x4(sdo32 + ld.a + ho + (uint32_t)((mi * 16 * G::O_PITCH + ocol + kk * 16) * 2), da[kk]);
     float dp[LP / 8][4];
 #pragma unroll
     for (int nj = 0; nj < LP / 8; ++nj)
@@ -323,7 +331,7 @@ __global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_m
     d1 = quad_sum(d1);
 #pragma unroll
     for (int nj = 0; nj < LP / 8; ++nj) {
-      const uint32_t off0 = ls.c + (uint32_t)((mi * 16 * G::S_PITCH + nj * 8) * 2), off1 = off0 + 8 * G::S_PITCH * 2;
+      const uint32_t off0 = ls.c + hs + (uint32_t)((mi * 16 * G::S_PITCH + nj * 8) * 2), off1 = off0 + 8 * G::S_PITCH * 2;
       sts32(sP32 + off0, pack2(s[nj][0], s[nj][1]));
       sts32(sP32 + off1, pack2(s[nj][2], s[nj][3]));
       sts32(sdS32 + off0, pack2(s[nj][0] * (dp[nj][0] - d0) * scale, s[nj][1] * (dp[nj][1] - d0) * scale));
@@ -333,51 +341,57 @@ __global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_m
   pair_sync();
 
   // ---- phase B1: dV = P^T dO  (A = P^T via transposed loads of the staged P) -> v columns ----
-#pragma unroll 1
-  for (int mj = half; mj < LP / 16; mj += WPH) {
+#pragma unroll
+  for (int i = 0; i < NTILE; ++i) {
+    if (!live(i)) break;
+    const int mj = i * WPH;
     uint32_t a[LP / 16][4];
 #pragma unroll
     for (int kk = 0; kk < LP / 16; ++kk)  // a0:(key 0-7, q 0-7) a1:(key 8-15, q 0-7) a2:(key 0-7, q 8-15) a3:(key 8-15, q 8-15)
-      ldsm_x4_t(sP32 + ls.k + (uint32_t)((kk * 16 * G::S_PITCH + mj * 16) * 2), a[kk]);
+      ldsm_x4_t(sP32 + ls.k + hc + (uint32_t)((kk * 16 * G::S_PITCH + mj * 16) * 2), a[kk]);
     float acc[DH / 8][4];
 #pragma unroll
     for (int nd = 0; nd < DH / 8; ++nd)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
     mma_a_regs_bt<LP / 16, DH / 8, G::O_PITCH>(a, sdo32 + ld.bt + ocol * 2, acc);
-    store_acc<DH / 8, G::QKV_PITCH>(sq32 + lq.c + vcol * 2, mj * 16, acc, 1.f, 1.f);
+    store_acc<DH / 8, G::QKV_PITCH>(sq32 + lq.c + vcol * 2 + hq, mj * 16, acc, 1.f, 1.f);
   }
   pair_sync();
   // ---- phase B2: dQ = dS K  -> the (now free) dO columns of this head ----
-#pragma unroll 1
-  for (int mi = half; mi < LP / 16; mi += WPH) {
+#pragma unroll
+  for (int i = 0; i < NTILE; ++i) {
+    if (!live(i)) break;
+    const int mi = i * WPH;
     uint32_t a[LP / 16][4];
 #pragma unroll
     for (int kk = 0; kk < LP / 16; ++kk)
-      ldsm_x4(sdS32 + ls.a + (uint32_t)((mi * 16 * G::S_PITCH + kk * 16) * 2), a[kk]);
+      ldsm_x4(sdS32 + ls.a + hs + (uint32_t)((mi * 16 * G::S_PITCH + kk * 16) * 2), a[kk]);
     float acc[DH / 8][4];
 #pragma unroll
     for (int nd = 0; nd < DH / 8; ++nd)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
     mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(a, sq32 + lq.bt + kcol * 2, acc);
-    store_acc<DH / 8, G::O_PITCH>(sdo32 + ld.c + ocol * 2, mi * 16, acc, 1.f, 1.f);
+    store_acc<DH / 8, G::O_PITCH>(sdo32 + ld.c + ocol * 2 + ho, mi * 16, acc, 1.f, 1.f);
   }
   pair_sync();
   // ---- phase B3: dK = dS^T Q  -> k columns (K is no longer needed by this warp) ----
-#pragma unroll 1
-  for (int mj = half; mj < LP / 16; mj += WPH) {
+#pragma unroll
+  for (int i = 0; i < NTILE; ++i) {
+    if (!live(i)) break;
+    const int mj = i * WPH;
     uint32_t a[LP / 16][4];
 #pragma unroll
     for (int kk = 0; kk < LP / 16; ++kk)
-      ldsm_x4_t(sdS32 + ls.k + (uint32_t)((kk * 16 * G::S_PITCH + mj * 16) * 2), a[kk]);
+      ldsm_x4_t(sdS32 + ls.k + hc + (uint32_t)((kk * 16 * G::S_PITCH + mj * 16) * 2), a[kk]);
     float acc[DH / 8][4];
 #pragma unroll
     for (int nd = 0; nd < DH / 8; ++nd)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nd][e] = 0.f;
     mma_a_regs_bt<LP / 16, DH / 8, G::QKV_PITCH>(a, sq32 + lq.bt + qcol * 2, acc);
-    store_acc<DH / 8, G::QKV_PITCH>(sq32 + lq.c + kcol * 2, mj * 16, acc, 1.f, 1.f);
+    store_acc<DH / 8, G::QKV_PITCH>(sq32 + lq.c + kcol * 2 + hq, mj * 16, acc, 1.f, 1.f);
   }
   __syncthreads();
   bf16* out = dqkv + b * L * 3 * D + h0 * DH;
