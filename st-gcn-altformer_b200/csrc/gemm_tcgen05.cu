@@ -5,12 +5,16 @@
 //   gemm_dw_kernel : dW[N1,N2] += G[M,N1]^T * X[M,N2]       weight gradients, contraction over
 //                    token rows (both operands MN-major), split over CTAs, fp32 atomics.
 //
-// Structure (one CTA per SM, persistent over tiles; 6 warps):
-//   warp 0    TMA producer  : cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx
+// Structure of gemm_tn_kernel (one CTA per SM, persistent over tiles; 10 warps):
+//   warp 0    TMA producer  : cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx; in B-stationary
+//                             mode the [BN x K] weight panel is loaded once and only A tiles stream
 //   warp 1    MMA issuer    : one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into one of
 //                             two TMEM accumulator stages; tcgen05.commit releases smem / signals
-//   warps 2-5 epilogue      : tcgen05.ld 32 lanes x 32 columns -> smem transpose -> coalesced
-//                             fused epilogue (bias, pos-embed, GELU, DropPath scale, residual)
+//   warps 2-9 epilogue      : thread = output row (tcgen05.ld 32x32b.x32), fused epilogue (bias, pos-embed, GELU,
+//                             GELU', DropPath scale, residual) -> 128B-swizzled staging -> TMA store; specialised
+//                             straight-line variants for the hot bf16 combinations (epi_fast_loop)
+// gemm_dw_kernel: producer + MMA issuer + 4 warps that sum the bias gradient from the G tiles while the MMAs run and
+// then drain the accumulators with vector reductions.
 #include <cuda.h>
 #include <stdlib.h>
 
