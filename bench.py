@@ -91,6 +91,16 @@ def flops_per_sample_fwd(T, V, cls):
     return f
 
 
+def synthetic_batch(N, T, V, cls, seed=1234):
+    """BASELINE.md 4 / SURVEY 8d inputs: 0.2*randn skeletons, palm-centred (Hand_Dataset.py:61), uniform labels.
+    (Own copy: the measured arm does not import anything from oracle/.)"""
+    g = torch.Generator().manual_seed(seed)
+    x = 0.2 * torch.randn(N, T, V, 3, generator=g)
+    x = x - x[:, :1, 1:2, :]
+    y = torch.randint(0, cls, (N,), generator=g)
+    return x, y
+
+
 def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline is meant to use every core it may run on."""
     try:
@@ -264,7 +274,6 @@ def main():
     import torch.distributed as dist
     import altformer_b200 as ab
     from altformer_b200 import ops
-    from oracle import altformer_oracle as O  # synthetic inputs + (rank 0) cpu_baseline only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -283,7 +292,7 @@ def main():
     with torch.no_grad():  # the reference's init makes gcn0 invisible (bn gamma 1e-6); use a live one for a fair workload
         model.gcn0.bn.weight.fill_(1.0)
     trainer = ab.DataParallelTrainer(model, use_graph=not args.no_graph)
-    x_cpu, y_cpu = O.synthetic_batch(B, T, V, cls, 1234 + rank)
+    x_cpu, y_cpu = synthetic_batch(B, T, V, cls, 1234 + rank)
     x_pin, y_pin = x_cpu.pin_memory(), y_cpu.pin_memory()
     x_dev, y_dev = x_pin.to(dev), y_pin.to(dev)
 
