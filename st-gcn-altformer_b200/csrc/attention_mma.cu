@@ -10,6 +10,8 @@
 //   C (16x8):       c0,c1 (g, 2t..2t+1)               c2,c3 (g+8, 2t..2t+1)
 // ldmatrix (non-transposed) of an 8x8 b16 tile gives thread (row g, cols 2t..2t+1); .trans gives
 // (rows 2t..2t+1, col g).  An accumulator tile pair (two n8 tiles) is therefore already an A fragment.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace afb {
@@ -56,7 +58,8 @@ template <int DH, int LP, int HG> struct Geo {
   static constexpr int S_PITCH = LP + 8;
   static constexpr int kThreads = HG * 32;
   static constexpr size_t fwd_bytes = (size_t)LP * QKV_PITCH * 2;   // O is staged over the consumed Q rows
-  static constexpr size_t bwd_bytes = ((size_t)LP * QKV_PITCH + (size_t)LP * O_PITCH + (size_t)HG * 2 * LP * S_PITCH) * 2;
+  static constexpr size_t bwd_tile_bytes = ((size_t)LP * QKV_PITCH + (size_t)LP * O_PITCH) * 2;   // q|k|v + dO
+  static constexpr size_t bwd_bytes = bwd_tile_bytes + (size_t)HG * 2 * LP * S_PITCH * 2;            // + P / dS staging
 };
 
 __host__ __device__ constexpr int bwd_wph(int LP) { return LP >= 32 ? 2 : 1; }   // backward: warps per head
@@ -400,6 +403,204 @@ __global__ void __launch_bounds__(HG * 32 * bwd_wph(LP), bwd_wph(LP)) attn_bwd_m
   store_tile<G::W, G::QKV_PITCH>(out + 2 * D, 3 * D, sq + 2 * G::W, L, NT);  // dV
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward for LP = 32 (L <= 32: the SHREC / DHG spatial and temporal stages), one warp per head, NO staging buffers:
+//   * both 16-row query tiles are processed together, so every K / V / dO / Q operand fragment is loaded from shared
+//     memory once and feeds the MMAs of both tiles (the two-warp variant above loads each fragment per tile);
+//   * P and dS stay in registers: as A operands they are the packed C fragments (FA2 reuse, for dQ = dS K), and their
+//     transposes (for dV = P^T dO, dK = dS^T Q) come from movmatrix on the same registers.
+// The older kernel's bound was the shared-memory data pipe (66 % of peak, ncu r01); this one moves ~40 % fewer
+// wavefronts and needs 41 KB less shared memory per CTA.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t movm_t(uint32_t v) {   // transpose of an 8x8 b16 tile held in mma fragment layout
+  uint32_t r;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+template <int DH, int HG>
+__global__ void __launch_bounds__(HG * 32, 2) attn_bwd32_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, bf16* __restrict__ dqkv,
+                                                                int L, int heads, float scale) {
+  constexpr int LP = 32;
+  using G = Geo<DH, LP, HG>;
+  constexpr int NT = HG * 32, KD = DH / 16, ND = DH / 8;
+  constexpr int QP = G::QKV_PITCH, OP = G::O_PITCH;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* sq = reinterpret_cast<bf16*>(smraw);           // q | k | v   ->  q | dK | dV
+  bf16* sdo = sq + LP * QP;                            // dO          ->  dQ
+  const int hw = threadIdx.x >> 5, t = threadIdx.x & 3;
+  const int groups = heads / HG;
+  const int64_t b = blockIdx.x / groups;
+  const int h0 = (blockIdx.x % groups) * HG;
+  const int D = heads * DH;
+  load_tile<G::W, QP, 3, LP, NT>(sq, qkv + b * L * 3 * D + h0 * DH, 3 * D, D, L);
+  load_tile<G::W, OP, 1, LP, NT>(sdo, dO + b * L * D + h0 * DH, D, 0, L);
+  cp_async_wait_all();
+  __syncthreads();
+  const int qcol = hw * DH, kcol = G::W + hw * DH, vcol = 2 * G::W + hw * DH, ocol = hw * DH;
+  const float scale_log2 = scale * 1.4426950408889634f;
+  const LaneOff<QP> lq;
+  const LaneOff<OP> ld;
+  const uint32_t sq32 = smem_u32(sq), sdo32 = smem_u32(sdo);
+  const int nt_valid = (L + 7) >> 3;   // key tiles holding at least one real key (warp-uniform)
+
+  // ---- phase A: S = Q K^T and dP = dO V^T for both query tiles; one K / V fragment load serves both ----
+  float s[2][4][4], dp[2][4][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s[m][n][e] = 0.f; dp[m][n][e] = 0.f; }
+#pragma unroll
+  for (int kd = 0; kd < KD; ++kd) {
+    uint32_t qa[2][4], da[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      ldsm_x4(sq32 + lq.a + (uint32_t)((m * 16 * QP + qcol + kd * 16) * 2), qa[m]);
+      ldsm_x4(sdo32 + ld.a + (uint32_t)((m * 16 * OP + ocol + kd * 16) * 2), da[m]);
+    }
+#pragma unroll
+    for (int n2 = 0; n2 < 2; ++n2) {
+      if (2 * n2 >= nt_valid) break;
+      uint32_t kb[4], vb[4];
+      ldsm_x4(sq32 + lq.k + (uint32_t)((n2 * 16 * QP + kcol + kd * 16) * 2), kb);
+      ldsm_x4(sq32 + lq.k + (uint32_t)((n2 * 16 * QP + vcol + kd * 16) * 2), vb);
+      const bool second = 2 * n2 + 1 < nt_valid;
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        mma(s[m][2 * n2], qa[m], kb[0], kb[1]);
+        mma(dp[m][2 * n2], da[m], vb[0], vb[1]);
+        if (second) {
+          mma(s[m][2 * n2 + 1], qa[m], kb[2], kb[3]);
+          mma(dp[m][2 * n2 + 1], da[m], vb[2], vb[3]);
+        }
+      }
+    }
+  }
+  // softmax rows, delta = sum_j P dP, dS = P (dP - delta) scale; P / dS packed as A fragments (keys = K dimension):
+  //   pa[m][kk][0..3] = { n-tile 2kk rows g, n-tile 2kk rows g+8, n-tile 2kk+1 rows g, n-tile 2kk+1 rows g+8 }
+  uint32_t pa[2][2][4], sa[2][2][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int c = n * 8 + 2 * t;
+      if (c >= L) { s[m][n][0] = -INFINITY; s[m][n][2] = -INFINITY; }
+      if (c + 1 >= L) { s[m][n][1] = -INFINITY; s[m][n][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[m][n][0], s[m][n][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[m][n][2], s[m][n][3]));
+    }
+    mx0 = quad_max(mx0);
+    mx1 = quad_max(mx1);
+    const float nm0 = -mx0 * scale_log2, nm1 = -mx1 * scale_log2;
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      s[m][n][0] = ex2_fast(fmaf(s[m][n][0], scale_log2, nm0));
+      s[m][n][1] = ex2_fast(fmaf(s[m][n][1], scale_log2, nm0));
+      s[m][n][2] = ex2_fast(fmaf(s[m][n][2], scale_log2, nm1));
+      s[m][n][3] = ex2_fast(fmaf(s[m][n][3], scale_log2, nm1));
+      sum0 += s[m][n][0] + s[m][n][1];
+      sum1 += s[m][n][2] + s[m][n][3];
+    }
+    const float inv0 = 1.0f / quad_sum(sum0), inv1 = 1.0f / quad_sum(sum1);
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      s[m][n][0] *= inv0; s[m][n][1] *= inv0;
+      s[m][n][2] *= inv1; s[m][n][3] *= inv1;
+      d0 += s[m][n][0] * dp[m][n][0] + s[m][n][1] * dp[m][n][1];
+      d1 += s[m][n][2] * dp[m][n][2] + s[m][n][3] * dp[m][n][3];
+    }
+    d0 = quad_sum(d0);
+    d1 = quad_sum(d1);
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = 2 * kk + j;
+        pa[m][kk][2 * j] = pack2(s[m][n][0], s[m][n][1]);
+        pa[m][kk][2 * j + 1] = pack2(s[m][n][2], s[m][n][3]);
+        sa[m][kk][2 * j] = pack2(s[m][n][0] * (dp[m][n][0] - d0) * scale, s[m][n][1] * (dp[m][n][1] - d0) * scale);
+        sa[m][kk][2 * j + 1] = pack2(s[m][n][2] * (dp[m][n][2] - d1) * scale, s[m][n][3] * (dp[m][n][3] - d1) * scale);
+      }
+  }
+
+  // out[kt] (16 keys x DH) = sum over both query tiles kq of X[kq]^T (16 keys x 16 queries) * B[kq] (16 queries x DH);
+  // X = P (dV, B = dO) or dS (dK, B = Q).  A fragment of X^T for key tile kt from the packed fragments of X:
+  //   a0 = T(x[kq][kt][0]) a1 = T(x[kq][kt][2]) a2 = T(x[kq][kt][1]) a3 = T(x[kq][kt][3])
+  auto xt_times = [&](const uint32_t (&x)[2][2][4], uint32_t bbase, int bpitch, uint32_t cbase) {
+    float acc[2][ND][4];
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+      for (int nd = 0; nd < ND; ++nd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[kt][nd][e] = 0.f;
+#pragma unroll
+    for (int kq = 0; kq < 2; ++kq) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt) {
+        a[kt][0] = movm_t(x[kq][kt][0]);
+        a[kt][1] = movm_t(x[kq][kt][2]);
+        a[kt][2] = movm_t(x[kq][kt][1]);
+        a[kt][3] = movm_t(x[kq][kt][3]);
+      }
+#pragma unroll
+      for (int n2 = 0; n2 < ND / 2; ++n2) {
+        uint32_t bf[4];
+        ldsm_x4_t(bbase + (uint32_t)((kq * 16 * bpitch + n2 * 16) * 2), bf);
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          mma(acc[kt][2 * n2], a[kt], bf[0], bf[1]);
+          mma(acc[kt][2 * n2 + 1], a[kt], bf[2], bf[3]);
+        }
+      }
+    }
+    __syncwarp();   // all lanes are done reading the operand columns this result may overwrite
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) store_acc<ND, QP>(cbase, kt * 16, acc[kt], 1.f, 1.f);
+  };
+
+  // ---- B1: dV = P^T dO -> v columns (V is dead after phase A) ----
+  xt_times(pa, sdo32 + ld.bt + ocol * 2, OP, sq32 + lq.c + vcol * 2);
+  // ---- B2: dQ = dS K -> the dO columns of this head (dO is dead after B1); one K^T fragment load serves both tiles ----
+  {
+    float acc[2][ND][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nd = 0; nd < ND; ++nd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[m][nd][e] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+      for (int n2 = 0; n2 < ND / 2; ++n2) {
+        uint32_t bf[4];
+        ldsm_x4_t(sq32 + lq.bt + (uint32_t)((kk * 16 * QP + kcol + n2 * 16) * 2), bf);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mma(acc[m][2 * n2], sa[m][kk], bf[0], bf[1]);
+          mma(acc[m][2 * n2 + 1], sa[m][kk], bf[2], bf[3]);
+        }
+      }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 2; ++m) store_acc<ND, OP>(sdo32 + ld.c + ocol * 2, m * 16, acc[m], 1.f, 1.f);
+  }
+  // ---- B3: dK = dS^T Q -> k columns (K is dead after B2) ----
+  xt_times(sa, sq32 + lq.bt + qcol * 2, QP, sq32 + lq.c + kcol * 2);
+  __syncthreads();
+  bf16* out = dqkv + b * L * 3 * D + h0 * DH;
+  store_tile<G::W, OP>(out, 3 * D, sdo, L, NT);                      // dQ
+  store_tile<G::W, QP>(out + D, 3 * D, sq + G::W, L, NT);            // dK
+  store_tile<G::W, QP>(out + 2 * D, 3 * D, sq + 2 * G::W, L, NT);    // dV
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
   if (bytes <= 48 * 1024) return 0;
@@ -423,6 +624,14 @@ int launch_fwd(const void* qkv, void* o, int64_t B, int L, int heads, float scal
 template <int DH, int LP, int HG>
 int launch_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int heads, float scale, cudaStream_t st) {
   using G = Geo<DH, LP, HG>;
+  static const bool staged = getenv("AFB_ATTN_BWD_STAGED") != nullptr;   // debugging knob: the older staged kernel
+  if (LP == 32 && DH == 32 && !staged) {   // register-resident P / dS, shared operand fragments
+    constexpr size_t bytes = G::bwd_tile_bytes;
+    int rc = set_smem(attn_bwd32_kernel<DH, HG>, bytes);
+    if (rc) return rc;
+    attn_bwd32_kernel<DH, HG><<<(unsigned)(B * (heads / HG)), HG * 32, bytes, st>>>((const bf16*)qkv, (const bf16*)dO, (bf16*)dqkv, L, heads, scale);
+    return check_launch("attention_bwd32");
+  }
   int rc = set_smem(attn_bwd_mma_kernel<DH, LP, HG>, G::bwd_bytes);
   if (rc) return rc;
   attn_bwd_mma_kernel<DH, LP, HG><<<(unsigned)(B * (heads / HG)), G::kThreads * bwd_wph(LP), G::bwd_bytes, st>>>((const bf16*)qkv, (const bf16*)dO, (bf16*)dqkv, L, heads,
