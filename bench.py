@@ -267,7 +267,15 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=CFG["per_gpu_batch"])
+    ap.add_argument("--shape", default=None,
+                    help="T,V,classes,style,graph for an ad-hoc workload, e.g. 64,46,14,TS,graph.LMDHG (BASELINE configs[3]); "
+                         "the default (and the line the driver records) is configs[1]")
     args = ap.parse_args()
+    graph_name = "graph.SHRE"
+    if args.shape:
+        parts = args.shape.split(",")
+        CFG.update(T=int(parts[0]), V=int(parts[1]), cls=int(parts[2]), style=parts[3] if parts[3] != "None" else None)
+        graph_name = parts[4] if len(parts) > 4 else graph_name
     if args.impl == "reference":
         return run_reference(args)
 
@@ -287,7 +295,7 @@ def main():
     pk = peaks()
 
     torch.manual_seed(0)
-    model = ab.ST_GCN_AltFormer(3, cls, num_frame=T, num_joints=V, style=CFG["style"], graph="graph.SHRE",
+    model = ab.ST_GCN_AltFormer(3, cls, num_frame=T, num_joints=V, style=CFG["style"], graph=graph_name,
                                 graph_args={"labeling_mode": "spatial"}).to(dev)
     with torch.no_grad():  # the reference's init makes gcn0 invisible (bn gamma 1e-6); use a live one for a fair workload
         model.gcn0.bn.weight.fill_(1.0)
@@ -339,7 +347,8 @@ def main():
         out = {
             "metric": METRIC, "value": gb / (ms * 1e-3), "unit": "seq/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[1]: SHREC'17-shape ST_GCN_AltFormer(style ST) fwd+bwd+AdamW training step, T=32 V=22 28 classes",
+            "config": {"workload": ("configs[1]: SHREC'17-shape ST_GCN_AltFormer(style ST) fwd+bwd+AdamW training step, T=32 V=22 28 classes"
+                                    if not args.shape else f"ad-hoc --shape {args.shape}: ST_GCN_AltFormer fwd+bwd+AdamW training step"),
                        "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
                        "l2": "no explicit flush: the step streams >5 GB of activations per GPU, far beyond the 126 MB L2"},
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "seq/s", "ms_per_step": ms_e2e,
