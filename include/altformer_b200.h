@@ -163,7 +163,8 @@ int afb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, 
 
 /* ------------------------------------------------------------------------------------------ *
  * Small-sequence multi-head attention (model_ST.py:49-67): qkv [B*L, 3*D] with feature index
- * s*D + h*dh + d -> o [B*L, D].  L <= 64, dh in {8,16,32,64}.  Softmax probabilities never leave
+ * s*D + h*dh + d -> o [B*L, D].  L <= 256 (tensor-core kernels for L <= 64 with dh 32 / 64 in bf16, CUDA-core kernels
+ * otherwise; backward needs 16 * L * (dh + 1) bytes of shared memory <= ~220 KB), dh <= 64.  Softmax probabilities never leave
  * the SM.  out_scale (optional, [B]) multiplies whole output sequences (DropPath keep factor; a
  * sequence with factor 0 is written as zeros without being computed).
  * ------------------------------------------------------------------------------------------ */

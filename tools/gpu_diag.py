@@ -429,7 +429,8 @@ def _attn_ref(qkv, B, L, H):
 def grp_attention():
     def attn():
         for (B, L, H, dh) in ((5, 22, 8, 32), (3, 32, 8, 64), (2, 46, 8, 32), (2, 64, 8, 64), (4, 8, 8, 16),
-                              (4, 32, 8, 32), (3, 17, 8, 32), (2, 25, 4, 32), (3, 24, 8, 32), (2, 16, 8, 32), (2, 9, 4, 64)):
+                              (4, 32, 8, 32), (3, 17, 8, 32), (2, 25, 4, 32), (3, 24, 8, 32), (2, 16, 8, 32), (2, 9, 4, 64),
+                              (2, 100, 8, 32), (1, 180, 8, 64), (2, 65, 4, 16), (1, 256, 2, 32)):   # L > 64: coverage kernels
             for dtp, tol in ((torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)):
                 D = H * dh
                 qkv = g(B * L, 3 * D, seed=L, dtype=dtp)

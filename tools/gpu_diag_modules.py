@@ -293,6 +293,7 @@ def grp_model():
     check(lambda: model_case(None, 2, 16, 46, 14, "bf16"))
     check(lambda: model_case("ST", 2, 16, 46, 14, "bf16", training=False))
     check(lambda: model_case("ST", 2, 64, 22, 28, "bf16", training=False))
+    check(lambda: model_case("ST", 2, 180, 22, 14, "fp32"))  # the reference's default num_frame = 180: L = 180 temporal attention
     check(lambda: model_case("TS", 2, 64, 46, 14, "bf16"))   # cfg4 shape (LMDHG: 46 joints, T=64): L=46 / L=64 attention, fwd+bwd
 
 
