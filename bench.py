@@ -213,6 +213,42 @@ def gcn0_roofline(model, x, dev, pk, iters=20):
             "alg_bytes_per_launch": alg_bytes, "ms_per_launch": ms}
 
 
+def step_kernel_rooflines(M, dev, pk, iters=10):
+    """The kernels that carry the step's time (spatial stage, D = 256, M = per-GPU tokens), each timed live with CUDA
+    events over `iters` back-to-back launches on tensors far larger than L2: algorithmic bytes / time vs the HBM peak."""
+    from altformer_b200 import ops
+    mk = lambda r, c: (0.5 * torch.randn(r, c, device=dev)).to(torch.bfloat16)  # noqa: E731
+    x256, x512, g768, res = mk(M, 256), mk(M, 512), mk(M, 768), mk(M, 256)
+    wqkv, wfc2 = mk(768, 256), mk(256, 512)
+    bq, b256 = torch.zeros(768, device=dev), torch.zeros(256, device=dev)
+    dW = torch.zeros(768, 256, device=dev)
+    gam, bet = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+    B, L, H = M // 22, 22, 8
+    cases = [
+        ("gemm_tn qkv 768x256 +bias", lambda: ops.gemm_tn(x256, wqkv, 768, bias=bq), M * (256 + 768) * 2),
+        ("gemm_tn fc2 256x512 +bias+residual", lambda: ops.gemm_tn(x512, wfc2, 256, bias=b256, residual=res), M * (512 + 512) * 2),
+        ("gemm_dw qkv 768x256 +dbias", lambda: ops.gemm_dw(g768, x256, dW, dbias=bq), M * 1024 * 2),
+        ("attention_fwd L=22 8x32", lambda: ops.attention_fwd(g768, B, L, H), M * 4 * 256 * 2),
+        ("attention_bwd L=22 8x32", lambda: ops.attention_bwd(g768, x256, B, L, H), M * 7 * 256 * 2),
+        ("layernorm_fwd 256", lambda: ops.layernorm_fwd(x256, gam, bet, 1e-6), M * 256 * 2 * 2),
+    ]
+    out = []
+    for name, fn, nbytes in cases:
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us = 1e3 * e0.elapsed_time(e1) / iters
+        gbs = nbytes / us / 1e3
+        out.append({"kernel": name, "us": round(us, 1), "achieved": round(gbs, 1), "unit": "GB/s", "frac": round(gbs / pk["hbm"], 3)})
+    return out
+
+
 def cpu_baseline(budget_s=20.0):
     from oracle import altformer_oracle as O
     use_all_host_threads()
@@ -356,6 +392,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clk.summary(),
             "roofline": roof,
+            # the kernels the step actually spends its time in (gcn0 above is the metric's kernel but <1 % of the step)
+            "roofline_step_kernels": (step_kernel_rooflines(B * T * V, dev, pk) if V == 22 and not args.shape else None),
             "roofline_tensor": {"bound": "tensor", "achieved": tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tf / pk["tf"],
                                 "peak_source": pk["src"] + " sustained", "note": "whole step, 3 x forward FLOPs (SURVEY 8d), per GPU"},
         }
