@@ -233,11 +233,19 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
   compute_coef(p, coef);
   __syncthreads();
   const float inv = 1.0f / (float)(p.IC * T);
-  // Gram form of the scores: two threads per (u, v) pair, each over half of the frames, combined by one shuffle
-  for (int it = tid; it < ((V * V * 2 + 31) & ~31); it += nthr) {
+  // Gram form of the scores.  G[a,u,b,v] = G[b,v,a,u]: only the pairs u <= v are accumulated (two threads per pair, each
+  // over half of the frames, combined by one shuffle); the (v, u) score uses the transposed 3x3 block and swapped sums.
+  const int npairs = V * (V + 1) / 2;
+  for (int it = tid; it < ((npairs * 2 + 31) & ~31); it += nthr) {
     const int pr = it >> 1, half = it & 1;
-    const bool live = pr < V * V;
-    const int u = live ? pr / V : 0, v = live ? pr % V : 0;
+    const bool live = pr < npairs;
+    int u = 0, v = 0;
+    if (live) {   // pr = u*V - u(u-1)/2 + (v - u)
+      u = (int)((2.f * V + 1.f - sqrtf((2.f * V + 1.f) * (2.f * V + 1.f) - 8.f * pr)) * 0.5f);
+      while (u * V - (u * (u - 1)) / 2 > pr) --u;
+      while ((u + 1) * V - ((u + 1) * u) / 2 <= pr) ++u;
+      v = u + pr - (u * V - (u * (u - 1)) / 2);
+    }
     float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, su[3] = {0.f, 0.f, 0.f}, sv[3] = {0.f, 0.f, 0.f};
     const int t0 = half ? (T + 1) / 2 : 0, t1 = half ? T : (T + 1) / 2;
 #pragma unroll 4
@@ -251,19 +259,29 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
       su[0] += u0; su[1] += u1; su[2] += u2;
       sv[0] += v0; sv[1] += v1; sv[2] += v2;
     }
-    float sc[3];
+    float sc[3], sct[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {   // the score is linear in (g, su, sv): each half contributes its partial
-      float acc = 0.f;
+      float acc = 0.f, acct = 0.f;
 #pragma unroll
-      for (int q = 0; q < 9; ++q) acc += coef[i][q] * g[q];
+      for (int a = 0; a < 3; ++a) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a) acc += coef[i][9 + a] * su[a] + coef[i][12 + a] * sv[a];
+        for (int c = 0; c < 3; ++c) {
+          acc += coef[i][a * 3 + c] * g[a * 3 + c];
+          acct += coef[i][a * 3 + c] * g[c * 3 + a];
+        }
+        acc += coef[i][9 + a] * su[a] + coef[i][12 + a] * sv[a];
+        acct += coef[i][9 + a] * sv[a] + coef[i][12 + a] * su[a];
+      }
       sc[i] = acc + __shfl_xor_sync(0xffffffffu, acc, 1);
+      sct[i] = acct + __shfl_xor_sync(0xffffffffu, acct, 1);
     }
     if (live && half == 0) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) Ms[(i * V + u) * V + v] = sc[i] * inv;
+      for (int i = 0; i < 3; ++i) {
+        Ms[(i * V + u) * V + v] = sc[i] * inv;
+        Ms[(i * V + v) * V + u] = sct[i] * inv;
+      }
     }
   }
   __syncthreads();
@@ -315,23 +333,42 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
     pb = pa + rem;
   }
   float macc = 0.f;
-  for (int c0 = 0; c0 < T * V; c0 += kPosChunk) {
-    const int np = min(kPosChunk, T * V - c0);
-    for (int it = tid; it < np * 4; it += nthr) {  // r vectors of this chunk: (position, subset | x)
-      const int pl = it >> 2, i = it & 3, pos = c0 + pl;
-      const int t = pos / V, v = pos % V;
-      const float* xt = xs + t * V * 3;
-      float* dst = rs + pl * NR;
-      if (i < 3) {
-        float z0 = 0.f, z1 = 0.f, z2 = 0.f;
-#pragma unroll 4
+  const int chunk_pos = (kPosChunk / V) * V;   // whole frames per chunk
+  for (int c0 = 0; c0 < T * V; c0 += chunk_pos) {
+    const int np = min(chunk_pos, T * V - c0);
+    // r vectors of this chunk: thread = (frame, pair of adjacent joints) computes all nine z for both joints, so every
+    // x value is loaded once for 18 FMAs (chunks hold whole frames: chunk_pos is a multiple of V)
+    {
+      const int vp_n = (V + 1) / 2;
+      const int frames = np / V;
+      for (int it = tid; it < frames * vp_n; it += nthr) {
+        const int tl = it / vp_n, v0 = (it % vp_n) * 2;
+        const bool two = v0 + 1 < V;
+        const int pos0 = c0 + tl * V + v0;
+        const float* xt = xs + (pos0 / V) * V * 3;
+        float z[2][9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) { z[0][j] = 0.f; z[1][j] = 0.f; }
+#pragma unroll 2
         for (int u = 0; u < V; ++u) {
-          const float m = Ms[(i * V + u) * V + v];
-          z0 += xt[u * 3] * m; z1 += xt[u * 3 + 1] * m; z2 += xt[u * 3 + 2] * m;
+          const float x0 = xt[u * 3], x1 = xt[u * 3 + 1], x2 = xt[u * 3 + 2];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float* mrow = Ms + (i * V + u) * V + v0;
+            const float ma = mrow[0], mb = two ? mrow[1] : 0.f;
+            z[0][i * 3] = fmaf(x0, ma, z[0][i * 3]); z[0][i * 3 + 1] = fmaf(x1, ma, z[0][i * 3 + 1]); z[0][i * 3 + 2] = fmaf(x2, ma, z[0][i * 3 + 2]);
+            z[1][i * 3] = fmaf(x0, mb, z[1][i * 3]); z[1][i * 3 + 1] = fmaf(x1, mb, z[1][i * 3 + 1]); z[1][i * 3 + 2] = fmaf(x2, mb, z[1][i * 3 + 2]);
+          }
         }
-        dst[i * 3] = z0; dst[i * 3 + 1] = z1; dst[i * 3 + 2] = z2;
-      } else {
-        dst[9] = xt[v * 3]; dst[10] = xt[v * 3 + 1]; dst[11] = xt[v * 3 + 2];
+        float* dst = rs + (pos0 - c0) * NR;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) dst[j] = z[0][j];
+        dst[9] = xt[v0 * 3]; dst[10] = xt[v0 * 3 + 1]; dst[11] = xt[v0 * 3 + 2];
+        if (two) {
+#pragma unroll
+          for (int j = 0; j < 9; ++j) dst[NR + j] = z[1][j];
+          dst[NR + 9] = xt[v0 * 3 + 3]; dst[NR + 10] = xt[v0 * 3 + 4]; dst[NR + 11] = xt[v0 * 3 + 5];
+        }
       }
     }
     __syncthreads();
