@@ -207,7 +207,7 @@ __device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm 
 // 90 moments) is a chain of small dependent phases, so the kernel is latency-bound -- a wide CTA shortens every
 // phase (only N CTAs exist, 256 for the benchmark batch, so wide CTAs also fill the SMs).
 constexpr int kScoreThreads = 512;    // 2 CTAs per SM: the benchmark's 256 samples run as one wave
-constexpr int kMomSegs = kScoreThreads / 90;   // position segments per moment (5 x 90 threads)
+constexpr int kMomSegs = kScoreThreads / 10;   // position segments per 3 x 3 moment block (51 x 10 threads)
 
 // (__grid_constant__: gcn0_finalize takes the parameter block by reference; without it every thread would first
 // copy the 464-byte struct to local memory -- 120 MB of local stores per launch, the top stall in the r01 profile)
@@ -217,8 +217,7 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
   float* xs = sm;                        // [T*V*3]
   float* Ms = xs + a4(T * V * 3);        // [3][V][V]
-  float* rs = Ms + a4(3 * V * V);        // [kPosChunk][12]   r vectors of one chunk of positions
-  float* part = rs + kPosChunk * NR;     // [kMomSegs][NMOM]
+  float* rs = Ms + a4(3 * V * V);        // [kPosChunk][12]   r vectors of one chunk of positions; then [segs][10][12] partial moments
   __shared__ float coef[3][16];
   __shared__ int is_last;
   const float* xg = p.x + (int64_t)n * T * V * 3;
@@ -228,7 +227,7 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
   } else {
     for (int i = tid; i < T * V * 3; i += nthr) xs[i] = xg[i];
   }
-  float* APs = part + kMomSegs * NMOM;   // [3][V][V]  A + PA (same for every sample; staged while x arrives)
+  float* APs = rs + kPosChunk * NR;      // [3][V][V]  A + PA (same for every sample; staged while x arrives)
   for (int i = tid; i < 3 * V * V; i += nthr) APs[i] = p.A[i] + p.PA[i];
   compute_coef(p, coef);
   __syncthreads();
@@ -323,16 +322,19 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
       p.colsum[(int64_t)n * 3 * VP + e] = cs;
     }
   }
-  // moments: thread (j, seg) owns moment j (12 first + 78 second) over every kMomSegs-th position -- no shuffles
-  const int mj = tid % 90, seg = tid / 90;
-  int pa = 0, pb = 0;
-  if (mj >= NR) {
-    int rem = mj - NR;
-    pa = 0;
-    while (rem >= NR - pa) { rem -= NR - pa; ++pa; }
-    pb = pa + rem;
+  // moments: the 12 x 12 second-moment matrix in 3 x 3 blocks (10 blocks of the upper triangle).  Thread (block, seg)
+  // accumulates its block's 9 products (+ the 3 first moments on diagonal blocks) over every kMomSegs-th position:
+  // 6 loads per 9 FMAs instead of 2 per 1, no shuffles.
+  const int mblk = tid % 10, seg = tid / 10;
+  int bj = 0, bk = 0;
+  {
+    int rem = mblk;
+    while (rem >= 4 - bj) { rem -= 4 - bj; ++bj; }
+    bk = bj + rem;
   }
-  float macc = 0.f;
+  float macc[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) macc[e] = 0.f;
   const int chunk_pos = (kPosChunk / V) * V;   // whole frames per chunk
   for (int c0 = 0; c0 < T * V; c0 += chunk_pos) {
     const int np = min(chunk_pos, T * V - c0);
@@ -373,22 +375,40 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
     }
     __syncthreads();
     if (seg < kMomSegs) {
-      if (mj < NR) {
-#pragma unroll 8
-        for (int pl = seg; pl < np; pl += kMomSegs) macc += rs[pl * NR + mj];
-      } else {
-#pragma unroll 8
-        for (int pl = seg; pl < np; pl += kMomSegs) macc = fmaf(rs[pl * NR + pa], rs[pl * NR + pb], macc);
+#pragma unroll 2
+      for (int pl = seg; pl < np; pl += kMomSegs) {
+        const float* r = rs + pl * NR;
+        const float a0 = r[3 * bj], a1 = r[3 * bj + 1], a2 = r[3 * bj + 2];
+        const float b0 = r[3 * bk], b1 = r[3 * bk + 1], b2 = r[3 * bk + 2];
+        macc[0] = fmaf(a0, b0, macc[0]); macc[1] = fmaf(a0, b1, macc[1]); macc[2] = fmaf(a0, b2, macc[2]);
+        macc[3] = fmaf(a1, b0, macc[3]); macc[4] = fmaf(a1, b1, macc[4]); macc[5] = fmaf(a1, b2, macc[5]);
+        macc[6] = fmaf(a2, b0, macc[6]); macc[7] = fmaf(a2, b1, macc[7]); macc[8] = fmaf(a2, b2, macc[8]);
+        macc[9] += a0; macc[10] += a1; macc[11] += a2;   // first moments (used from the diagonal blocks)
       }
     }
     __syncthreads();
   }
-  if (seg < kMomSegs) part[seg * NMOM + mj] = macc;
+  // per-thread partials -> rs (free now): [seg][block][12]; then moment j gathers its element over the segments
+  if (seg < kMomSegs) {
+#pragma unroll
+    for (int e = 0; e < 12; ++e) rs[(seg * 10 + mblk) * 12 + e] = macc[e];
+  }
   __syncthreads();
   if (tid < 90) {
+    int blk, elem;
+    if (tid < NR) {   // first moment of component tid: diagonal block (tid / 3, tid / 3)
+      const int d = tid / 3;
+      blk = d * 4 - (d * (d - 1)) / 2;
+      elem = 9 + tid % 3;
+    } else {          // second moment (pa <= pb) in the tri() order of the moments buffer
+      int rem = tid - NR, pa = 0;
+      while (rem >= NR - pa) { rem -= NR - pa; ++pa; }
+      const int pb = pa + rem, ja = pa / 3, jb = pb / 3;
+      blk = ja * 4 - (ja * (ja - 1)) / 2 + (jb - ja);
+      elem = (pa % 3) * 3 + (pb % 3);
+    }
     double tot = 0.0;
-#pragma unroll
-    for (int sg = 0; sg < kMomSegs; ++sg) tot += (double)part[sg * NMOM + tid];
+    for (int sg = 0; sg < kMomSegs; ++sg) tot += (double)rs[(sg * 10 + blk) * 12 + elem];
     atomicAdd(p.moments + (blockIdx.x % kSlots) * NMOM + tid, tot);
   }
   // last CTA to finish turns the accumulated moments into statistics and folded weights
@@ -1012,7 +1032,7 @@ extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
   cudaStream_t st = as_stream(s);
   const int T = p->T, V = p->V;
   {
-    size_t smem = ((size_t)a4(T * V * 3) + 2 * a4(3 * V * V) + (size_t)kPosChunk * NR + kMomSegs * NMOM) * sizeof(float);
+    size_t smem = ((size_t)a4(T * V * 3) + 2 * a4(3 * V * V) + (size_t)kPosChunk * NR) * sizeof(float);
     if (smem < 2048 + 8) smem = 2048 + 8;   // the finalize step reuses the buffer for ~252 doubles
     AFB_REQUIRE(smem <= 220 * 1024, "gcn0: T*V too large for the per-sample shared-memory stage (%zu B)", smem);
     if ((rc = set_smem(gcn0_scores_kernel, smem, "gcn0_scores"))) return rc;
