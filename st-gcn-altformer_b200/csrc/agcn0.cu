@@ -110,15 +110,30 @@ constexpr int kSlots = AFB_GCN0_SLOTS;   // fp64 accumulation slots (spreads ato
 constexpr int kPosChunk = 704;           // positions staged per moment pass (33 KB of r vectors)
 
 // E[r], Cov(r) -> batch statistics of both BatchNorms -> BN-folded weights.  Runs in the last CTA to finish.
-__device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm /* >= 96 + 12 + 144 doubles */) {
+__device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm /* >= (96 + 12 + 144 + 4 * 96) doubles + Cout * 12 floats */) {
   double* tot = dsm;
   double* E = dsm + NMOM;
   double* Cov = E + NR;   // [NR][NR]
   const int tid = threadIdx.x;
-  for (int j = tid; j < NMOM; j += blockDim.x) {
-    double s = 0.0;
-    for (int l = 0; l < kSlots; ++l) s += __ldcg(p.moments + l * NMOM + j);
-    tot[j] = s;
+  // slot sums with every thread holding at most a few loads in flight (a 32-long dependent load chain per moment
+  // used to put ~5 us on the tail of the launch): thread (j, group) sums its group's slots, then the groups are added
+  {
+    double* partial = Cov + NR * NR;          // [kSlotGroups][NMOM] scratch behind Cov
+    constexpr int kSlotGroups = 4;
+    const int j = tid % NMOM, grp = tid / NMOM;
+    if (grp < kSlotGroups) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int l = grp; l < kSlots; l += kSlotGroups) sacc += __ldcg(p.moments + l * NMOM + j);
+      partial[grp * NMOM + j] = sacc;
+    }
+    __syncthreads();
+    if (tid < NMOM) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int q = 0; q < kSlotGroups; ++q) sacc += partial[q * NMOM + tid];
+      tot[tid] = sacc;
+    }
   }
   __syncthreads();
   const double m = (double)p.N * p.T * p.V;
@@ -132,16 +147,20 @@ __device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm 
   __syncthreads();
   if (tid < NR) p.stats[tid] = (float)E[tid];
   for (int e = tid; e < NR * NR; e += blockDim.x) p.stats[NR + e] = (float)Cov[e];
+  // the 12 mixing weights of every output channel -> shared memory with all threads (the per-channel loop below used to
+  // start with 12 + 3 dependent global loads and a dynamically indexed local array: 6-8 us on the tail of the launch)
+  float* wsm = reinterpret_cast<float*>(Cov + NR * NR + 4 * NMOM);   // [Cout][12] behind the slot partials
+  for (int e = tid; e < p.Cout * NR; e += blockDim.x) {
+    const int o = e / NR, j = e % NR;
+    wsm[e] = j < 9 ? p.Wd[j / 3][o * 3 + j % 3] : p.Wdn[o * 3 + (j - 9)];
+  }
+  __syncthreads();
   // 4 lanes per output channel split the rows of the two quadratic forms (fp64 chains are the critical path here)
   for (int o4 = tid; o4 < p.Cout * 4; o4 += blockDim.x) {
     const int o = o4 >> 2, part = o4 & 3;
-    double w[NR];
+    const float* w = wsm + o * NR;
     double b = 0.0;
-    for (int i = 0; i < 3; ++i) {
-      for (int a = 0; a < 3; ++a) w[i * 3 + a] = p.Wd[i][o * 3 + a];
-      b += p.bd[i][o];
-    }
-    for (int a = 0; a < 3; ++a) w[9 + a] = p.Wdn[o * 3 + a];
+    if (part == 0) b = (double)p.bd[0][o] + (double)p.bd[1][o] + (double)p.bd[2][o];
     double mean_h = 0.0, mean_d = 0.0, var_h = 0.0, var_d = 0.0;
     for (int j = part; j < 9; j += 4) {
       mean_h += w[j] * E[j];
@@ -181,17 +200,20 @@ __device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm 
     }
     const double rstd_h = 1.0 / sqrt(var_h + (double)p.eps), rstd_d = 1.0 / sqrt(var_d + (double)p.eps);
     const double sh = p.bn_g[o] * rstd_h, sd = p.dn_g[o] * rstd_d;
-    float* wf = p.Wfold + o * 16;
+    float wf[16];   // folded weights stay in registers: stored as float4s, packed into the MMA fragments from here
+#pragma unroll
     for (int j = 0; j < 9; ++j) wf[j] = (float)(sh * w[j]);
+#pragma unroll
     for (int j = 9; j < 12; ++j) wf[j] = (float)(sd * w[j]);
     wf[12] = (float)(sh * (ctr_h - mean_h) + p.bn_b[o] + sd * (ctr_d - mean_d) + p.dn_b[o]);
     wf[13] = wf[14] = wf[15] = 0.f;
+    float4* wfg = reinterpret_cast<float4*>(p.Wfold + o * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wfg[q] = make_float4(wf[4 * q], wf[4 * q + 1], wf[4 * q + 2], wf[4 * q + 3]);
     if (p.Wfrag != nullptr) {   // mma.m16n8k16 B fragments of Wfold^T, one uint2 per (n-tile, lane)
-      uint32_t* frag = reinterpret_cast<uint32_t*>(p.Wfrag) + ((o >> 3) * 32 + (o & 7) * 4) * 2;
-      for (int t = 0; t < 4; ++t) {
-        frag[t * 2] = pack_bf16(wf[2 * t], wf[2 * t + 1]);
-        frag[t * 2 + 1] = pack_bf16(wf[2 * t + 8], wf[2 * t + 9]);
-      }
+      uint2* frag = reinterpret_cast<uint2*>(p.Wfrag) + ((o >> 3) * 32 + (o & 7) * 4);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) frag[t] = make_uint2(pack_bf16(wf[2 * t], wf[2 * t + 1]), pack_bf16(wf[2 * t + 8], wf[2 * t + 9]));
     }
     p.stats[NSTAT + o] = (float)mean_h;
     p.stats[NSTAT + p.Cout + o] = (float)rstd_h;
@@ -284,26 +306,53 @@ __global__ void __launch_bounds__(kScoreThreads, 2) gcn0_scores_kernel(const __g
     }
   }
   __syncthreads();
-  // softmax over u for fixed (i, v): one warp per column, lanes over u (V <= 64: two rows per lane)
-  for (int col = warp; col < 3 * V; col += nthr >> 5) {
-    const int i = col / V, v = col % V;
-    const int u0 = lane, u1 = lane + 32;
-    const float s0 = u0 < V ? Ms[(i * V + u0) * V + v] : -INFINITY;
-    const float s1 = u1 < V ? Ms[(i * V + u1) * V + v] : -INFINITY;
-    const float mx = warp_max(fmaxf(s0, s1));
-    const float e0 = u0 < V ? __expf(s0 - mx) : 0.f, e1 = u1 < V ? __expf(s1 - mx) : 0.f;
-    const float rden = 1.0f / warp_sum(e0 + e1);
-    if (u0 < V) {
-      const int idx = (i * V + u0) * V + v;
-      const float m = e0 * rden + APs[idx];
-      Ms[idx] = m;
-      p.Mmat[(int64_t)n * 3 * V * V + idx] = m;
-    }
-    if (u1 < V) {
-      const int idx = (i * V + u1) * V + v;
-      const float m = e1 * rden + APs[idx];
-      Ms[idx] = m;
-      p.Mmat[(int64_t)n * 3 * V * V + idx] = m;
+  // softmax over u for fixed (i, v): one warp per column, lanes over u (V <= 64: two rows per lane); four columns per
+  // warp step so four independent reduce / exp / reduce chains are in flight
+  {
+    const int nw = nthr >> 5, ncol = 3 * V;
+    for (int c0 = warp; c0 < ncol; c0 += 4 * nw) {
+      float s0[4], s1[4], mx[4], e0[4], e1[4], den[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int col = c0 + k * nw;
+        const int i = col / V, v = col % V;
+        s0[k] = (col < ncol && lane < V) ? Ms[(i * V + lane) * V + v] : -INFINITY;
+        s1[k] = (col < ncol && lane + 32 < V) ? Ms[(i * V + lane + 32) * V + v] : -INFINITY;
+        mx[k] = fmaxf(s0[k], s1[k]);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], off));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        e0[k] = s0[k] > -INFINITY ? __expf(s0[k] - mx[k]) : 0.f;
+        e1[k] = s1[k] > -INFINITY ? __expf(s1[k] - mx[k]) : 0.f;
+        den[k] = e0[k] + e1[k];
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) den[k] += __shfl_xor_sync(0xffffffffu, den[k], off);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int col = c0 + k * nw;
+        if (col >= ncol) continue;
+        const int i = col / V, v = col % V;
+        const float rden = 1.0f / den[k];
+        if (lane < V) {
+          const int idx = (i * V + lane) * V + v;
+          const float m = e0[k] * rden + APs[idx];
+          Ms[idx] = m;
+          p.Mmat[(int64_t)n * 3 * V * V + idx] = m;
+        }
+        if (lane + 32 < V) {
+          const int idx = (i * V + lane + 32) * V + v;
+          const float m = e1[k] * rden + APs[idx];
+          Ms[idx] = m;
+          p.Mmat[(int64_t)n * 3 * V * V + idx] = m;
+        }
+      }
     }
   }
   __syncthreads();
@@ -1033,7 +1082,8 @@ extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
   const int T = p->T, V = p->V;
   {
     size_t smem = ((size_t)a4(T * V * 3) + 2 * a4(3 * V * V) + (size_t)kPosChunk * NR) * sizeof(float);
-    if (smem < 2048 + 8) smem = 2048 + 8;   // the finalize step reuses the buffer for ~252 doubles
+    const size_t fin_bytes = 636 * sizeof(double) + (size_t)p->Cout * NR * sizeof(float) + 16;
+    if (smem < fin_bytes) smem = fin_bytes;   // the finalize step reuses the buffer (636 doubles + Cout x 12 floats)
     AFB_REQUIRE(smem <= 220 * 1024, "gcn0: T*V too large for the per-sample shared-memory stage (%zu B)", smem);
     if ((rc = set_smem(gcn0_scores_kernel, smem, "gcn0_scores"))) return rc;
     gcn0_scores_kernel<<<p->N, kScoreThreads, smem, st>>>(*p);
