@@ -150,6 +150,10 @@ __device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm 
   // the 12 mixing weights of every output channel -> shared memory with all threads (the per-channel loop below used to
   // start with 12 + 3 dependent global loads and a dynamically indexed local array: 6-8 us on the tail of the launch)
   float* wsm = reinterpret_cast<float*>(Cov + NR * NR + 4 * NMOM);   // [Cout][12] behind the slot partials
+  float* Ef = wsm + p.Cout * NR;                                     // [12] + [144] fp32 copies of E and Cov
+  float* Covf = Ef + 16;
+  if (tid < NR) Ef[tid] = (float)E[tid];
+  for (int e = tid; e < NR * NR; e += blockDim.x) Covf[e] = (float)Cov[e];
   for (int e = tid; e < p.Cout * NR; e += blockDim.x) {
     const int o = e / NR, j = e % NR;
     wsm[e] = j < 9 ? p.Wd[j / 3][o * 3 + j % 3] : p.Wdn[o * 3 + (j - 9)];
@@ -161,27 +165,32 @@ __device__ __noinline__ void gcn0_finalize(const afb_gcn0_fwd_t& p, double* dsm 
     const float* w = wsm + o * NR;
     double b = 0.0;
     if (part == 0) b = (double)p.bd[0][o] + (double)p.bd[1][o] + (double)p.bd[2][o];
-    double mean_h = 0.0, mean_d = 0.0, var_h = 0.0, var_d = 0.0;
+    // E and Cov were formed in fp64 (that is where the cancellation is); the per-channel contractions run in fp32 like
+    // the reference's own BatchNorm statistics -- fp64 chains here were the serial tail of the launch
+    float mean_hf = 0.f, mean_df = 0.f, var_hf = 0.f, var_df = 0.f;
     for (int j = part; j < 9; j += 4) {
-      mean_h += w[j] * E[j];
-      double row = 0.0;
-      for (int k = 0; k < 9; ++k) row += Cov[j * NR + k] * w[k];
-      var_h += w[j] * row;
+      mean_hf = fmaf(w[j], Ef[j], mean_hf);
+      float row = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) row = fmaf(Covf[j * NR + k], w[k], row);
+      var_hf = fmaf(w[j], row, var_hf);
     }
     if (part < 3) {
       const int j = 9 + part;
-      mean_d += w[j] * E[j];
-      double row = 0.0;
-      for (int k = 9; k < 12; ++k) row += Cov[j * NR + k] * w[k];
-      var_d += w[j] * row;
+      mean_df = w[j] * Ef[j];
+      float row = 0.f;
+#pragma unroll
+      for (int k = 9; k < 12; ++k) row = fmaf(Covf[j * NR + k], w[k], row);
+      var_df = w[j] * row;
     }
 #pragma unroll
     for (int off = 1; off < 4; off <<= 1) {   // the 4 lanes of a channel are adjacent; blockDim and Cout*4 are multiples of 32
-      mean_h += __shfl_xor_sync(0xffffffffu, mean_h, off);
-      mean_d += __shfl_xor_sync(0xffffffffu, mean_d, off);
-      var_h += __shfl_xor_sync(0xffffffffu, var_h, off);
-      var_d += __shfl_xor_sync(0xffffffffu, var_d, off);
+      mean_hf += __shfl_xor_sync(0xffffffffu, mean_hf, off);
+      mean_df += __shfl_xor_sync(0xffffffffu, mean_df, off);
+      var_hf += __shfl_xor_sync(0xffffffffu, var_hf, off);
+      var_df += __shfl_xor_sync(0xffffffffu, var_df, off);
     }
+    double mean_h = mean_hf, mean_d = mean_df, var_h = var_hf, var_d = var_df;
     if (part != 0) continue;
     mean_h += b;
     mean_d += p.bdn[o];
@@ -1082,7 +1091,7 @@ extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
   const int T = p->T, V = p->V;
   {
     size_t smem = ((size_t)a4(T * V * 3) + 2 * a4(3 * V * V) + (size_t)kPosChunk * NR) * sizeof(float);
-    const size_t fin_bytes = 636 * sizeof(double) + (size_t)p->Cout * NR * sizeof(float) + 16;
+    const size_t fin_bytes = 636 * sizeof(double) + ((size_t)p->Cout * NR + 16 + NR * NR) * sizeof(float) + 16;
     if (smem < fin_bytes) smem = fin_bytes;   // the finalize step reuses the buffer (636 doubles + Cout x 12 floats)
     AFB_REQUIRE(smem <= 220 * 1024, "gcn0: T*V too large for the per-sample shared-memory stage (%zu B)", smem);
     if ((rc = set_smem(gcn0_scores_kernel, smem, "gcn0_scores"))) return rc;
