@@ -35,6 +35,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// relu(a), relu(b) -> bf16x2 (a in the low half), one instruction
+__device__ __forceinline__ uint32_t relu_pack2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// four 8x8 b16 tiles from mma C-fragment registers to shared memory; lane l supplies the row address of tile l / 8, row l % 8
+__device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
 struct Coef {  // per subset: C (3x3), e (3), f (3)
   float v[3][16];
 };
@@ -707,13 +718,15 @@ __global__ void __launch_bounds__(kThreads) gcn0_apply_mma_kernel(const afb_gcn0
         a2[2] = 0u;
         a2[3] = 0u;
       }
+      // two n-tiles per step: ReLU folded into the bf16 conversion (cvt.rn.relu), the four 8x8 tiles (rows g / g+8 of
+      // both n-tiles) leave through one stmatrix instead of four 4-byte stores
+      const uint32_t st_row = smem_u32(mystage + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * OP + (lane >> 4) * 8);
 #pragma unroll
-      for (int nt = 0; nt < COUT / 8; ++nt) {
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
-        mma(d, a2, bfrag[nt][0], bfrag[nt][1]);
-        bf16* o0 = mystage + v0 * OP + nt * 8 + 2 * t;
-        *reinterpret_cast<uint32_t*>(o0) = pack2(fmaxf(d[0], 0.f), fmaxf(d[1], 0.f));
-        *reinterpret_cast<uint32_t*>(o0 + 8 * OP) = pack2(fmaxf(d[2], 0.f), fmaxf(d[3], 0.f));
+      for (int nt = 0; nt < COUT / 8; nt += 2) {
+        float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+        mma(d0, a2, bfrag[nt][0], bfrag[nt][1]);
+        mma(d1, a2, bfrag[nt + 1][0], bfrag[nt + 1][1]);
+        stsm_x4(st_row + nt * 16, relu_pack2(d0[0], d0[1]), relu_pack2(d0[2], d0[3]), relu_pack2(d1[0], d1[1]), relu_pack2(d1[2], d1[3]));
       }
     }
     __syncwarp();
