@@ -245,12 +245,24 @@ __global__ void __launch_bounds__(kBlock) colstats_kernel(const T* __restrict__ 
   __shared__ float sred[2][kRowLanes][kColTile];
   const ColTile t = col_tile(M, C);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-  if (t.active)
-    for (int64_t r = t.r_begin + t.rl; r < t.r_end; r += kRowLanes) {
+  if (t.active) {
+    int64_t r = t.r_begin + t.rl;
+    for (; r + 3 * kRowLanes < t.r_end; r += 4 * kRowLanes) {   // four independent row loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = ld4<T>(x + (r + k * kRowLanes) * ldx + t.c4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w;
+        q.x += v[k].x * v[k].x; q.y += v[k].y * v[k].y; q.z += v[k].z * v[k].z; q.w += v[k].w * v[k].w;
+      }
+    }
+    for (; r < t.r_end; r += kRowLanes) {
       const float4 v = ld4<T>(x + r * ldx + t.c4);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
     }
+  }
   *reinterpret_cast<float4*>(&sred[0][t.rl][(threadIdx.x & 31) * 4]) = s;
   *reinterpret_cast<float4*>(&sred[1][t.rl][(threadIdx.x & 31) * 4]) = q;
   __syncthreads();
@@ -760,7 +772,9 @@ extern "C" int afb_layernorm_bwd(const void* dy, int dyd, const void* x, int xd,
 static bool col_shape_ok(int C) { return C % 4 == 0 && C >= 4; }
 static dim3 col_grid(int64_t M, int C) {
   const int col_tiles = ceil_div(C, kColTile);
-  int row_blocks = grid_for(M, kRowLanes * 16, (148 * 8) / col_tiles > 0 ? (148 * 8) / col_tiles : 1);
+  // every block ends with one atomic per column: ~4 blocks per SM keep the same-address atomics (fp64 for the BatchNorm
+  // statistics) off the critical path -- 1184 blocks spent most of a 35 us launch queueing 1184 atomics per address
+  int row_blocks = grid_for(M, kRowLanes * 16, (148 * 4) / col_tiles > 0 ? (148 * 4) / col_tiles : 1);
   return dim3(row_blocks, col_tiles);
 }
 
