@@ -20,3 +20,17 @@ with torch.no_grad():
         y = mod.forward_skeleton(x)
 torch.cuda.synchronize()
 print("ok", tuple(y.shape), float(y.float().abs().mean()))
+
+if os.environ.get("BWD") == "1":   # forward + backward (parameter gradients), CUDA events over 10 iterations
+    g = torch.randn(y.shape, device="cuda").to(y.dtype)
+    for _ in range(3):
+        mod.zero_grad(set_to_none=True)
+        mod.forward_skeleton(x).backward(g)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        mod.forward_skeleton(x).backward(g)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"gcn0 fwd+bwd (eager, incl. host launch gaps): {1e3 * e0.elapsed_time(e1) / 10:.1f} us")
