@@ -258,12 +258,16 @@ typedef struct {
   int32_t training;
   float momentum, eps;
   float* Mmat;         /* out [N][3][V][V]: softmax_u(S_i) + A_i + PA_i (saved for backward) */
-  double* moments;     /* persistent workspace [AFB_GCN0_SLOTS][AFB_GCN0_NMOM], ZERO before the first call; the
-                          kernel re-zeroes it, so one buffer serves every launch on a stream */
-  int32_t* counter;    /* persistent, zero-initialised CTA ticket (re-armed by the kernel) */
+  double* moments;     /* persistent workspace [3][AFB_GCN0_SLOTS][AFB_GCN0_NMOM], ZERO before the first call; the
+                          kernels re-zero it ([0]: two-kernel path; [1], [2]: the fused kernel's ping-pong halves),
+                          so one buffer serves every launch on a stream */
+  int32_t* counter;    /* persistent, zero-initialised int32[8]: CTA ticket (word 0) / fused kernel's grid-barrier words (4..6)
+                          (re-armed by the kernels) */
   float* stats;        /* out [AFB_GCN0_NSTAT_BASE + 4*Cout]: E[r] (12), Cov(r) (144), mean_h, rstd_h, mean_d, rstd_d */
   float* Wfold;        /* out [Cout][16]: BN-folded weights of the apply pass */
-  void* Aop;           /* out (optional) bf16 [N][3][VP][VP+8], VP = V rounded up to 16: A_i[v][u] = M_i[u][v] */
+  void* Aop;           /* out (optional) bf16 operand copy of M for the tensor-core passes, afb_gcn0_aop_bytes(N, V)
+                          bytes: two-kernel path [N][3][VP][VP+8] (A_i[v][u] = M_i[u][v], VP = V rounded up to 16);
+                          fused kernel [N][2 (hi, lo)][3*CB][40] with column c = i*CB + v, CB = V rounded up to 8 */
   float* colsum;       /* out (optional) [N][3][VP]: sum_u M_i[u][v] */
   void* Wfrag;         /* out (optional) uint32 [Cout/8][32][2]: Wfold as mma.m16n8k16 B fragments (bf16 pairs);
                           the tensor-core apply pass needs Aop, colsum and Wfrag (V <= 48) */
@@ -276,6 +280,11 @@ typedef struct {
 #define AFB_GCN0_SLOTS 32       /* fp64 accumulation slots */
 #define AFB_GCN0_NSTAT_BASE 160 /* 12 + 144, padded */
 int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s);
+/* bytes the caller allocates for afb_gcn0_fwd_t::Aop */
+int64_t afb_gcn0_aop_bytes(int N, int V);
+/* profiling aid: globaltimer stamps (ns) of the last fused-kernel launch, 8 per CTA for the first `ctas` CTAs:
+ * entry, operands staged, M done, r rows done, moments posted, barrier passed, weights folded, stores issued */
+int afb_gcn0_fused_stamps(uint64_t* out, int ctas);
 
 /* Backward (parameter gradients only: gcn0's input is the data tensor, model/AltFormer/
  * ST_GCN_AltFormer.py:70, so dx is never required).  Training-mode BN only. */

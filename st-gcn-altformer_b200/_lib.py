@@ -104,6 +104,8 @@ def _declare(L):
         "afb_step_inc": [vp, vp],
         "afb_scale_rows": [vp, vp, i32, i64, i32, vp, i32, vp],
         "afb_gcn0_fwd": [P(Gcn0Fwd), vp],
+        "afb_gcn0_aop_bytes": [i32, i32],
+        "afb_gcn0_fused_stamps": [vp, i32],
         "afb_gcn0_bwd": [P(Gcn0Bwd), vp],
         "afb_agcn_scores_fwd": [vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "afb_agcn_aggregate_fwd": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
@@ -116,7 +118,7 @@ def _declare(L):
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args
-        fn.restype = C.c_int
+        fn.restype = C.c_int64 if name == "afb_gcn0_aop_bytes" else C.c_int
     L._afb_signatures = sig
 
 

@@ -1095,12 +1095,31 @@ int check_fwd_args(const afb_gcn0_fwd_t* p) {
 }  // namespace
 }  // namespace afb
 
+namespace afb {
+int gcn0_fused_launch(const afb_gcn0_fwd_t* p, cudaStream_t st);   // agcn0_fused.cu
+size_t gcn0_fused_mop_bytes(int N, int V);
+int gcn0_fused_stamps(unsigned long long* out, int ctas);
+}
+
 using namespace afb;
+
+extern "C" int64_t afb_gcn0_aop_bytes(int N, int V) {
+  const int VP = V <= 16 ? 16 : (V <= 32 ? 32 : 48);
+  const size_t two_kernel = (size_t)N * 3 * VP * (VP + 8) * 2, fused = gcn0_fused_mop_bytes(N, V);
+  return (int64_t)(two_kernel > fused ? two_kernel : fused);
+}
+
+extern "C" int afb_gcn0_fused_stamps(uint64_t* out, int ctas) {
+  AFB_REQUIRE(out && ctas > 0, "gcn0_fused_stamps: bad args");
+  return gcn0_fused_stamps(reinterpret_cast<unsigned long long*>(out), ctas);
+}
 
 extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
   int rc = check_fwd_args(p);
   if (rc) return rc;
   cudaStream_t st = as_stream(s);
+  rc = gcn0_fused_launch(p, st);   // one cooperative kernel (bf16 mode, shapes it covers); -1 = not covered
+  if (rc >= 0) return rc;
   const int T = p->T, V = p->V;
   {
     size_t smem = ((size_t)a4(T * V * 3) + 2 * a4(3 * V * V) + (size_t)kPosChunk * NR) * sizeof(float);

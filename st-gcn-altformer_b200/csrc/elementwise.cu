@@ -807,9 +807,16 @@ extern "C" int afb_bn_act_fwd(const void* x, int xd, const float* scale, const f
                               const void* res_post, int rd, int relu, void* y, void* y2, int yd, int64_t M, int C, int T, int V,
                               afb_stream s) {
   AFB_REQUIRE(x && scale && shift && (y || y2) && M > 0 && C % 4 == 0, "bn_act_fwd: bad args");
-  AFB_REQUIRE(xd == yd && ((!res_pre && !res_post) || rd == yd), "bn_act_fwd: activations must share one dtype");
+  // one dtype for everything, or the "exact mask" layout of the bf16 mode: fp32 pre-activation x, bf16 residual / outputs
+  const bool mixed = xd == AFB_F32 && yd == AFB_BF16;
+  AFB_REQUIRE((xd == yd || mixed) && ((!res_pre && !res_post) || rd == yd), "bn_act_fwd: unsupported dtype combination");
   AFB_REQUIRE(y2 == nullptr || (T > 0 && V > 0 && M % ((int64_t)T * V) == 0), "bn_act_fwd: permuted copy needs T,V");
   const int grid = grid_for(M * (C / 4), kBlock);
+  if (mixed) {
+    bn_act_fwd_kernel<float, bf16, bf16><<<grid, kBlock, 0, as_stream(s)>>>((const float*)x, scale, shift, (const bf16*)res_pre,
+                                                                            (const bf16*)res_post, relu, (bf16*)y, (bf16*)y2, M, C, T, V);
+    return check_launch("bn_act_fwd");
+  }
   DISPATCH_DT(xd, T_, (bn_act_fwd_kernel<T_, T_, T_><<<grid, kBlock, 0, as_stream(s)>>>(
                           (const T_*)x, scale, shift, (const T_*)res_pre, (const T_*)res_post, relu, (T_*)y, (T_*)y2, M, C, T, V)));
   return check_launch("bn_act_fwd");
@@ -820,8 +827,14 @@ extern "C" int afb_bn_bwd_reduce(const void* dy, const void* dy2, int gd, const 
                                  float* dgamma, float* dbeta, int64_t M, int C, int T, int V, afb_stream s) {
   AFB_REQUIRE((dy || dy2) && x && mean && rstd && gamma && beta && dgamma && dbeta && M > 0, "bn_bwd_reduce: bad args");
   AFB_REQUIRE(col_shape_ok(C), "bn_bwd_reduce: C=%d unsupported", C);
-  AFB_REQUIRE(gd == xd && (res_pre == nullptr || rd == xd), "bn_bwd_reduce: activations must share one dtype");
+  const bool mixed = xd == AFB_F32 && gd == AFB_BF16;
+  AFB_REQUIRE((gd == xd || mixed) && (res_pre == nullptr || rd == gd), "bn_bwd_reduce: unsupported dtype combination");
   AFB_REQUIRE(dy2 == nullptr || (T > 0 && V > 0 && M % ((int64_t)T * V) == 0), "bn_bwd_reduce: permuted grad needs T,V");
+  if (mixed) {
+    bn_bwd_reduce_kernel<bf16, float, bf16><<<col_grid(M, C), kBlock, 0, as_stream(s)>>>(
+        (const bf16*)dy, (const bf16*)dy2, (const float*)x, (const bf16*)res_pre, mean, rstd, gamma, beta, relu, dgamma, dbeta, M, C, T, V);
+    return check_launch("bn_bwd_reduce");
+  }
   DISPATCH_DT(xd, T_, (bn_bwd_reduce_kernel<T_, T_, T_><<<col_grid(M, C), kBlock, 0, as_stream(s)>>>(
                           (const T_*)dy, (const T_*)dy2, (const T_*)x, (const T_*)res_pre, mean, rstd, gamma, beta, relu, dgamma, dbeta,
                           M, C, T, V)));
@@ -834,8 +847,15 @@ extern "C" int afb_bn_bwd_apply(const void* dy, const void* dy2, int gd, const v
                                 int V, afb_stream s) {
   AFB_REQUIRE((dy || dy2) && x && mean && rstd && gamma && beta && dgamma && dbeta && dx && M > 0 && C % 4 == 0,
               "bn_bwd_apply: bad args");
-  AFB_REQUIRE(gd == xd && od == xd && (res_pre == nullptr || rd == xd), "bn_bwd_apply: activations must share one dtype");
+  const bool mixed = xd == AFB_F32 && gd == AFB_BF16;
+  AFB_REQUIRE((gd == xd || mixed) && od == gd && (res_pre == nullptr || rd == gd), "bn_bwd_apply: unsupported dtype combination");
   const int grid = grid_for(M * (C / 4), kBlock);
+  if (mixed) {
+    bn_bwd_apply_kernel<bf16, float, bf16, bf16><<<grid, kBlock, 0, as_stream(s)>>>(
+        (const bf16*)dy, (const bf16*)dy2, (const float*)x, (const bf16*)res_pre, mean, rstd, gamma, beta, dgamma, dbeta, relu, training,
+        (bf16*)dx, (bf16*)dres, M, C, T, V);
+    return check_launch("bn_bwd_apply");
+  }
   DISPATCH_DT(xd, T_, (bn_bwd_apply_kernel<T_, T_, T_, T_><<<grid, kBlock, 0, as_stream(s)>>>(
                           (const T_*)dy, (const T_*)dy2, (const T_*)x, (const T_*)res_pre, mean, rstd, gamma, beta, dgamma, dbeta, relu,
                           training, (T_*)dx, (T_*)dres, M, C, T, V)));

@@ -1194,6 +1194,12 @@ int launch_dw(const CUtensorMap& tmG, const CUtensorMap& tmX, const DwArgs& a, c
 }
 
 }  // namespace
+
+// bf16 3-D tensor map (cols, rows, batch) with 128B swizzle for kernels in other translation units (gcn0 fused store)
+int make_tensor_map_bf16(void* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
+                         uint32_t box0, uint32_t box1) {
+  return make_map(reinterpret_cast<CUtensorMap*>(map), ptr, d0, d1, d2, stride1, stride2, box0, box1, 3);
+}
 }  // namespace afb
 
 using namespace afb;

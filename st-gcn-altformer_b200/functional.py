@@ -7,6 +7,7 @@ Precision modes (set_precision):
          over hi/lo-split operands (hi*hi + lo*hi + hi*lo, K-concatenated), good to ~1e-5 relative.
 """
 import ctypes as C
+import os
 import weakref
 
 import torch
@@ -15,6 +16,7 @@ from . import _lib, ops
 from .ops import ACT_GELU, ACT_GELU_BWD, ACT_NONE
 
 _PRECISION = ["bf16"]
+_EXACT_BN = [True]   # bf16 mode: BatchNorm+ReLU pre-activations kept in fp32 and computed with hi+lo weights (see set_exact_bn_mask)
 _EPOCH = [0]  # bumped by the trainer after an optimizer step that bypasses tensor version counters
 
 
@@ -26,6 +28,20 @@ def set_precision(mode):
 
 def get_precision():
     return _PRECISION[0]
+
+
+def set_exact_bn_mask(on):
+    """bf16 mode only.  A batch-stat BatchNorm followed by ReLU turns a 2^-9 rounding of its input into flipped mask
+    entries (~0.1 % of them), and every flipped entry moves the gradient by its full magnitude: 2-7e-2 relative L2 on
+    the layer's gradients (tools/probe_relu_mask.py reproduces it on the CPU reference).  With this switch on
+    (default) the temporal conv that feeds such a BatchNorm adds the bf16 LOW half of its fp32 weights in a second
+    tcgen05 pass and writes the pre-activation in fp32, so the mask is decided on unrounded values; gcn0 does the same
+    inside its apply pass.  Costs one extra conv GEMM (~1 % of a cfg2 step)."""
+    _EXACT_BN[0] = bool(on)
+
+
+def exact_bn_mask():
+    return _EXACT_BN[0] and _PRECISION[0] == "bf16"
 
 
 def act_dtype():
@@ -102,6 +118,16 @@ def conv_packs(p):
         return ops.split3(f32_fwd, 1).view(co, k * 3 * ci), ops.split3(f32_bwd, 1).view(ci, k * 3 * co)
 
     return _derived(p, "conv_split", make)
+
+
+def conv_pack_lo(p):
+    """forward operand [co, k*ci] of the bf16 LOW half  w - bf16(w)  of the conv weight (exact-mask second pass)."""
+    def make(w):
+        w = w.contiguous()
+        hi32 = ops.cast(ops.cast(w, torch.bfloat16), torch.float32)
+        return ops.conv_weight_pack(ops.axpby(w, 1.0, hi32, -1.0))[0]
+
+    return _derived(p, "conv_lo", make)
 
 
 def _grad_sink(p):
@@ -469,11 +495,15 @@ class Unit2DFn(torch.autograd.Function):
         fwd_w, _ = conv_packs(conv_w)
         three = 1 if get_precision() == "bf16" else 3
         a = x if three == 1 else ops.split3(x, 0)
-        raw = ops.gemm_tn(a, fwd_w, co, k_per_tap=three * ci, taps=k, tap_row_stride=V, tap_pad=(k - 1) // 2,
-                          rows_per_batch=T * V, batches=N, bias=None if conv_b is None else conv_b.detach(),
-                          out_dtype=act_dtype())
+        exact = exact_bn_mask()
+        geo = dict(k_per_tap=three * ci, taps=k, tap_row_stride=V, tap_pad=(k - 1) // 2, rows_per_batch=T * V, batches=N)
+        raw = ops.gemm_tn(a, fwd_w, co, bias=None if conv_b is None else conv_b.detach(),
+                          out_dtype=torch.float32 if exact else act_dtype(), **geo)
+        if exact:   # + x * (w - bf16(w)): the pre-activation is now the fp32 conv of the bf16 activations
+            ops.gemm_tn(a, conv_pack_lo(conv_w), co, residual=raw, out=raw, out_dtype=torch.float32, **geo)
         stats = _bn_forward(raw, bn_w, bn_b, rm, rv, training, momentum, eps)
-        y, y2 = ops.bn_act_fwd(raw, stats[2], stats[3], True, res_post=res_post, T=T, V=V, want_perm=want_perm)
+        y, y2 = ops.bn_act_fwd(raw, stats[2], stats[3], True, res_post=res_post, T=T, V=V, want_perm=want_perm,
+                               out_dtype=act_dtype())
         ctx.save_for_backward(x, raw, stats, conv_w, conv_b, bn_w, bn_b)
         ctx.cfg = (N, T, V, training, res_post is not None, want_perm)
         if want_perm:
@@ -537,11 +567,12 @@ _gcn0_ws = {}
 
 
 def _gcn0_workspace(device):
-    """Persistent zero-initialised (moments fp64 [32, 96], CTA ticket) pair per device; the kernel re-arms it."""
+    """Persistent zero-initialised (moments fp64 [3, 32, 96], int32[8] ticket / barrier words) pair per device; the
+    kernels re-arm it ([0] / word 0: two-kernel path; [1:3] / words 4..6: fused kernel's ping-pong halves and barrier)."""
     key = (device.type, device.index)
     if key not in _gcn0_ws:
-        _gcn0_ws[key] = (torch.zeros((_lib.GCN0_SLOTS, _lib.GCN0_NMOM), device=device, dtype=torch.float64),
-                         torch.zeros(1, device=device, dtype=torch.int32))
+        _gcn0_ws[key] = (torch.zeros((3 * _lib.GCN0_SLOTS, _lib.GCN0_NMOM), device=device, dtype=torch.float64),
+                         torch.zeros(8, device=device, dtype=torch.int32))
     return _gcn0_ws[key]
 
 
@@ -594,11 +625,13 @@ class Gcn0Fn(torch.autograd.Function):
         mma_ws = None
         if y.dtype == torch.bfloat16 and Cout == 128 and V <= 48:   # operands of the tensor-core apply pass
             VP = 16 if V <= 16 else (32 if V <= 32 else 48)
-            mma_ws = (torch.empty((N, 3, VP, VP + 8), device=dev, dtype=torch.bfloat16),
+            mma_ws = (torch.empty(int(_lib.lib().afb_gcn0_aop_bytes(N, V)) // 2, device=dev, dtype=torch.bfloat16),
                       torch.empty((N, 3, VP), device=dev, dtype=torch.float32),
                       torch.empty((Cout // 8, 32, 2), device=dev, dtype=torch.int32))
         st = _gcn0_struct(x, A, PA.detach(), mods, bufs, training, momentum, eps, Mmat, moments, stats, wfold, y, mma_ws)
         ops._call("afb_gcn0_fwd", C.byref(st), ops.stream())
+        if mma_ws is not None and V % 2 == 0 and V <= 24 and os.environ.get("AFB_GCN0_FUSED", "1")[0] != "0":
+            ops.LAUNCHES[0] -= 1   # the fused cooperative kernel is one launch (the two-kernel path counts 2)
         ctx.save_for_backward(x, A, PA, Mmat, stats, wfold, y, *params, *bufs)
         ctx.cfg = (training, momentum, eps)
         return y

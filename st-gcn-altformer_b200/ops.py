@@ -256,14 +256,17 @@ def bn_finalize(acc, M, gamma, beta, running_mean, running_var, momentum, eps, t
     return out
 
 
-def bn_act_fwd(x, scale, shift, relu, res_pre=None, res_post=None, T=0, V=0, want=True, want_perm=False):
+def bn_act_fwd(x, scale, shift, relu, res_pre=None, res_post=None, T=0, V=0, want=True, want_perm=False, out_dtype=None):
+    """out_dtype: bf16 outputs from an fp32 pre-activation (the bf16 mode keeps BatchNorm inputs in fp32 so the ReLU
+    mask is decided on unrounded values); default = x.dtype."""
     need_cuda(x, scale, shift, res_pre, res_post)
     M, Cc = x.shape
-    y = torch.empty_like(x) if want else None
-    y2 = torch.empty_like(x) if want_perm else None
+    od = out_dtype or x.dtype
+    y = torch.empty_like(x, dtype=od) if want else None
+    y2 = torch.empty_like(x, dtype=od) if want_perm else None
     res = res_pre if res_pre is not None else res_post
     _call("afb_bn_act_fwd", ptr(x), dt(x), ptr(scale), ptr(shift), ptr(res_pre), ptr(res_post),
-          0 if res is None else dt(res), int(relu), ptr(y), ptr(y2), dt(x), M, Cc, T, V, stream())
+          0 if res is None else dt(res), int(relu), ptr(y), ptr(y2), _DT[od], M, Cc, T, V, stream())
     return y, y2
 
 
@@ -275,11 +278,11 @@ def bn_bwd(dy, dy2, x, stats, gamma, beta, relu, training, dgamma, dbeta, res_pr
     _call("afb_bn_bwd_reduce", ptr(dy), ptr(dy2), dt(g), ptr(x), dt(x), ptr(res_pre),
           0 if res_pre is None else dt(res_pre), ptr(stats[0]), ptr(stats[1]), ptr(gamma), ptr(beta), int(relu),
           ptr(dgamma), ptr(dbeta), M, Cc, T, V, stream())
-    dx = torch.empty_like(x)
-    dres = torch.empty_like(x) if want_dres else None
+    dx = torch.empty_like(x, dtype=g.dtype)      # x may be the fp32 pre-activation of the bf16 mode; gradients follow dy
+    dres = torch.empty_like(x, dtype=g.dtype) if want_dres else None
     _call("afb_bn_bwd_apply", ptr(dy), ptr(dy2), dt(g), ptr(x), dt(x), ptr(res_pre),
           0 if res_pre is None else dt(res_pre), ptr(stats[0]), ptr(stats[1]), ptr(gamma), ptr(beta), ptr(dgamma),
-          ptr(dbeta), int(relu), int(training), ptr(dx), ptr(dres), dt(x), M, Cc, T, V, stream())
+          ptr(dbeta), int(relu), int(training), ptr(dx), ptr(dres), dt(dx), M, Cc, T, V, stream())
     return dx, dres
 
 
