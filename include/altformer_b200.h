@@ -273,7 +273,9 @@ typedef struct {
                           the tensor-core apply pass needs Aop, colsum and Wfrag (V <= 48) */
   void* y;             /* out [N*T*V][Cout] */
   int32_t y_dtype;
-  int32_t precise;     /* 1: fp32 FMA apply (parity mode); 0: bf16 mma.sync apply */
+  int32_t precise;     /* 0: bf16 tensor-core apply (fused kernel when it covers the shape, else mma.sync two-kernel path);
+                          1: fp32 FMA apply (parity mode); 2: exact ReLU masks wanted in bf16 mode -- fused kernel (hi/lo
+                          operands) when it covers the shape, else the fp32 FMA apply with bf16 output */
 } afb_gcn0_fwd_t;
 #define AFB_GCN0_NR 12          /* r = (z_0, z_1, z_2, x): 9 + 3 */
 #define AFB_GCN0_NMOM 96        /* 12 first + 78 second moments (upper triangle), padded */

@@ -272,9 +272,20 @@ def unit2d_forward(x, p, prefix, training=False, stride=1):
     return torch.relu(_bn(y, p, prefix + "bn.", training))
 
 
-def tcn_gcn_forward(x, p, prefix, A, training=False):
+def boundary_bf16(x):
+    """Module-boundary quantiser for checking the bf16 mode: the SAME fp32 reference math, but the activation handed from
+    one conv+BN+ReLU module to the next is the bf16 value the CUDA path stores there (straight-through gradient).  Without
+    it a composite of two such modules cannot be compared tighter than ~4e-2 on gradients: the second module's ReLU masks
+    are decided on inputs that differ by the storage rounding (2^-9), which flips ~1e-3 of them."""
+    return x + (x.detach().bfloat16().to(x.dtype) - x.detach())
+
+
+def tcn_gcn_forward(x, p, prefix, A, training=False, boundary=None):
     """tcn1(gcn1(x)) + x  (C_in == C_out, stride 1).  ST_TR_new.py:376-385."""
-    return unit2d_forward(agcn_forward(x, p, prefix + "gcn1.", A, training), p, prefix + "tcn1.", training) + x
+    h = agcn_forward(x, p, prefix + "gcn1.", A, training)
+    if boundary is not None:
+        h = boundary(h)
+    return unit2d_forward(h, p, prefix + "tcn1.", training) + x
 
 
 def mlp_forward(x, p, prefix):
@@ -351,15 +362,19 @@ def ts_forward(x, p, prefix, heads=8, keeps=None):
     return _head(h.mean(dim=1), p, prefix)
 
 
-def backbone_forward(x, p, A, training=False):
+def backbone_forward(x, p, A, training=False, boundary=None):
     """(N,T,V,3) -> (N,128,T,V): gcn0 then tcn0."""
     x = x.permute(0, 3, 1, 2).contiguous()
-    return unit2d_forward(agcn_forward(x, p, "gcn0.", A, training), p, "tcn0.", training)
+    h = agcn_forward(x, p, "gcn0.", A, training)
+    if boundary is not None:
+        h = boundary(h)
+    return unit2d_forward(h, p, "tcn0.", training)
 
 
-def model_forward(x, p, A, style="ST", training=False, keeps=None):
-    """ST_GCN_AltFormer.forward: x (N,T,V,3) -> (N,cls).  keeps: dict {'A':..., 'B':...} or None."""
-    f = backbone_forward(x, p, A, training)
+def model_forward(x, p, A, style="ST", training=False, keeps=None, boundary=None):
+    """ST_GCN_AltFormer.forward: x (N,T,V,3) -> (N,cls).  keeps: dict {'A':..., 'B':...} or None.
+    boundary: optional module-boundary quantiser (boundary_bf16) applied to the gcn0 output."""
+    f = backbone_forward(x, p, A, training, boundary)
     ka = None if keeps is None else keeps.get("A")
     kb = None if keeps is None else keeps.get("B")
     if style == "ST":

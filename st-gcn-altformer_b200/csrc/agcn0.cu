@@ -1133,7 +1133,8 @@ extern "C" int afb_gcn0_fwd(const afb_gcn0_fwd_t* p, afb_stream s) {
   const int TT = pick_tt(T, V), chunks = ceil_div(T, TT);
   const int P16 = (TT * V + 15) / 16 * 16;
   const size_t head = ((size_t)a4(3 * V * V) + a4(TT * V * 3) + 16) * sizeof(float);
-  const bool mma = !p->precise && p->y_dtype == AFB_BF16 && p->Cout == 128;
+  const bool mma = p->precise == 0 && p->y_dtype == AFB_BF16 && p->Cout == 128;   // precise 2 (exact ReLU masks) on a shape the fused kernel
+                                                                                 // does not cover: fp32 FMA apply, bf16 output
   static const bool old_apply = getenv("AFB_GCN0_APPLY_V1") != nullptr;
   if (mma && !old_apply && V <= 48 && p->Aop != nullptr && p->colsum != nullptr && p->Wfrag != nullptr) {
     const int TT2 = T < 8 ? T : 8, chunks2 = ceil_div(T, TT2);   // one frame per warp; 2 CTAs per SM overlap each other's setup

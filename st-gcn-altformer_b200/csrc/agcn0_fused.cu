@@ -997,7 +997,7 @@ int launch_fused(const afb_gcn0_fwd_t* p, cudaStream_t st) {
 // 0: launched; -1: shape not covered (caller falls back to the two-kernel path); > 0: error (message set)
 int gcn0_fused_launch(const afb_gcn0_fwd_t* p, cudaStream_t st) {
   static const bool off = getenv("AFB_GCN0_FUSED") != nullptr && getenv("AFB_GCN0_FUSED")[0] == '0';
-  if (off || p->precise || p->y_dtype != AFB_BF16 || p->Cout != COUT || p->Aop == nullptr) return -1;
+  if (off || p->precise == 1 || p->y_dtype != AFB_BF16 || p->Cout != COUT || p->Aop == nullptr) return -1;
   if (p->V < 2 || (p->V & 1) || p->V > 24 || p->IC <= 0 || p->IC > 36) return -1;
   if (((uintptr_t)p->y & 15) != 0 || ((uintptr_t)p->x & 7) != 0) return -1;
   const int cbt = (p->V + 7) / 8;

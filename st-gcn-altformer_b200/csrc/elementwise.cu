@@ -808,10 +808,18 @@ extern "C" int afb_bn_act_fwd(const void* x, int xd, const float* scale, const f
                               afb_stream s) {
   AFB_REQUIRE(x && scale && shift && (y || y2) && M > 0 && C % 4 == 0, "bn_act_fwd: bad args");
   // one dtype for everything, or the "exact mask" layout of the bf16 mode: fp32 pre-activation x, bf16 residual / outputs
-  const bool mixed = xd == AFB_F32 && yd == AFB_BF16;
-  AFB_REQUIRE((xd == yd || mixed) && ((!res_pre && !res_post) || rd == yd), "bn_act_fwd: unsupported dtype combination");
+  // (mixed2: the residual is itself an fp32 BatchNorm output -- unit_agcn's `down` branch -- and must reach the mask unrounded)
+  const bool has_res = res_pre || res_post;
+  const bool mixed2 = xd == AFB_F32 && yd == AFB_BF16 && has_res && rd == AFB_F32;
+  const bool mixed = xd == AFB_F32 && yd == AFB_BF16 && !mixed2;
+  AFB_REQUIRE((xd == yd || mixed || mixed2) && (!has_res || rd == yd || mixed2), "bn_act_fwd: unsupported dtype combination");
   AFB_REQUIRE(y2 == nullptr || (T > 0 && V > 0 && M % ((int64_t)T * V) == 0), "bn_act_fwd: permuted copy needs T,V");
   const int grid = grid_for(M * (C / 4), kBlock);
+  if (mixed2) {
+    bn_act_fwd_kernel<float, float, bf16><<<grid, kBlock, 0, as_stream(s)>>>((const float*)x, scale, shift, (const float*)res_pre,
+                                                                             (const float*)res_post, relu, (bf16*)y, (bf16*)y2, M, C, T, V);
+    return check_launch("bn_act_fwd");
+  }
   if (mixed) {
     bn_act_fwd_kernel<float, bf16, bf16><<<grid, kBlock, 0, as_stream(s)>>>((const float*)x, scale, shift, (const bf16*)res_pre,
                                                                             (const bf16*)res_post, relu, (bf16*)y, (bf16*)y2, M, C, T, V);
@@ -827,9 +835,15 @@ extern "C" int afb_bn_bwd_reduce(const void* dy, const void* dy2, int gd, const 
                                  float* dgamma, float* dbeta, int64_t M, int C, int T, int V, afb_stream s) {
   AFB_REQUIRE((dy || dy2) && x && mean && rstd && gamma && beta && dgamma && dbeta && M > 0, "bn_bwd_reduce: bad args");
   AFB_REQUIRE(col_shape_ok(C), "bn_bwd_reduce: C=%d unsupported", C);
-  const bool mixed = xd == AFB_F32 && gd == AFB_BF16;
-  AFB_REQUIRE((gd == xd || mixed) && (res_pre == nullptr || rd == gd), "bn_bwd_reduce: unsupported dtype combination");
+  const bool mixed2 = xd == AFB_F32 && gd == AFB_BF16 && res_pre != nullptr && rd == AFB_F32;
+  const bool mixed = xd == AFB_F32 && gd == AFB_BF16 && !mixed2;
+  AFB_REQUIRE((gd == xd || mixed || mixed2) && (res_pre == nullptr || rd == gd || mixed2), "bn_bwd_reduce: unsupported dtype combination");
   AFB_REQUIRE(dy2 == nullptr || (T > 0 && V > 0 && M % ((int64_t)T * V) == 0), "bn_bwd_reduce: permuted grad needs T,V");
+  if (mixed2) {
+    bn_bwd_reduce_kernel<bf16, float, float><<<col_grid(M, C), kBlock, 0, as_stream(s)>>>(
+        (const bf16*)dy, (const bf16*)dy2, (const float*)x, (const float*)res_pre, mean, rstd, gamma, beta, relu, dgamma, dbeta, M, C, T, V);
+    return check_launch("bn_bwd_reduce");
+  }
   if (mixed) {
     bn_bwd_reduce_kernel<bf16, float, bf16><<<col_grid(M, C), kBlock, 0, as_stream(s)>>>(
         (const bf16*)dy, (const bf16*)dy2, (const float*)x, (const bf16*)res_pre, mean, rstd, gamma, beta, relu, dgamma, dbeta, M, C, T, V);
@@ -847,9 +861,17 @@ extern "C" int afb_bn_bwd_apply(const void* dy, const void* dy2, int gd, const v
                                 int V, afb_stream s) {
   AFB_REQUIRE((dy || dy2) && x && mean && rstd && gamma && beta && dgamma && dbeta && dx && M > 0 && C % 4 == 0,
               "bn_bwd_apply: bad args");
-  const bool mixed = xd == AFB_F32 && gd == AFB_BF16;
-  AFB_REQUIRE((gd == xd || mixed) && od == gd && (res_pre == nullptr || rd == gd), "bn_bwd_apply: unsupported dtype combination");
+  const bool mixed2 = xd == AFB_F32 && gd == AFB_BF16 && res_pre != nullptr && rd == AFB_F32;
+  const bool mixed = xd == AFB_F32 && gd == AFB_BF16 && !mixed2;
+  AFB_REQUIRE((gd == xd || mixed || mixed2) && od == gd && (res_pre == nullptr || rd == gd || mixed2),
+              "bn_bwd_apply: unsupported dtype combination");
   const int grid = grid_for(M * (C / 4), kBlock);
+  if (mixed2) {
+    bn_bwd_apply_kernel<bf16, float, float, bf16><<<grid, kBlock, 0, as_stream(s)>>>(
+        (const bf16*)dy, (const bf16*)dy2, (const float*)x, (const float*)res_pre, mean, rstd, gamma, beta, dgamma, dbeta, relu, training,
+        (bf16*)dx, (bf16*)dres, M, C, T, V);
+    return check_launch("bn_bwd_apply");
+  }
   if (mixed) {
     bn_bwd_apply_kernel<bf16, float, bf16, bf16><<<grid, kBlock, 0, as_stream(s)>>>(
         (const bf16*)dy, (const bf16*)dy2, (const float*)x, (const bf16*)res_pre, mean, rstd, gamma, beta, dgamma, dbeta, relu, training,

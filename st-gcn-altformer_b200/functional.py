@@ -83,6 +83,12 @@ def lowp(p):
     """bf16 copy of a parameter (the trainer installs a persistent shadow as p._afb_shadow)."""
     sh = getattr(p, "_afb_shadow", None)
     if sh is not None:
+        # AdamW refreshes the shadow through raw pointers (no version bump); any other in-place edit of the parameter
+        # (load_state_dict, manual init) bumps p._version and the shadow is re-cast here before it is used
+        if getattr(p, "_afb_shadow_ver", None) != p._version:
+            with torch.no_grad():
+                ops.cast(p.detach(), torch.bfloat16, out=sh)
+            p._afb_shadow_ver = p._version
         return sh
     return _derived(p, "bf16", lambda w: ops.cast(w.contiguous(), torch.bfloat16))
 
@@ -95,6 +101,11 @@ def w_fwd(p):
     """B operand of y = x W^T: [N, K] bf16, or the (hi|hi|lo) split [N, 3K] in fp32 mode."""
     if _PRECISION[0] == "bf16":
         return lowp(p).reshape(p.shape[0], -1)
+    return _derived(p, "split_b", lambda w: ops.split3(w.reshape(w.shape[0], -1).contiguous(), 1))
+
+
+def w_fwd3(p):
+    """(hi|hi|lo) split [N, 3K] of a weight regardless of the precision mode (exact-mask forward of the bf16 mode)."""
     return _derived(p, "split_b", lambda w: ops.split3(w.reshape(w.shape[0], -1).contiguous(), 1))
 
 
@@ -590,7 +601,7 @@ def _gcn0_struct(x, A, PA, mods, bufs, training, momentum, eps, Mmat, moments, s
                         IC=IC, training=int(training), momentum=momentum, eps=eps, Mmat=Mmat.data_ptr(),
                         moments=moments.data_ptr(), counter=counter.data_ptr(), stats=stats.data_ptr(), Wfold=wfold.data_ptr(), Aop=ops.ptr(aop), colsum=ops.ptr(colsum),
                         Wfrag=ops.ptr(wfrag), y=y.data_ptr(),
-                        y_dtype=ops.dt(y), precise=int(get_precision() == "fp32"))
+                        y_dtype=ops.dt(y), precise=1 if get_precision() == "fp32" else (2 if exact_bn_mask() else 0))
 
 
 class Gcn0Fn(torch.autograd.Function):
@@ -681,7 +692,7 @@ def _agcn_stacked(wa, ba, wb, bb, wd, bd):
        Wab  fp32 [ldt, C]  rows (a0,a1,a2,b0,b1,b2, zero pad), bab fp32 [ldt]
        Wdc  fp32 [Cout, 3C] (Wd_0 | Wd_1 | Wd_2),             bdc fp32 [Cout] = sum_i bd_i."""
     members = (*wa, *ba, *wb, *bb, *wd, *bd)
-    ver = tuple((m._version, m.data_ptr()) for m in members) + (_EPOCH[0],)
+    ver = tuple((m._version, m.data_ptr()) for m in members) + (_EPOCH[0], _PRECISION[0], exact_bn_mask())
     slot = _slot(wa[0])
     ent = slot.get("agcn_stack")
     if ent is not None and ent[0] == ver:
@@ -701,14 +712,17 @@ def _agcn_stacked(wa, ba, wb, bb, wd, bd):
             ops.copy2d(bb[i].detach(), bab, 1, IC, IC, IC, dst_off=(3 + i) * IC)
             ops.copy2d(wd[i].detach(), Wdc, Cout, Cin, Cin, 3 * Cin, dst_off=i * Cin)
         bdc = ops.axpby(ops.axpby(bd[0].detach(), 1.0, bd[1].detach(), 1.0), 1.0, bd[2].detach(), 1.0)
+        ab_f3 = dc_f3 = None
         if _PRECISION[0] == "bf16":
             ab_f, dc_f = ops.cast(Wab, torch.bfloat16), ops.cast(Wdc, torch.bfloat16)
             ab_x, dc_x = ab_f, dc_f
+            if exact_bn_mask():   # forward operands of the exact-mask forward (hi|hi|lo)
+                ab_f3, dc_f3 = ops.split3(Wab, 1), ops.split3(Wdc, 1)
         else:
             ab_f, dc_f = ops.split3(Wab, 1), ops.split3(Wdc, 1)
             ab_x = ops.split3(Wab, 2).view(3 * ldt, Cin)
             dc_x = ops.split3(Wdc, 2).view(3 * Cout, 3 * Cin)
-        out = dict(ldt=ldt, bab=bab, bdc=bdc, ab_f=ab_f, dc_f=dc_f, ab_x=ab_x, dc_x=dc_x)
+        out = dict(ldt=ldt, bab=bab, bdc=bdc, ab_f=ab_f, dc_f=dc_f, ab_x=ab_x, dc_x=dc_x, ab_f3=ab_f3, dc_f3=dc_f3)
     slot["agcn_stack"] = (ver, out)
     return out
 
@@ -756,26 +770,47 @@ class AgcnFn(torch.autograd.Function):
         Cout, IC = wd[0].shape[0], wa[0].shape[0]
         st = _agcn_stacked(wa, ba, wb, bb, wd, bd)
         ldt = st["ldt"]
-        thph = _gemm_raw(x, st["ab_f"], ldt, bias=st["bab"])
+        exact = exact_bn_mask()
+        # exact (bf16 mode): every value that decides a ReLU mask -- theta/phi -> M -> z -> conv_d, down -- is formed at
+        # fp32 accuracy from the bf16 input (hi/lo split GEMMs, fp32 intermediates); only y and the tensors kept for the
+        # backward GEMMs are bf16.  Rounding any of them to bf16 first moves the pre-activation by ~2^-9 of its typical
+        # size, flips ~1e-3 of the masks and costs 3-5e-2 of gradient error against the fp32 reference.
         P = torch.empty((N, 3, V, V), device=x.device, dtype=torch.float32)
         Mmat = torch.empty_like(P)
-        ops._call("afb_agcn_scores_fwd", ops.ptr(thph), ops.dt(thph), ldt, ops.ptr(A), ops.ptr(PA.detach()), ops.ptr(P),
-                  ops.ptr(Mmat), N, T, V, IC, ops.stream())
-        z = torch.empty((M, 3 * Cin), device=x.device, dtype=x.dtype)
-        ops._call("afb_agcn_aggregate_fwd", ops.ptr(x), ops.ptr(Mmat), ops.ptr(z), ops.dt(x), N, T, V, Cin, ops.stream())
-        h_raw = _gemm_raw(z, st["dc_f"], Cout, bias=st["bdc"])
+        if exact:
+            x32 = ops.cast(x, torch.float32)
+            xs = ops.split3(x32, 0)
+            thph32 = ops.gemm_tn(xs, st["ab_f3"], ldt, bias=st["bab"], out_dtype=torch.float32)
+            ops._call("afb_agcn_scores_fwd", ops.ptr(thph32), ops.dt(thph32), ldt, ops.ptr(A), ops.ptr(PA.detach()), ops.ptr(P),
+                      ops.ptr(Mmat), N, T, V, IC, ops.stream())
+            thph = ops.cast(thph32, torch.bfloat16)
+            z32 = torch.empty((M, 3 * Cin), device=x.device, dtype=torch.float32)
+            ops._call("afb_agcn_aggregate_fwd", ops.ptr(x32), ops.ptr(Mmat), ops.ptr(z32), ops.dt(x32), N, T, V, Cin, ops.stream())
+            h_raw = ops.gemm_tn(ops.split3(z32, 0), st["dc_f3"], Cout, bias=st["bdc"], out_dtype=torch.float32)
+            z = ops.cast(z32, torch.bfloat16)
+            del thph32, z32
+        else:
+            thph = _gemm_raw(x, st["ab_f"], ldt, bias=st["bab"])
+            ops._call("afb_agcn_scores_fwd", ops.ptr(thph), ops.dt(thph), ldt, ops.ptr(A), ops.ptr(PA.detach()), ops.ptr(P),
+                      ops.ptr(Mmat), N, T, V, IC, ops.stream())
+            z = torch.empty((M, 3 * Cin), device=x.device, dtype=x.dtype)
+            ops._call("afb_agcn_aggregate_fwd", ops.ptr(x), ops.ptr(Mmat), ops.ptr(z), ops.dt(x), N, T, V, Cin, ops.stream())
+            h_raw = _gemm_raw(z, st["dc_f"], Cout, bias=st["bdc"])
         stats_h = _bn_forward(h_raw, bng, bnb, bufs[0], bufs[1], training, momentum, eps)
         if has_down:
             wdn, bdn, dng, dnb = params[20:24]
-            d_raw = mm_fwd(x, wdn, bias=bdn.detach())
+            if exact:
+                d_raw = ops.gemm_tn(xs, w_fwd3(wdn), Cout, bias=bdn.detach(), out_dtype=torch.float32)
+            else:
+                d_raw = mm_fwd(x, wdn, bias=bdn.detach())
             stats_d = _bn_forward(d_raw, dng, dnb, bufs[2], bufs[3], training, momentum, eps)
-            res, _ = ops.bn_act_fwd(d_raw, stats_d[2], stats_d[3], False)
+            res, _ = ops.bn_act_fwd(d_raw, stats_d[2], stats_d[3], False)     # same dtype as d_raw (fp32 when exact)
         else:
             if Cin != Cout:
                 raise RuntimeError("unit_agcn without `down` needs in_channels == out_channels")
             d_raw = stats_d = None
             res = x
-        y, _ = ops.bn_act_fwd(h_raw, stats_h[2], stats_h[3], True, res_pre=res)
+        y, _ = ops.bn_act_fwd(h_raw, stats_h[2], stats_h[3], True, res_pre=res, out_dtype=act_dtype())
         ctx.save_for_backward(x, A, thph, P, Mmat, z, h_raw, stats_h, d_raw, stats_d, res if has_down else None, PA, *params)
         ctx.cfg = (N, T, V, training, has_down, len(bufs))
         return y

@@ -364,8 +364,9 @@ def motion_stream(x):
     return y
 
 
-def axpby(a, wa, b, wb):
+def axpby(a, wa, b, wb, out=None):
     need_cuda(a, b)
-    out = torch.empty_like(a)
+    if out is None:
+        out = torch.empty_like(a)
     _call("afb_axpby", ptr(a), wa, ptr(b), wb, ptr(out), a.numel(), stream())
     return out

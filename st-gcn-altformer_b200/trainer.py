@@ -52,7 +52,11 @@ class FlatBuffers:
 
 class GradReducer:
     """Mean all-reduce of the flat gradient buffer.  With backend nccl this is one collective over
-    NVLink/NVSwitch; the division by world size is folded into the optimizer kernel (grad_scale)."""
+    NVLink/NVSwitch; the division by world size is folded into the optimizer kernel (grad_scale).
+
+    Every rank's gradient is the gradient of ITS shard's mean loss.  The reference's DataParallel loss is the mean over
+    the global batch (train_sttran.py:161,189), so with shards of unequal size rank r's gradient carries the weight
+    local_n_r / global_n instead of 1 / world: `shard_weight` returns the factor to apply before the SUM."""
 
     def __init__(self, group=None):
         self.group = group
@@ -62,10 +66,23 @@ class GradReducer:
     def grad_scale(self):
         return 1.0 / self.world
 
+    def shard_weight(self, local_n, global_n):
+        """Pre-reduction factor f with  f * grad_scale == local_n / global_n  (1.0 for equal shards)."""
+        if global_n is None or local_n * self.world == global_n:
+            return 1.0
+        return float(local_n) * self.world / float(global_n)
+
     def reduce(self, flat_grad):
         if self.world > 1:
             dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         return flat_grad
+
+    def broadcast(self, tensors, src=0):
+        """Rank `src`'s values everywhere (parameters and BatchNorm buffers at construction: DataParallel replicates
+        module 0 every forward, train_sttran.py:84; here it happens once)."""
+        if self.world > 1:
+            for t in tensors:
+                dist.broadcast(t, src=src, group=self.group)
 
 
 class DataParallelTrainer:
@@ -92,12 +109,30 @@ class DataParallelTrainer:
                 p._afb_shadow = self.layout.view(self.flat_lowp, name)
                 p.grad = p._afb_grad
                 self.params.append(p)
-            ops.cast(self.flat_p, torch.bfloat16, out=self.flat_lowp)
         self.reducer = GradReducer(group)
+        # ranks start from rank 0's weights and BatchNorm buffers (a model built per rank without a shared seed or
+        # checkpoint would otherwise train diverging replicas: only gradients are exchanged afterwards)
+        self.reducer.broadcast([self.flat_p] + [b for b in model.buffers() if b.is_cuda])
+        self.sync_shadow()
         self.use_graph = use_graph
         self._graph = None
         self._static = None
         self.launches_per_step = None
+
+    @torch.no_grad()
+    def sync_shadow(self):
+        """Re-cast the fp32 master weights into the bf16 GEMM operands.  Called at construction; call it (or rely on the
+        per-parameter version check in functional.lowp) after editing parameters outside AdamW, e.g. load_state_dict."""
+        ops.cast(self.flat_p, torch.bfloat16, out=self.flat_lowp)
+        for p in self.params:
+            p._afb_shadow_ver = p._version
+        AF.bump_weights_epoch()
+
+    def load_state_dict(self, state, strict=True):
+        """model.load_state_dict + shadow refresh (the parameters live in the flat buffer: copy_ lands there)."""
+        out = self.model.load_state_dict(state, strict=strict)
+        self.sync_shadow()
+        return out
 
     # -- one training step -------------------------------------------------------------------
     def _fwd_bwd(self, x, labels):
@@ -107,41 +142,57 @@ class DataParallelTrainer:
         loss.backward()
         return loss.detach(), logits.detach()
 
-    def _optimize(self):
+    def _optimize(self, shard_weight=1.0):
+        if shard_weight != 1.0:
+            ops.axpby(self.flat_g, shard_weight, self.flat_g, 0.0, out=self.flat_g)
         self.reducer.reduce(self.flat_g)
         h = self.hp
         ops.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_lowp, self.step_count, h["lr"], h["b1"],
                   h["b2"], h["eps"], h["wd"], self.reducer.grad_scale)
         AF.bump_weights_epoch()
 
-    def step(self, x, labels):
+    def step(self, x, labels, global_batch=None):
         """x (n, T, V, 3) float32 and labels (n,) int64 of THIS rank's shard: tensors on the trainer's device, or
         (pinned) host tensors, which are copied asynchronously straight into the step's input buffers.
-        Returns (loss, logits) as device tensors (no host sync)."""
+        `global_batch`: total samples over all ranks; needed only when shards are unequal (shard_range allows it) so the
+        reduced gradient is the global-batch mean.  Returns (loss, logits) as device tensors (no host sync); with
+        use_graph they are the graph's static buffers, valid until the next step() — clone to keep them."""
         self.model.train()
+        sw = self.reducer.shard_weight(x.shape[0], global_batch)
         if not self.use_graph:
             if not x.is_cuda:
                 x, labels = x.to(self.device, non_blocking=True), labels.to(self.device, non_blocking=True)
             out = self._fwd_bwd(x, labels)
-            self._optimize()
+            self._optimize(sw)
             return out
         if self._graph is None:
             self._capture(x, labels)
         sx, sy, sloss, slogits = self._static
+        if tuple(x.shape) != tuple(sx.shape):
+            raise RuntimeError(f"captured step has batch shape {tuple(sx.shape)}, got {tuple(x.shape)} (use_graph needs a fixed shape)")
         sx.copy_(x, non_blocking=True)
         sy.copy_(labels, non_blocking=True)
         self._graph.replay()
-        self._optimize()
+        self._optimize(sw)
         return sloss, slogits
 
     def _capture(self, x, labels):
         sx, sy = x.to(self.device, copy=True), labels.to(self.device, copy=True)
+        # the warm-up passes must leave no trace: BatchNorm running statistics / num_batches_tracked and the RNG stream
+        # (DropPath masks) are restored, so step 1 under a graph equals step 1 without one
+        bufs = [b for b in self.model.buffers()]
+        saved = [b.detach().clone() for b in bufs]
+        rng = torch.cuda.get_rng_state(self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):            # warm-up outside capture (lazy inits, smem attributes, caches)
             for _ in range(2):
                 self._fwd_bwd(sx, sy)
         torch.cuda.current_stream().wait_stream(side)
+        with torch.no_grad():
+            for b, s0 in zip(bufs, saved):
+                b.copy_(s0)
+        torch.cuda.set_rng_state(rng, self.device)
         AF.bump_weights_epoch()                   # force derived-weight kernels to be part of the graph
         self._graph = torch.cuda.CUDAGraph()
         ops.LAUNCHES[0] = 0

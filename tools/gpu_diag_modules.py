@@ -25,6 +25,10 @@ from altformer_b200 import functional as AF
 from oracle import altformer_oracle as O
 
 
+import os
+VERBOSE = bool(os.environ.get("AFB_DIAG_VERBOSE"))
+
+
 def is_zero_class(name, training=True):
     if not name.endswith(".bias"):
         return False
@@ -63,6 +67,8 @@ def grad_report(tag, mod, ref_params, tol, abs_rel=None, training=True, worst_to
             continue
         e_inf, e_l2 = rel(got, rg)
         errs.append(e_l2)
+        if VERBOSE:
+            print(f"       . {k:44s} rel_l2={e_l2:.3e} rel_inf={e_inf:.3e} |ref|={float(rg.norm()):.3e}", flush=True)
         if e_l2 != e_l2:
             fails.append(f"{k}: NaN")
         elif worst_tol is None and ((e_inf > tol and not l2_only) or e_l2 > tol):
@@ -108,7 +114,7 @@ def _tols(mode, bn):
     """(forward tol, dx tol, param-grad tol)"""
     if mode == "fp32":
         return 1e-4, 5e-4, 5e-4
-    return (1e-2, 1e-1, 1e-1) if bn else (1.5e-2, 3e-2, 3e-2)
+    return 1e-2, 1e-2, 1e-2     # north_star: bf16 <= 1e-2 for outputs AND gradients, per module on identical inputs
 
 
 # --------------------------------------------------------------------------------------------
@@ -117,7 +123,7 @@ def grp_gcn0():
         with precision(mode):
             ftol, _, gtol = _tols(mode, True)
             tiny = N * T * V < 2000   # tiny batches: BN statistics over < 2000 positions amplify rounding (and single
-            if tiny:                  # near-zero gradient entries dominate rel_inf): 2x tolerance, judged on rel-L2
+            if tiny and mode == "fp32":   # near-zero gradient entries dominate rel_inf): 2x tolerance, judged on rel-L2
                 gtol *= 2
             A = O.spatial_graph(V)
             st = O.random_state(O.agcn_spec("", 3, 128, V), seed)
@@ -247,15 +253,18 @@ def grp_modules():
             st = O.random_state(spec, 31)
             x = torch.randn(N, Cc, T, V, generator=torch.Generator().manual_seed(131))
             x = r16(x) if mode == "bf16" else x
-            yr, dxr, params, cot = oracle_run(lambda x_, p: O.tcn_gcn_forward(x_, p, "", A, True), st, x, True, mode == "bf16")
+            # bf16 mode: the activation between gcn1 and tcn1 is a bf16 tensor by contract; the oracle quantises it the same
+            # way (O.boundary_bf16), everything else stays the fp32 reference math
+            bnd = O.boundary_bf16 if mode == "bf16" else None
+            yr, dxr, params, cot = oracle_run(lambda x_, p: O.tcn_gcn_forward(x_, p, "", A, True, bnd), st, x, True, mode == "bf16")
             mod = ab.TCN_GCN_unit(Cc, Cc, A, dropout=0.0).to(DEV)
             mod.load_state_dict(st)
             xg = x.to(DEV).requires_grad_(True)
             y = mod(xg)
-            report(f"TCN_GCN_unit {mode} fwd", y.float(), yr, 2 * ftol)
+            report(f"TCN_GCN_unit {mode} fwd", y.float(), yr, ftol)
             (y.float() * cot.to(DEV)).sum().backward()
-            (report_l2 if mode == "bf16" else report)(f"TCN_GCN_unit {mode} dx", xg.grad, dxr, 1.5 * xtol)
-            grad_report(f"TCN_GCN_unit {mode}", mod, params, 1.5 * gtol, l2_only=mode == "bf16")
+            (report_l2 if mode == "bf16" else report)(f"TCN_GCN_unit {mode} dx", xg.grad, dxr, xtol)
+            grad_report(f"TCN_GCN_unit {mode}", mod, params, gtol, l2_only=mode == "bf16")
     check(lambda: tcn_gcn_case("fp32"))
     check(lambda: tcn_gcn_case("bf16"))
 
