@@ -90,3 +90,30 @@ def set_identity_droppath(module):
         else:
             set_identity_droppath(child)
     return module
+
+
+class _CpuReference(torch.nn.Module):
+    """The unmodified reference ST_GCN_AltFormer running on CPU tensors (Tensor.cuda patched to identity per call)."""
+
+    def __init__(self, mod):
+        super().__init__()
+        self.mod = mod
+
+    def forward(self, x):
+        with cpu_cuda_noop():
+            return self.mod(x)
+
+
+def build_model(state, num_class, T, V, style, graph, train=True):
+    """Reference ST_GCN_AltFormer (model/AltFormer/ST_GCN_AltFormer.py:16-87) with `state` loaded, adjacency de-aliased
+    (SURVEY 8c shim 2) and DropPath as constructed (drop_path_rate 0.1: the reference's own training behaviour).  Used by
+    bench.py's CPU arm when the reference tree is present, so that arm times the reference's modules, not the port."""
+    ref = load()
+    mod = ref.ST_GCN_AltFormer(channel=3, num_class=num_class, num_frame=T, num_joints=V, style=style, graph=graph,
+                               graph_args={"labeling_mode": "spatial"})
+    A = torch.from_numpy((ref.graph.SHRE if V == 22 else ref.graph.LMDHG)("spatial").A).float()
+    mod.gcn0.A = A.clone()
+    missing, unexpected = mod.load_state_dict(state, strict=False)
+    if unexpected or any(not k.startswith(("modelA.", "modelB.")) for k in missing):
+        raise RuntimeError(f"reference state_dict mismatch: missing {missing[:4]}, unexpected {unexpected[:4]}")
+    return _CpuReference(mod).train(train)
