@@ -686,8 +686,7 @@ def run_stack(env, cfg, args):
     from altformer_b200 import ops
     dev, V, layers = env.dev, cfg["V"], 4
     NB = (args.batch or cfg["per_gpu_batch"]) // env.world
-    A = ab.graph.SHRE(labeling_mode="spatial").A if hasattr(ab, "graph") else None
-    A = torch.as_tensor(A, dtype=torch.float32)
+    A = torch.as_tensor(ab.import_class(cfg["graph"])(labeling_mode="spatial").A, dtype=torch.float32)
     sweep = []
     Cs = [int(c) for c in args.stack_c.split(",")]
     Ts = [int(t) for t in args.stack_t.split(",")]

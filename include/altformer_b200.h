@@ -325,6 +325,8 @@ int afb_agcn_scores_bwd(const void* thph, int ld, const float* P, const float* d
  * ------------------------------------------------------------------------------------------ */
 int afb_bone_stream(const float* x, const int32_t* parent, float* y, int64_t NT, int V, afb_stream s);
 int afb_motion_stream(const float* x, float* y, int N, int T, int V, afb_stream s);
+/* y = x - x[:, 0, joint, :] per sequence: palm-centre normalisation (data_process/Hand_Dataset.py:61, joint = 1); out of place */
+int afb_palm_center(const float* x, float* y, int N, int T, int V, int joint, afb_stream s);
 int afb_axpby(const float* a, float wa, const float* b, float wb, float* out, int64_t n, afb_stream s);
 
 #ifdef __cplusplus

@@ -951,6 +951,21 @@ extern "C" int afb_motion_stream(const float* x, float* y, int N, int T, int V, 
   motion_kernel<<<grid_for((int64_t)N * T * V * 3, kBlock), kBlock, 0, as_stream(s)>>>(x, y, N, T, V);
   return check_launch("motion_stream");
 }
+// palm-centre normalisation (Hand_Dataset.py:61): every joint of every frame minus joint 1 of frame 0 of its sequence
+__global__ void __launch_bounds__(kBlock) palm_center_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total,
+                                                             int64_t per_seq, int joint) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / per_seq;
+    const int c = (int)(i % 3);
+    y[i] = x[i] - __ldg(x + n * per_seq + joint * 3 + c);
+  }
+}
+extern "C" int afb_palm_center(const float* x, float* y, int N, int T, int V, int joint, afb_stream s) {
+  AFB_REQUIRE(x && y && x != y && N > 0 && T > 0 && joint >= 0 && joint < V, "palm_center: bad args (out of place only)");
+  const int64_t per_seq = (int64_t)T * V * 3;
+  palm_center_kernel<<<grid_for(N * per_seq, kBlock), kBlock, 0, as_stream(s)>>>(x, y, N * per_seq, per_seq, joint);
+  return check_launch("palm_center");
+}
 extern "C" int afb_axpby(const float* a, float wa, const float* b, float wb, float* out, int64_t n, afb_stream s) {
   AFB_REQUIRE(a && b && out && n > 0, "axpby: bad args");
   axpby_kernel<<<grid_for(n, kBlock), kBlock, 0, as_stream(s)>>>(a, wa, b, wb, out, n);

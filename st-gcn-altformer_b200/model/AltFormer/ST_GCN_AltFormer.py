@@ -72,11 +72,21 @@ class ST_GCN_AltFormer(nn.Module):
         x_ts = self.modelB.forward_tokens_nvt(tok_nvt, dims)
         return AddFn.apply(x_ts, x_st)
 
-    def load_state_dict(self, state_dict, strict=True, **kw):
-        """Accepts the reference's DataParallel checkpoints (keys prefixed with 'module.', emsemble.py:99-104)."""
-        if any(k.startswith("module.") for k in state_dict):
+    def load_state_dict(self, state_dict, strict=True, reference_adjacency=None, **kw):
+        """Accepts the reference's DataParallel checkpoints (keys prefixed with 'module.', emsemble.py:99-104).
+        reference_adjacency: None (default) = switch gcn0 to the reference's effective adjacency (A == 1e-6, see
+        unit_agcn.use_reference_adjacency) exactly when the keys carry the 'module.' prefix -- i.e. the file was written
+        by the reference's training scripts; True / False force it."""
+        prefixed = any(k.startswith("module.") for k in state_dict)
+        if prefixed:
             state_dict = {k[len("module."):] if k.startswith("module.") else k: v for k, v in state_dict.items()}
-        return super().load_state_dict(state_dict, strict=strict, **kw)
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        if reference_adjacency is None:
+            reference_adjacency = prefixed
+        for m in self.modules():
+            if hasattr(m, "use_reference_adjacency"):
+                m.use_reference_adjacency(bool(reference_adjacency))
+        return out
 
 
 class AddFn(torch.autograd.Function):

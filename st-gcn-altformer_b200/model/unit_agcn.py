@@ -3,8 +3,9 @@
 Same constructor signature, attribute names (PA, conv_a, conv_b, conv_d, down, bn, soft, relu) and
 init (conv_init / bn_init / conv_branch_init, :12-28,64-71), hence the same state_dict keys.  Two
 deliberate, documented deltas: `A` is *copied* into a non-persistent buffer (the
-reference aliases it with PA and overwrites it with 1e-6), and `A` lives on the module's device
-instead of being re-uploaded every forward (:75).
+reference aliases it with PA and overwrites it with 1e-6; `use_reference_adjacency()` reproduces that
+for checkpoints the reference trained), and `A` lives on the module's device instead of being
+re-uploaded every forward (:75).
 
 forward: C_in == 3 -> the fused gcn0 kernels (Gram-form scores, moment-trick BN, one write pass);
 otherwise the general path (tcgen05 GEMMs for theta/phi, conv_d, down + per-sample graph kernels).
@@ -44,6 +45,7 @@ class unit_agcn(nn.Module):
         A = torch.as_tensor(A, dtype=torch.float32)
         self.PA = nn.Parameter(torch.full_like(A, 1e-6))
         self.register_buffer("A", A.clone(), persistent=False)
+        self.register_buffer("A_graph", A.clone(), persistent=False)   # the normalised adjacency, kept for use_reference_adjacency(False)
         self.conv_a, self.conv_b, self.conv_d = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
         for _ in range(num_subset):
             self.conv_a.append(nn.Conv2d(in_channels, self.inter_c, 1))
@@ -64,6 +66,20 @@ class unit_agcn(nn.Module):
         bn_init(self.bn, 1e-6)
         for i in range(num_subset):
             conv_branch_init(self.conv_d[i], num_subset)
+
+    def use_reference_adjacency(self, on=True):
+        """Reference-compat mode for weights TRAINED BY THE REFERENCE.  The reference builds `PA = nn.Parameter(A)` and then
+        `constant_(PA, 1e-6)` (model/unit_agcn.py:36-38): the parameter aliases the caller's tensor, so `self.A` (:38) is
+        overwritten with 1e-6 too, and after `model.cuda()` it stays a CPU constant 1e-6 that forward() adds to PA (:75-76).
+        A checkpoint saved by the reference's scripts therefore holds a PA that was learnt against A == 1e-6, not against
+        the normalised graph adjacency this module is constructed with.  on=True fills the `A` buffer with 1e-6 so such a
+        checkpoint reproduces the reference's logits; on=False restores the graph adjacency."""
+        with torch.no_grad():
+            if on:
+                self.A.fill_(1e-6)
+            else:
+                self.A.copy_(self.A_graph)
+        return self
 
     @property
     def has_down(self):

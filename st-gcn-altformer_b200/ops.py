@@ -356,6 +356,14 @@ def bone_stream(x, parent):
     return y
 
 
+def palm_center(x, joint=1):
+    need_cuda(x)
+    N, T, V, _ = x.shape
+    y = torch.empty_like(x)
+    _call("afb_palm_center", ptr(x), ptr(y), N, T, V, joint, stream())
+    return y
+
+
 def motion_stream(x):
     need_cuda(x)
     N, T, V, _ = x.shape

@@ -1,5 +1,6 @@
 """Input streams and ensemble combine on device.
 
+palm   = x - x[frame 0, joint 1]   data_process/Hand_Dataset.py:61
 bone   = joint - parent joint      data_process/Hand_Dataset.py:200-217 (table :201-202)
 motion = next frame - this frame   data_process/Hand_Dataset.py:183-198 (last frame zero)
 combine 0.8*ST + 0.2*TS            SHREC/ST_TS/emsemble.py:217-218
@@ -18,6 +19,11 @@ def bone(x, parent=SHREC_PARENT):
     if key not in _parent_cache:
         _parent_cache[key] = torch.tensor(parent, dtype=torch.int32, device=x.device)
     return ops.bone_stream(x.contiguous(), _parent_cache[key])
+
+
+def palm_normalise(x, joint=1):
+    """x (N, T, V, 3) float32 CUDA -> x - x[:, :1, joint:joint+1, :]  (Hand_Dataset.py:61: `skeleton -= skeleton[0][1]`)."""
+    return ops.palm_center(x.contiguous(), joint)
 
 
 def motion(x):

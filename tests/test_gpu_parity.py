@@ -238,3 +238,20 @@ def test_cfg2_train_step_against_oracle(mode):
         assert not bad, bad[:8]
     finally:
         ab.set_precision("bf16")
+
+
+def test_ddp_world2_against_oracle():
+    """Two ranks over NCCL (skipped with fewer than 2 GPUs): the all-reduced mean gradient equals the oracle run on every shard
+    separately and averaged, ranks end bit-identical although they were built from different seeds, and unequal
+    shards reduce to the global-batch mean.  tools/gpu_ddp_check.py holds the check; this test launches it under torchrun."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + os.getpid() % 300), os.path.join(root, "tools", "gpu_ddp_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0 and "ddp-check: PASS" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
