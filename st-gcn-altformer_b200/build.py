@@ -19,6 +19,8 @@ LIB = os.path.join(LIBDIR, "libaltformer_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math" if os.environ.get("AFB_FAST_MATH") else "-DAFB_NO_FAST_MATH"]
+if os.environ.get("AFB_GCN0_STAMPS"):      # phase time stamps inside gcn0_fused_kernel (tools/time_gcn0.py prints them)
+    FLAGS.append("-DAFB_GCN0_STAMPS")
 
 
 def _sources():

@@ -68,6 +68,7 @@ struct SmemPlan {   // byte offsets inside the dynamic shared memory (all multip
   int stage;                                              // 8 x 4 KB TMA staging (overlays X2 / Ms in the resident modes)
   int team, team_bytes, aop_l, xt_h, xt_l, pup;           // generic mode; pup = pitch of the team's RT (elements)
   int fin;                                                // phase 2 scratch
+  int xraw, xraw_bytes;                                   // the sample's (T, V, 3) fp32 block, landed by one bulk copy
   int total;
 };
 // resident: the r rows of the CTA's sample stay in shared memory until they are expanded (one sample per CTA, or eval)
@@ -104,6 +105,9 @@ __host__ __device__ inline SmemPlan make_plan(int T, int V, bool resident) {
   const int p3_end = s.team + kTeams * s.team_bytes;
   s.fin = s.work;
   s.total = (resident || s.p1_end > p3_end) ? s.p1_end : p3_end;
+  s.xraw = (s.total + 127) & ~127;
+  s.xraw_bytes = T * V * 12;
+  s.total = s.xraw + ((s.xraw_bytes + 15) & ~15);
   return s;
 }
 
@@ -158,8 +162,14 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// (compiled in with -DAFB_GCN0_STAMPS only: a %globaltimer read costs ~100 ns of the issuing warp's time and the other
+// warps meet it at the next barrier -- 13 stamps were 7 % of the kernel's stall samples)
 __device__ __forceinline__ void stamp(int k) {
+#ifdef AFB_GCN0_STAMPS
   if (threadIdx.x == 0 && blockIdx.x < kStampCtas) g_stamps[blockIdx.x * kStamps + k] = global_ns();
+#else
+  (void)k;
+#endif
 }
 __device__ __forceinline__ void team_sync(int team) {   // the two warps of a generic-mode team
   asm volatile("bar.sync %0, 64;" ::"r"(team + 1) : "memory");
@@ -169,6 +179,26 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
+}
+// plain (non-tensor) bulk copy global -> shared, completion on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && (++spins > (1u << 24))) __trap();   // bounded: a lost copy traps instead of hanging the GPU
+  }
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -219,7 +249,7 @@ __device__ __forceinline__ void zero_region(uint8_t* base, int bytes, int tid) {
 template <int CBT>
 __device__ __forceinline__ void phase1_sample(const afb_gcn0_fwd_t& p, const FusedArgs& fa, const SmemPlan& pl, uint8_t* sm,
                                               const float (*coef_s)[12], int n, const Lane& L, bool write_mop, bool moments,
-                                              float (&D0)[4], float (&D1)[4]) {
+                                              float (&D0)[4], float (&D1)[4], const float* xs) {
   using C = Cfg<CBT>;
   constexpr int CB = C::CB, NC = C::NC, NT = C::NT, MT = C::MT, YP = C::YP;
   const int T = p.T, V = p.V;
@@ -237,7 +267,7 @@ __device__ __forceinline__ void phase1_sample(const afb_gcn0_fwd_t& p, const Fus
   // S1: x[n] -> X2 (hi/lo) and Y (hi/lo); thread = (frame, pair of adjacent joints).  Two pairs per thread per round, both
   // pairs' loads issued before either is used.
   {
-    const float* xg = p.x + (size_t)n * T * V * 3;
+    const float* xg = xs != nullptr ? xs : p.x + (size_t)n * T * V * 3;   // xs: the sample already sits in shared memory
     const int VH = V >> 1, npairs = T * VH;
     for (int pr0 = tid; pr0 < npairs; pr0 += 2 * kThreads) {
       float2 q[2][3];
@@ -552,10 +582,37 @@ __global__ void __launch_bounds__(kThreads, 2) gcn0_fused_kernel(const __grid_co
     s_gen = training ? ld_acquire_u32(fa.ctrl + 1) : 0u;
     s_par = training ? ld_acquire_u32(fa.ctrl + 2) : 0u;
   }
-  if (blockIdx.x < N) {   // x[n] -> L2 (consumed two barriers from here)
+  // x[n] (T*V*12 contiguous bytes) -> shared memory by ONE bulk copy issued before anything else: S1 then reads it at
+  // shared-memory latency instead of paying an L2 round trip per round.  (16-byte size / alignment: else direct loads.)
+  __shared__ __align__(8) unsigned long long xbar;
+  const uint32_t xbar_u32 = smem_u32(&xbar);
+  const bool use_bulk = ((T * V * 12) & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+  float* xraw = reinterpret_cast<float*>(sm + pl.xraw);
+  uint32_t xphase = 0;
+  if (use_bulk) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xbar_u32));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (blockIdx.x < N) bulk_load(smem_u32(xraw), p.x + (size_t)blockIdx.x * T * V * 3, (uint32_t)(T * V * 12), xbar_u32);
+    }
+  } else if (blockIdx.x < N) {   // x[n] -> L2 (consumed two barriers from here)
     const char* xg = reinterpret_cast<const char*>(p.x + (size_t)blockIdx.x * T * V * 3);
     for (int i = tid; i < (T * V * 12 + 127) >> 7; i += kThreads) prefetch_l2(xg + i * 128);
   }
+  // per-sample: wait for the sample's copy (issuing it first for every sample after the CTA's first)
+  auto acquire_x = [&](int n, bool first) -> const float* {
+    if (!use_bulk) return nullptr;
+    if (!first) {
+      // (the previous sample's S1 reads of xraw are behind at least one __syncthreads)
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bulk_load(smem_u32(xraw), p.x + (size_t)n * T * V * 3, (uint32_t)(T * V * 12), xbar_u32);
+      }
+    }
+    mbar_wait_parity(xbar_u32, xphase);
+    xphase ^= 1u;
+    return xraw;
+  };
   // A + PA and the score weights -> shared memory.  All loads are issued before the first use (fixed trip counts, fully
   // unrolled): a load -> store loop would pay one cold-miss latency per iteration.
   const int IC = p.IC, per = 7 * IC;
@@ -762,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, 2) gcn0_fused_kernel(const __grid_co
         zero_region(sm + pl.work, pl.p1_end - pl.work, tid);
         __syncthreads();
       }
-      phase1_sample<CBT>(p, fa, pl, sm, coef_s, n, L, false, false, D0, D1);
+      phase1_sample<CBT>(p, fa, pl, sm, coef_s, n, L, false, false, D0, D1, acquire_x(n, first));
       if (first) fold_weights();   // after phase 1: its scratch overlays the (now dead) X2 operand
       first = false;
       for (int mt = warp; mt < ntiles_all; mt += kWarps)
@@ -783,9 +840,10 @@ __global__ void __launch_bounds__(kThreads, 2) gcn0_fused_kernel(const __grid_co
       zero_region(sm + pl.work, pl.p1_end - pl.work, tid);
       __syncthreads();
     }
+    const float* xs = acquire_x(n, !had_sample);
     had_sample = true;
     my_n = n;
-    phase1_sample<CBT>(p, fa, pl, sm, coef_s, n, L, !resident, true, D0, D1);
+    phase1_sample<CBT>(p, fa, pl, sm, coef_s, n, L, !resident, true, D0, D1, xs);
   }
   stamp(6);
   if (had_sample) {

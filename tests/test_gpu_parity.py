@@ -255,3 +255,52 @@ def test_ddp_world2_against_oracle():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     print(r.stdout[-2000:])
     assert r.returncode == 0 and "ddp-check: PASS" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_reference_trained_checkpoint_loads_and_matches():
+    """a DataParallel checkpoint as the reference's scripts write it ('module.'-prefixed keys,
+    SHREC/ST_TS/emsemble.py:99-104) loads into the CUDA model and reproduces the reference's eval logits -- which requires
+    the reference's EFFECTIVE adjacency (1e-6, model/unit_agcn.py:36-38,75), switched on by load_state_dict for such files."""
+    import altformer_b200 as ab
+    from oracle import altformer_oracle as O
+    from tests import goldenlib as G
+    case = G.load("model_ST_22_refckpt")
+    N, T, V, cls = case["shape"]
+    st = O.random_state(O.model_spec(3, cls, T, V), case["state_seed"])
+    ckpt = {"module." + k: v for k, v in st.items()}
+    x, _ = O.synthetic_batch(N, T, V, cls, case["batch_seed"])
+    ab.set_precision("fp32")
+    try:
+        mod = ab.ST_GCN_AltFormer(3, cls, num_frame=T, num_joints=V, style="ST", graph="graph.SHRE", graph_args={"labeling_mode": "spatial"}).cuda()
+        res = mod.load_state_dict(ckpt)          # after .cuda(): the adjacency switch must act on the device buffer
+        assert not res.missing_keys and not res.unexpected_keys
+        assert float(mod.gcn0.A.max()) == pytest.approx(1e-6)
+        mod.eval()
+        with torch.no_grad():
+            y = mod(x.cuda())
+        G.check_entry(case["y"], y, 2e-4, "eval logits of a reference-trained checkpoint")
+        # the same tensors without the prefix are a checkpoint of THIS package: graph adjacency, different logits
+        mod.load_state_dict(st)
+        assert float(mod.gcn0.A.max()) > 1e-3
+        with torch.no_grad():
+            y2 = mod(x.cuda())
+        assert float((y2.cpu() - case["y"]).norm() / case["y"].norm()) > 1e-2
+        ab.set_precision("bf16")
+        mod.load_state_dict(ckpt)
+        with torch.no_grad():
+            yb = mod(x.cuda())
+        G.check_entry(case["y"], yb.float(), 2e-2, "bf16 eval logits of a reference-trained checkpoint")
+    finally:
+        ab.set_precision("bf16")
+
+
+def test_streams_against_reference_hand_dataset_gpu():
+    """Device stream transforms vs the reference's own Hand_Dataset.motion / bone / palm normalisation outputs."""
+    import altformer_b200 as ab
+    from tests import goldenlib as G
+    case = G.load("streams_22")
+    x = case["x"][None].cuda()
+    palm = ab.streams.palm_normalise(x)
+    assert torch.allclose(palm[0].cpu(), case["palm"], atol=1e-6)
+    assert torch.allclose(ab.streams.motion(palm)[0].cpu(), case["motion"], atol=1e-6)
+    assert torch.allclose(ab.streams.bone(palm)[0].cpu(), case["bone"], atol=1e-6)

@@ -135,3 +135,26 @@ def test_streams_match_reference_loops():
     assert torch.allclose(b[:, :, 0], torch.zeros_like(b[:, :, 0]))
     m = O.motion_stream(x)
     assert torch.allclose(m[1, 2], x[1, 3] - x[1, 2]) and float(m[:, -1].abs().max()) == 0.0
+
+
+def test_reference_checkpoint_semantics():
+    """model_ST_22_refckpt: logits of the reference exactly as its constructor + .cuda() leave it (adjacency == 1e-6, see
+    tests/golden/make_golden_extra.py).  The oracle reproduces them with A = 1e-6 -- and NOT with the graph adjacency."""
+    case = G.load("model_ST_22_refckpt")
+    N, T, V, cls = case["shape"]
+    st = O.random_state(O.model_spec(3, cls, T, V), case["state_seed"])
+    x, _ = O.synthetic_batch(N, T, V, cls, case["batch_seed"])
+    y = O.model_forward(x, st, torch.full((3, V, V), 1e-6), "ST", False)
+    G.check_entry(case["y"], y, 5e-5, "logits with the reference's effective adjacency")
+    y_graph = O.model_forward(x, st, O.spatial_graph(V), "ST", False)
+    assert float((y_graph - case["y"]).norm() / case["y"].norm()) > 1e-2
+
+
+def test_streams_against_reference_hand_dataset():
+    """bone / motion / palm normalisation vs the outputs of the reference's own Hand_Dataset methods (streams_22.pt)."""
+    case = G.load("streams_22")
+    x = case["x"][None]                      # (1, T, 22, 3)
+    palm = x - x[:, :1, 1:2, :]
+    assert torch.allclose(palm[0], case["palm"], atol=1e-6)
+    assert torch.allclose(O.motion_stream(palm)[0], case["motion"], atol=1e-6)
+    assert torch.allclose(O.bone_stream(palm)[0], case["bone"], atol=1e-6)

@@ -47,6 +47,8 @@ if __name__ == "__main__":
         nbytes = N * T * V * (12 + 256)
         print(f"gcn0 fwd N={N} T={T} V={V} train={train}: {us:.2f} us per launch = {nbytes / us / 1e3:.0f} GB/s "
               f"(fused={os.environ.get('AFB_GCN0_FUSED', '1')})")
+    if not os.environ.get("AFB_GCN0_STAMPS"):
+        sys.exit(0)   # the stamps exist only in a library built with AFB_GCN0_STAMPS=1 (python st-gcn-altformer_b200/build.py --force)
     # phase stamps of one plain launch (globaltimer, thread 0 of each CTA), relative to the earliest CTA entry
     import ctypes as C
     import numpy as np
