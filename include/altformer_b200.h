@@ -320,6 +320,14 @@ int afb_agcn_aggregate_bwd(const void* x, const void* dz, const float* Mmat, voi
 int afb_agcn_scores_bwd(const void* thph, int ld, const float* P, const float* dM, float* dPA, void* dthph,
                         int dtype, int N, int T, int V, int IC, afb_stream s);
 
+/* Tensor-core (mma.sync) versions of the two aggregate steps for bf16 activations, V <= 48, C % 64 == 0 (csrc/agcn_mma.cu).
+ * aggregate_fwd_mma: split == 0 -> z [M, 3C] bf16; split == 1 -> z [M, 9C] = (hi | lo | hi) slabs of 3C columns, the A operand
+ * of the 3-term (hi/lo) conv_d GEMM of the exact-mask forward (M is applied as bf16 hi + lo).
+ * aggregate_bwd_mma: dx (+)= sum_{i,v} dz M_i ; dM_i = sum_{t,c} x dz (written, not accumulated). */
+int afb_agcn_aggregate_fwd_mma(const void* x, const float* Mmat, void* z, int split, int N, int T, int V, int C, afb_stream s);
+int afb_agcn_aggregate_bwd_mma(const void* x, const void* dz, const float* Mmat, void* dx, int accumulate, float* dM,
+                               int N, int T, int V, int C, afb_stream s);
+
 /* ------------------------------------------------------------------------------------------ *
  * Input streams + ensemble (data_process/Hand_Dataset.py:183-217; SHREC/ST_TS/emsemble.py:217-218)
  * ------------------------------------------------------------------------------------------ */

@@ -777,6 +777,8 @@ class AgcnFn(torch.autograd.Function):
         # size, flips ~1e-3 of the masks and costs 3-5e-2 of gradient error against the fp32 reference.
         P = torch.empty((N, 3, V, V), device=x.device, dtype=torch.float32)
         Mmat = torch.empty_like(P)
+        use_mma = _PRECISION[0] == "bf16" and Cin % 64 == 0 and V <= 48 and os.environ.get("AFB_AGCN_MMA", "1")[0] != "0"
+        xs = None
         if exact:
             x32 = ops.cast(x, torch.float32)
             xs = ops.split3(x32, 0)
@@ -784,23 +786,34 @@ class AgcnFn(torch.autograd.Function):
             ops._call("afb_agcn_scores_fwd", ops.ptr(thph32), ops.dt(thph32), ldt, ops.ptr(A), ops.ptr(PA.detach()), ops.ptr(P),
                       ops.ptr(Mmat), N, T, V, IC, ops.stream())
             thph = ops.cast(thph32, torch.bfloat16)
-            z32 = torch.empty((M, 3 * Cin), device=x.device, dtype=torch.float32)
-            ops._call("afb_agcn_aggregate_fwd", ops.ptr(x32), ops.ptr(Mmat), ops.ptr(z32), ops.dt(x32), N, T, V, Cin, ops.stream())
-            h_raw = ops.gemm_tn(ops.split3(z32, 0), st["dc_f3"], Cout, bias=st["bdc"], out_dtype=torch.float32)
-            z = ops.cast(z32, torch.bfloat16)
-            del thph32, z32
+            del thph32
+            if use_mma:   # z leaves the tensor-core aggregate already split: (hi | lo | hi) slabs of 3C columns
+                z = torch.empty((M, 9 * Cin), device=x.device, dtype=torch.bfloat16)
+                ops._call("afb_agcn_aggregate_fwd_mma", ops.ptr(x), ops.ptr(Mmat), ops.ptr(z), 1, N, T, V, Cin, ops.stream())
+                h_raw = ops.gemm_tn(z, st["dc_f3"], Cout, bias=st["bdc"], out_dtype=torch.float32)
+            else:
+                z32 = torch.empty((M, 3 * Cin), device=x.device, dtype=torch.float32)
+                ops._call("afb_agcn_aggregate_fwd", ops.ptr(x32), ops.ptr(Mmat), ops.ptr(z32), ops.dt(x32), N, T, V, Cin, ops.stream())
+                h_raw = ops.gemm_tn(ops.split3(z32, 0), st["dc_f3"], Cout, bias=st["bdc"], out_dtype=torch.float32)
+                z = ops.cast(z32, torch.bfloat16)
+                del z32
+            del x32
         else:
             thph = _gemm_raw(x, st["ab_f"], ldt, bias=st["bab"])
             ops._call("afb_agcn_scores_fwd", ops.ptr(thph), ops.dt(thph), ldt, ops.ptr(A), ops.ptr(PA.detach()), ops.ptr(P),
                       ops.ptr(Mmat), N, T, V, IC, ops.stream())
             z = torch.empty((M, 3 * Cin), device=x.device, dtype=x.dtype)
-            ops._call("afb_agcn_aggregate_fwd", ops.ptr(x), ops.ptr(Mmat), ops.ptr(z), ops.dt(x), N, T, V, Cin, ops.stream())
+            if use_mma:
+                ops._call("afb_agcn_aggregate_fwd_mma", ops.ptr(x), ops.ptr(Mmat), ops.ptr(z), 0, N, T, V, Cin, ops.stream())
+            else:
+                ops._call("afb_agcn_aggregate_fwd", ops.ptr(x), ops.ptr(Mmat), ops.ptr(z), ops.dt(x), N, T, V, Cin, ops.stream())
             h_raw = _gemm_raw(z, st["dc_f"], Cout, bias=st["bdc"])
         stats_h = _bn_forward(h_raw, bng, bnb, bufs[0], bufs[1], training, momentum, eps)
         if has_down:
             wdn, bdn, dng, dnb = params[20:24]
             if exact:
                 d_raw = ops.gemm_tn(xs, w_fwd3(wdn), Cout, bias=bdn.detach(), out_dtype=torch.float32)
+                xs = None
             else:
                 d_raw = mm_fwd(x, wdn, bias=bdn.detach())
             stats_d = _bn_forward(d_raw, dng, dnb, bufs[2], bufs[3], training, momentum, eps)
@@ -812,7 +825,7 @@ class AgcnFn(torch.autograd.Function):
             res = x
         y, _ = ops.bn_act_fwd(h_raw, stats_h[2], stats_h[3], True, res_pre=res, out_dtype=act_dtype())
         ctx.save_for_backward(x, A, thph, P, Mmat, z, h_raw, stats_h, d_raw, stats_d, res if has_down else None, PA, *params)
-        ctx.cfg = (N, T, V, training, has_down, len(bufs))
+        ctx.cfg = (N, T, V, training, has_down, len(bufs), use_mma)
         return y
 
     @staticmethod
@@ -820,7 +833,7 @@ class AgcnFn(torch.autograd.Function):
         saved = ctx.saved_tensors
         x, A, thph, P, Mmat, z, h_raw, stats_h, d_raw, stats_d, res, PA = saved[:12]
         params = saved[12:]
-        N, T, V, training, has_down, nbufs = ctx.cfg
+        N, T, V, training, has_down, nbufs, use_mma = ctx.cfg
         wa, ba = params[0:6:2], params[1:6:2]
         wb, bb = params[6:12:2], params[7:12:2]
         wd, bd = params[12:18:2], params[13:18:2]
@@ -847,8 +860,12 @@ class AgcnFn(torch.autograd.Function):
             ops.colsum(dh, sk(14 + 2 * i))
         dz = _gemm_raw_dx(dh, st["dc_x"], 3 * Cin)
         dM = torch.empty_like(P)
-        ops._call("afb_agcn_aggregate_bwd", ops.ptr(x), ops.ptr(dz), ops.ptr(Mmat), ops.ptr(dx), 1, ops.ptr(dM), ops.dt(x),
-                  N, T, V, Cin, ops.stream())
+        if use_mma:
+            ops._call("afb_agcn_aggregate_bwd_mma", ops.ptr(x), ops.ptr(dz), ops.ptr(Mmat), ops.ptr(dx), 1, ops.ptr(dM), N, T, V, Cin,
+                      ops.stream())
+        else:
+            ops._call("afb_agcn_aggregate_bwd", ops.ptr(x), ops.ptr(dz), ops.ptr(Mmat), ops.ptr(dx), 1, ops.ptr(dM), ops.dt(x),
+                      N, T, V, Cin, ops.stream())
         dthph = torch.zeros_like(thph) if ldt != 6 * IC else torch.empty_like(thph)
         ops._call("afb_agcn_scores_bwd", ops.ptr(thph), ldt, ops.ptr(P), ops.ptr(dM), ops.ptr(sk(0)), ops.ptr(dthph),
                   ops.dt(thph), N, T, V, IC, ops.stream())
