@@ -327,6 +327,12 @@ int afb_agcn_scores_bwd(const void* thph, int ld, const float* P, const float* d
 int afb_agcn_aggregate_fwd_mma(const void* x, const float* Mmat, void* z, int split, int N, int T, int V, int C, afb_stream s);
 int afb_agcn_aggregate_bwd_mma(const void* x, const void* dz, const float* Mmat, void* dx, int accumulate, float* dM,
                                int N, int T, int V, int C, afb_stream s);
+/* scores on tensor cores (V <= 48, IC % 16 == 0): thph bf16, or fp32 applied as bf16 hi + lo (exact-mask forward); the backward
+ * takes / produces bf16. */
+int afb_agcn_scores_fwd_mma(const void* thph, int dtype, int ld, const float* A, const float* PA, float* P, float* Mmat,
+                            int N, int T, int V, int IC, afb_stream s);
+int afb_agcn_scores_bwd_mma(const void* thph, int ld, const float* P, const float* dM, float* dPA, void* dthph,
+                            int N, int T, int V, int IC, afb_stream s);
 
 /* ------------------------------------------------------------------------------------------ *
  * Input streams + ensemble (data_process/Hand_Dataset.py:183-217; SHREC/ST_TS/emsemble.py:217-218)

@@ -113,6 +113,8 @@ def _declare(L):
         "afb_agcn_scores_bwd": [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "afb_agcn_aggregate_fwd_mma": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "afb_agcn_aggregate_bwd_mma": [vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, vp],
+        "afb_agcn_scores_fwd_mma": [vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "afb_agcn_scores_bwd_mma": [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "afb_bone_stream": [vp, vp, vp, i64, i32, vp],
         "afb_motion_stream": [vp, vp, i32, i32, i32, vp],
         "afb_palm_center": [vp, vp, i32, i32, i32, i32, vp],

@@ -311,6 +311,235 @@ __global__ void __launch_bounds__(kThreads, 2) agcn_aggr_bwd_dm_mma_kernel(const
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// scores forward: grid (N, 3).  S_i[u][v] = sum_t sum_ic theta_t[u][ic] phi_t[v][ic] / (IC T); warps take frames round robin
+// and keep a private S in registers; one shared-memory reduction, then softmax over u, M = P + A + PA.
+// TIN = float: theta/phi arrive at fp32 accuracy (exact-mask forward) and are applied as bf16 hi + lo (3 MMA terms).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int ICC = 32;   // inner-channel chunk staged per round (IC = 16 runs with a chunk of 16)
+
+template <int VP, typename TIN>
+__global__ void __launch_bounds__(kThreads, 2) agcn_scores_fwd_mma_kernel(const TIN* __restrict__ thph, int ld, const float* __restrict__ A,
+                                                                         const float* __restrict__ PA, float* __restrict__ P,
+                                                                         float* __restrict__ Mmat, int T, int V, int IC) {
+  constexpr bool EXACT = sizeof(TIN) == 4;
+  constexpr int MT = VP / 16, NT = VP / 8;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int icc = IC < ICC ? IC : ICC, pitch = icc + 8;
+  const int tile = VP * pitch;                                    // elements of one [VP][pitch] operand tile
+  bf16* base = reinterpret_cast<bf16*>(smraw);                    // per warp: th_hi, ph_hi, (th_lo, ph_lo)
+  const int per_warp = (EXACT ? 4 : 2) * tile;
+  float* S = reinterpret_cast<float*>(base + kWarps * per_warp);  // [VP][VP] reduction target
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3, lj = lane >> 3, lr = lane & 7;
+  const int n = blockIdx.x, i = blockIdx.y;
+  {
+    uint32_t* w = reinterpret_cast<uint32_t*>(smraw);
+    const int words = (kWarps * per_warp) / 2 + VP * VP;
+    for (int e = tid; e < words; e += kThreads) w[e] = 0u;
+  }
+  __syncthreads();
+  bf16* thh = base + warp * per_warp;
+  bf16* phh = thh + tile;
+  bf16* thl = phh + tile;
+  bf16* phl = thl + tile;
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+  for (int t = warp; t < T; t += kWarps) {
+    const TIN* src = thph + ((int64_t)n * T + t) * V * ld;
+    for (int c0 = 0; c0 < IC; c0 += icc) {
+      __syncwarp();
+      if (EXACT) {
+        const int quads = icc / 4;
+        for (int e = lane; e < 2 * V * quads; e += 32) {
+          const int which = e / (V * quads), r = (e / quads) % V, q = e % quads;
+          const float4 v4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (int64_t)r * ld + (which ? 3 + i : i) * IC + c0 + q * 4);
+          const uint32_t h0 = pack2(v4.x, v4.y), h1 = pack2(v4.z, v4.w);
+          const uint32_t l0 = pack2(v4.x - __uint_as_float(h0 << 16), v4.y - __uint_as_float(h0 & 0xffff0000u));
+          const uint32_t l1 = pack2(v4.z - __uint_as_float(h1 << 16), v4.w - __uint_as_float(h1 & 0xffff0000u));
+          bf16* dh = (which ? phh : thh) + r * pitch + q * 4;
+          bf16* dl = (which ? phl : thl) + r * pitch + q * 4;
+          *reinterpret_cast<uint2*>(dh) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(dl) = make_uint2(l0, l1);
+        }
+      } else {
+        const int pieces = icc / 8;
+        for (int e = lane; e < 2 * V * pieces; e += 32) {
+          const int which = e / (V * pieces), r = (e / pieces) % V, q = e % pieces;
+          cp_async16(smem_u32((which ? phh : thh) + r * pitch + q * 8),
+                     reinterpret_cast<const bf16*>(src) + (int64_t)r * ld + (which ? 3 + i : i) * IC + c0 + q * 8);
+        }
+        cp_async_wait_all();
+      }
+      __syncwarp();
+      for (int ks = 0; ks < icc / 16; ++ks) {
+        uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+        for (int np = 0; np < NT / 2; ++np) {
+          uint32_t r4[4];   // phi rows = v (n index), columns = ic (k index)
+          const int off = (np * 16 + (lj >> 1) * 8 + lr) * pitch + ks * 16 + (lj & 1) * 8;
+          ldsm_x4(smem_u32(phh + off), r4);
+          bh[2 * np][0] = r4[0]; bh[2 * np][1] = r4[1]; bh[2 * np + 1][0] = r4[2]; bh[2 * np + 1][1] = r4[3];
+          if (EXACT) {
+            ldsm_x4(smem_u32(phl + off), r4);
+            bl[2 * np][0] = r4[0]; bl[2 * np][1] = r4[1]; bl[2 * np + 1][0] = r4[2]; bl[2 * np + 1][1] = r4[3];
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          uint32_t a[4];
+          const int off = (mt * 16 + (lj & 1) * 8 + lr) * pitch + ks * 16 + (lj >> 1) * 8;
+          ldsm_x4(smem_u32(thh + off), a);
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            mma(acc[mt][nt], a, bh[nt][0], bh[nt][1]);
+            if (EXACT) mma(acc[mt][nt], a, bl[nt][0], bl[nt][1]);
+          }
+          if (EXACT) {
+            ldsm_x4(smem_u32(thl + off), a);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma(acc[mt][nt], a, bh[nt][0], bh[nt][1]);
+          }
+        }
+      }
+    }
+  }
+  // reduce the warps' partial S
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int u0 = mt * 16 + g, v = nt * 8 + 2 * tq;
+      atomicAdd(S + u0 * VP + v, acc[mt][nt][0]);
+      atomicAdd(S + u0 * VP + v + 1, acc[mt][nt][1]);
+      atomicAdd(S + (u0 + 8) * VP + v, acc[mt][nt][2]);
+      atomicAdd(S + (u0 + 8) * VP + v + 1, acc[mt][nt][3]);
+    }
+  __syncthreads();
+  const float inv = 1.0f / (float)(IC * T);
+  // softmax over u for column v: one warp per column, lanes over u
+  for (int v = warp; v < V; v += kWarps) {
+    float s0 = lane < V ? S[lane * VP + v] * inv : -INFINITY;
+    float s1 = lane + 32 < V ? S[(lane + 32) * VP + v] * inv : -INFINITY;
+    float mx = fmaxf(s0, s1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e0 = lane < V ? __expf(s0 - mx) : 0.f, e1 = lane + 32 < V ? __expf(s1 - mx) : 0.f;
+    float den = e0 + e1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+    const float rden = 1.0f / den;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int u = lane + 32 * h;
+      if (u < V) {
+        const float pr = (h ? e1 : e0) * rden;
+        const int idx = (i * V + u) * V + v;
+        const int64_t gi = (int64_t)n * 3 * V * V + idx;
+        P[gi] = pr;
+        Mmat[gi] = pr + A[idx] + PA[idx];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// scores backward: grid (N, 3).  dPA += dM; dS = P (dM - colsum_u(P dM)) / (IC T);
+// d(theta)_t [u][ic] = sum_v dS[u][v] phi_t[v][ic],  d(phi)_t [v][ic] = sum_u dS[u][v] theta_t[u][ic]   (one frame per warp round)
+// ------------------------------------------------------------------------------------------------------------------
+template <int VP>
+__global__ void __launch_bounds__(kThreads, 2) agcn_scores_bwd_mma_kernel(const bf16* __restrict__ thph, int ld, const float* __restrict__ P,
+                                                                         const float* __restrict__ dM, float* __restrict__ dPA,
+                                                                         bf16* __restrict__ dthph, int T, int V, int IC) {
+  constexpr int UP = VP + 8, MT = VP / 16, KS = VP / 16;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int icc = IC < ICC ? IC : ICC, pitch = icc + 8, tile = VP * pitch;
+  float* dSf = reinterpret_cast<float*>(smraw);                   // [V][V] scratch
+  bf16* dS = reinterpret_cast<bf16*>(dSf + VP * VP);              // [VP u][UP v]
+  bf16* dSt = dS + VP * UP;                                       // [VP v][UP u]
+  bf16* stage = dSt + VP * UP;                                    // per warp: theta tile, phi tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3, lj = lane >> 3, lr = lane & 7;
+  const int n = blockIdx.x, i = blockIdx.y;
+  {
+    uint32_t* w = reinterpret_cast<uint32_t*>(smraw);
+    const int words = VP * VP + (2 * VP * UP + kWarps * 2 * tile) / 2;
+    for (int e = tid; e < words; e += kThreads) w[e] = 0u;
+  }
+  __syncthreads();
+  const int64_t g0 = ((int64_t)n * 3 + i) * V * V;
+  for (int e = tid; e < V * V; e += kThreads) {
+    const float d = dM[g0 + e];
+    dSf[e] = d;
+    atomicAdd(dPA + i * V * V + e, d);
+  }
+  __syncthreads();
+  const float inv = 1.0f / (float)(IC * T);
+  for (int v = warp; v < V; v += kWarps) {   // column v: dot over u, then dS
+    float part = 0.f;
+    for (int u = lane; u < V; u += 32) part += P[g0 + u * V + v] * dSf[u * V + v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    for (int u = lane; u < V; u += 32) {
+      const bf16 val = __float2bfloat16_rn(P[g0 + u * V + v] * (dSf[u * V + v] - part) * inv);
+      dS[u * UP + v] = val;
+      dSt[v * UP + u] = val;
+    }
+  }
+  __syncthreads();
+  bf16* ths = stage + warp * 2 * tile;
+  bf16* phs = ths + tile;
+  const int pieces = icc / 8;
+  for (int t = warp; t < T; t += kWarps) {
+    const int64_t row0 = ((int64_t)n * T + t) * V;
+    for (int c0 = 0; c0 < IC; c0 += icc) {
+      __syncwarp();
+      for (int e = lane; e < 2 * V * pieces; e += 32) {
+        const int which = e / (V * pieces), r = (e / pieces) % V, q = e % pieces;
+        cp_async16(smem_u32((which ? phs : ths) + r * pitch + q * 8), thph + (row0 + r) * ld + (which ? 3 + i : i) * IC + c0 + q * 8);
+      }
+      cp_async_wait_all();
+      __syncwarp();
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {   // 0: d(theta) = dS phi ; 1: d(phi) = dS^T theta
+        const bf16* Aop = which ? dSt : dS;
+        const bf16* Bop = which ? ths : phs;
+        for (int nq = 0; nq < icc / 16; ++nq) {   // 16 output channels per pass
+          float acc[MT][2][4];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[mt][j][0] = acc[mt][j][1] = acc[mt][j][2] = acc[mt][j][3] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            uint32_t r4[4];
+            ldsm_x4_t(smem_u32(Bop + (ks * 16 + (lj & 1) * 8 + lr) * pitch + nq * 16 + (lj >> 1) * 8), r4);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              uint32_t a[4];
+              ldsm_x4(smem_u32(Aop + (mt * 16 + (lj & 1) * 8 + lr) * UP + ks * 16 + (lj >> 1) * 8), a);
+              mma(acc[mt][0], a, r4[0], r4[1]);
+              mma(acc[mt][1], a, r4[2], r4[3]);
+            }
+          }
+          const int col = (which ? 3 + i : i) * IC + c0 + nq * 16 + 2 * tq;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (r0 < V) *reinterpret_cast<uint32_t*>(dthph + (row0 + r0) * ld + col + j * 8) = pack2(acc[mt][j][0], acc[mt][j][1]);
+              if (r1 < V) *reinterpret_cast<uint32_t*>(dthph + (row0 + r1) * ld + col + j * 8) = pack2(acc[mt][j][2], acc[mt][j][3]);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace afb
 
@@ -369,4 +598,45 @@ extern "C" int afb_agcn_aggregate_bwd_mma(const void* x, const void* dz, const f
     }
   }
   return check_launch("agcn_aggregate_bwd_dm");
+}
+
+// thph: [M, ld] bf16 (dtype AFB_BF16) or fp32 (AFB_F32: applied as bf16 hi + lo); V <= 48, IC % 16 == 0
+extern "C" int afb_agcn_scores_fwd_mma(const void* thph, int dt, int ld, const float* A, const float* PA, float* P, float* Mmat, int N, int T,
+                                       int V, int IC, afb_stream s) {
+  AFB_REQUIRE(thph && A && PA && P && Mmat && N > 0 && T > 0 && V > 0 && V <= 48 && IC % 16 == 0 && ld >= 6 * IC && ld % 8 == 0,
+              "agcn_scores_fwd_mma: bad args (V <= 48, IC %% 16 == 0)");
+  AFB_REQUIRE(IC <= ICC || IC % ICC == 0, "agcn_scores_fwd_mma: IC=%d unsupported", IC);
+  const int VP = V <= 32 ? 32 : 48, icc = IC < ICC ? IC : ICC, tile = VP * (icc + 8);
+  const bool f32 = dt == AFB_F32;
+  const size_t smem = (size_t)kWarps * (f32 ? 4 : 2) * tile * 2 + (size_t)VP * VP * 4;
+  dim3 grid(N, 3);
+  int rc;
+#define LAUNCH(VP_, T_)                                                                                                  \
+  do {                                                                                                                   \
+    if ((rc = set_smem(agcn_scores_fwd_mma_kernel<VP_, T_>, smem, "agcn_scores_fwd_mma"))) return rc;                    \
+    agcn_scores_fwd_mma_kernel<VP_, T_><<<grid, kThreads, smem, as_stream(s)>>>((const T_*)thph, ld, A, PA, P, Mmat, T, V, IC); \
+  } while (0)
+  if (VP == 32) { if (f32) LAUNCH(32, float); else LAUNCH(32, bf16); }
+  else { if (f32) LAUNCH(48, float); else LAUNCH(48, bf16); }
+#undef LAUNCH
+  return check_launch("agcn_scores_fwd_mma");
+}
+
+extern "C" int afb_agcn_scores_bwd_mma(const void* thph, int ld, const float* P, const float* dM, float* dPA, void* dthph, int N, int T, int V,
+                                       int IC, afb_stream s) {
+  AFB_REQUIRE(thph && P && dM && dPA && dthph && N > 0 && T > 0 && V > 0 && V <= 48 && IC % 16 == 0 && ld >= 6 * IC && ld % 8 == 0,
+              "agcn_scores_bwd_mma: bad args (V <= 48, IC %% 16 == 0)");
+  AFB_REQUIRE(IC <= ICC || IC % ICC == 0, "agcn_scores_bwd_mma: IC=%d unsupported", IC);
+  const int VP = V <= 32 ? 32 : 48, icc = IC < ICC ? IC : ICC, tile = VP * (icc + 8);
+  const size_t smem = (size_t)VP * VP * 4 + ((size_t)2 * VP * (VP + 8) + (size_t)kWarps * 2 * tile) * 2;
+  dim3 grid(N, 3);
+  int rc;
+  if (VP == 32) {
+    if ((rc = set_smem(agcn_scores_bwd_mma_kernel<32>, smem, "agcn_scores_bwd_mma"))) return rc;
+    agcn_scores_bwd_mma_kernel<32><<<grid, kThreads, smem, as_stream(s)>>>((const bf16*)thph, ld, P, dM, dPA, (bf16*)dthph, T, V, IC);
+  } else {
+    if ((rc = set_smem(agcn_scores_bwd_mma_kernel<48>, smem, "agcn_scores_bwd_mma"))) return rc;
+    agcn_scores_bwd_mma_kernel<48><<<grid, kThreads, smem, as_stream(s)>>>((const bf16*)thph, ld, P, dM, dPA, (bf16*)dthph, T, V, IC);
+  }
+  return check_launch("agcn_scores_bwd_mma");
 }

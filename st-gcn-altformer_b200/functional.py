@@ -777,14 +777,15 @@ class AgcnFn(torch.autograd.Function):
         # size, flips ~1e-3 of the masks and costs 3-5e-2 of gradient error against the fp32 reference.
         P = torch.empty((N, 3, V, V), device=x.device, dtype=torch.float32)
         Mmat = torch.empty_like(P)
-        use_mma = _PRECISION[0] == "bf16" and Cin % 64 == 0 and V <= 48 and os.environ.get("AFB_AGCN_MMA", "1")[0] != "0"
+        use_mma = (_PRECISION[0] == "bf16" and Cin % 64 == 0 and IC % 16 == 0 and (IC <= 32 or IC % 32 == 0) and V <= 48
+                   and os.environ.get("AFB_AGCN_MMA", "1")[0] != "0")
         xs = None
         if exact:
             x32 = ops.cast(x, torch.float32)
             xs = ops.split3(x32, 0)
             thph32 = ops.gemm_tn(xs, st["ab_f3"], ldt, bias=st["bab"], out_dtype=torch.float32)
-            ops._call("afb_agcn_scores_fwd", ops.ptr(thph32), ops.dt(thph32), ldt, ops.ptr(A), ops.ptr(PA.detach()), ops.ptr(P),
-                      ops.ptr(Mmat), N, T, V, IC, ops.stream())
+            ops._call("afb_agcn_scores_fwd_mma" if use_mma else "afb_agcn_scores_fwd", ops.ptr(thph32), ops.dt(thph32), ldt, ops.ptr(A),
+                      ops.ptr(PA.detach()), ops.ptr(P), ops.ptr(Mmat), N, T, V, IC, ops.stream())
             thph = ops.cast(thph32, torch.bfloat16)
             del thph32
             if use_mma:   # z leaves the tensor-core aggregate already split: (hi | lo | hi) slabs of 3C columns
@@ -800,8 +801,8 @@ class AgcnFn(torch.autograd.Function):
             del x32
         else:
             thph = _gemm_raw(x, st["ab_f"], ldt, bias=st["bab"])
-            ops._call("afb_agcn_scores_fwd", ops.ptr(thph), ops.dt(thph), ldt, ops.ptr(A), ops.ptr(PA.detach()), ops.ptr(P),
-                      ops.ptr(Mmat), N, T, V, IC, ops.stream())
+            ops._call("afb_agcn_scores_fwd_mma" if use_mma else "afb_agcn_scores_fwd", ops.ptr(thph), ops.dt(thph), ldt, ops.ptr(A),
+                      ops.ptr(PA.detach()), ops.ptr(P), ops.ptr(Mmat), N, T, V, IC, ops.stream())
             z = torch.empty((M, 3 * Cin), device=x.device, dtype=x.dtype)
             if use_mma:
                 ops._call("afb_agcn_aggregate_fwd_mma", ops.ptr(x), ops.ptr(Mmat), ops.ptr(z), 0, N, T, V, Cin, ops.stream())
@@ -867,8 +868,12 @@ class AgcnFn(torch.autograd.Function):
             ops._call("afb_agcn_aggregate_bwd", ops.ptr(x), ops.ptr(dz), ops.ptr(Mmat), ops.ptr(dx), 1, ops.ptr(dM), ops.dt(x),
                       N, T, V, Cin, ops.stream())
         dthph = torch.zeros_like(thph) if ldt != 6 * IC else torch.empty_like(thph)
-        ops._call("afb_agcn_scores_bwd", ops.ptr(thph), ldt, ops.ptr(P), ops.ptr(dM), ops.ptr(sk(0)), ops.ptr(dthph),
-                  ops.dt(thph), N, T, V, IC, ops.stream())
+        if use_mma:
+            ops._call("afb_agcn_scores_bwd_mma", ops.ptr(thph), ldt, ops.ptr(P), ops.ptr(dM), ops.ptr(sk(0)), ops.ptr(dthph),
+                      N, T, V, IC, ops.stream())
+        else:
+            ops._call("afb_agcn_scores_bwd", ops.ptr(thph), ldt, ops.ptr(P), ops.ptr(dM), ops.ptr(sk(0)), ops.ptr(dthph),
+                      ops.dt(thph), N, T, V, IC, ops.stream())
         for i in range(3):
             _dw_cols(dthph, x, sk(1 + 2 * i).view(IC, Cin), IC, Cin, g_col0=i * IC)
             ops.colsum(dthph, sk(2 + 2 * i), col0=i * IC, ncols=IC)
