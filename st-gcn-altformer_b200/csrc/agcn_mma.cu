@@ -48,6 +48,7 @@ __device__ __forceinline__ void warp_stage(bf16* dst, const bf16* src, int64_t l
     cp_async16(smem_u32(dst + r * (CH + 8) + q * 8), src + (int64_t)r * ld + q * 8);
   }
 }
+constexpr int kFwdFramesPerWarp = 4;   // aggregate forward: frames per warp (amortises the per-CTA staging of M)
 constexpr int CX = 32;          // channel chunk of the dx kernel (three dz slabs staged per warp: 64 would allow one CTA per SM only)
 constexpr int CXP = CX + 8;
 
@@ -62,8 +63,9 @@ __global__ void __launch_bounds__(kThreads, 2) agcn_aggr_fwd_mma_kernel(const bf
   bf16* Ah = reinterpret_cast<bf16*>(smraw);                 // [3][VP v][UP u] = M_i^T (hi)
   bf16* Al = Ah + 3 * VP * UP;                               // (lo; EXACT only)
   bf16* Xs = Ah + (EXACT ? 2 : 1) * 3 * VP * UP;             // [kWarps][VP][CP]
+  bf16* Os = Xs + kWarps * VP * CP;                          // [kWarps][EXACT ? 2 : 1][16][CP] output staging (hi, lo)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3, lj = lane >> 3, lr = lane & 7;
-  const int n = blockIdx.x / groups, t = (blockIdx.x % groups) * kWarps + warp;
+  const int n = blockIdx.x / groups, tbase = (blockIdx.x % groups) * (kWarps * kFwdFramesPerWarp);
   // zero everything once (operand padding must be exact zeros), then M^T
   {
     const int words = ((EXACT ? 2 : 1) * 3 * VP * UP + kWarps * VP * CP) / 2;
@@ -80,13 +82,19 @@ __global__ void __launch_bounds__(kThreads, 2) agcn_aggr_fwd_mma_kernel(const bf
     if (EXACT) Al[(i * VP + v) * UP + u] = __float2bfloat16_rn(m - __bfloat162float(h));
   }
   __syncthreads();
-  if (t >= T) return;
-  bf16* Xw = Xs + warp * VP * CP;
-  const int64_t row0 = ((int64_t)n * T + t) * V;
+  bf16* Ow = Os + warp * (EXACT ? 2 : 1) * 16 * CP;
+  // this warp's work items: (frame, channel chunk) pairs
+  const int chunks = C / CC;
+  int nfr = 0;
+  for (int k = 0; k < kFwdFramesPerWarp; ++k) nfr += (tbase + warp + k * kWarps) < T ? 1 : 0;
+  const int items = nfr * chunks;
+  if (items == 0) return;
   const int ldz = (EXACT ? 9 : 3) * C;
-  for (int c0 = 0; c0 < C; c0 += CC) {
-    __syncwarp();
-    warp_stage<CC>(Xw, x + row0 * C + c0, C, V, lane);
+  bf16* Xw = Xs + warp * VP * CP;
+  for (int it = 0; it < items; ++it) {
+    const int t = tbase + warp + (it / chunks) * kWarps, c0 = (it % chunks) * CC;
+    const int64_t row0 = ((int64_t)n * T + t) * V;
+    warp_stage<CC>(Xw, x + row0 * C + c0, C, V, lane);   // (the previous item's ldmatrix reads are warp-synchronous: done)
     cp_async_wait_all();
     __syncwarp();
     uint32_t b[KS][8][2];
@@ -119,26 +127,31 @@ __global__ void __launch_bounds__(kThreads, 2) agcn_aggr_fwd_mma_kernel(const bf
             for (int nt = 0; nt < 8; ++nt) mma(acc[nt], a, b[ks][nt][0], b[ks][nt][1]);
           }
         }
-        const int v0 = mt * 16 + g, v1 = v0 + 8;
-        bf16* zr0 = z + (row0 + v0) * ldz + i * C + c0 + 2 * tq;
-        bf16* zr1 = z + (row0 + v1) * ldz + i * C + c0 + 2 * tq;
+        // fragments -> staging tile(s) [16][CP] (conflict-free 4-byte stores) -> 16-byte row-contiguous global stores
+        __syncwarp();   // the previous tile's copy-out has finished reading the staging tile
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
           const uint32_t h0 = pack2(acc[nt][0], acc[nt][1]), h1 = pack2(acc[nt][2], acc[nt][3]);
-          if (v0 < V) {
-            *reinterpret_cast<uint32_t*>(zr0 + nt * 8) = h0;
-            if (EXACT) {
-              *reinterpret_cast<uint32_t*>(zr0 + nt * 8 + 3 * C) =
-                  pack2(acc[nt][0] - __uint_as_float(h0 << 16), acc[nt][1] - __uint_as_float(h0 & 0xffff0000u));
-              *reinterpret_cast<uint32_t*>(zr0 + nt * 8 + 6 * C) = h0;
-            }
+          *reinterpret_cast<uint32_t*>(Ow + g * CP + nt * 8 + 2 * tq) = h0;
+          *reinterpret_cast<uint32_t*>(Ow + (g + 8) * CP + nt * 8 + 2 * tq) = h1;
+          if (EXACT) {
+            *reinterpret_cast<uint32_t*>(Ow + (16 + g) * CP + nt * 8 + 2 * tq) =
+                pack2(acc[nt][0] - __uint_as_float(h0 << 16), acc[nt][1] - __uint_as_float(h0 & 0xffff0000u));
+            *reinterpret_cast<uint32_t*>(Ow + (16 + g + 8) * CP + nt * 8 + 2 * tq) =
+                pack2(acc[nt][2] - __uint_as_float(h1 << 16), acc[nt][3] - __uint_as_float(h1 & 0xffff0000u));
           }
-          if (v1 < V) {
-            *reinterpret_cast<uint32_t*>(zr1 + nt * 8) = h1;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // 16 rows x 8 pieces of 16 bytes: lane -> (row = lane / 8 + 4 k, piece = lane % 8)
+          const int r = (lane >> 3) + 4 * k, q = lane & 7, v = mt * 16 + r;
+          if (v < V) {
+            bf16* dst = z + (row0 + v) * ldz + i * C + c0 + q * 8;
+            const uint4 hi = *reinterpret_cast<const uint4*>(Ow + r * CP + q * 8);
+            *reinterpret_cast<uint4*>(dst) = hi;
             if (EXACT) {
-              *reinterpret_cast<uint32_t*>(zr1 + nt * 8 + 3 * C) =
-                  pack2(acc[nt][2] - __uint_as_float(h1 << 16), acc[nt][3] - __uint_as_float(h1 & 0xffff0000u));
-              *reinterpret_cast<uint32_t*>(zr1 + nt * 8 + 6 * C) = h1;
+              *reinterpret_cast<uint4*>(dst + 3 * C) = *reinterpret_cast<const uint4*>(Ow + (16 + r) * CP + q * 8);
+              *reinterpret_cast<uint4*>(dst + 6 * C) = hi;
             }
           }
         }
@@ -548,8 +561,8 @@ using namespace afb;
 // z: split == 0 -> [M, 3C] bf16; split == 1 -> [M, 9C] = (hi | lo | hi) slabs of 3C columns each (exact-mask forward)
 extern "C" int afb_agcn_aggregate_fwd_mma(const void* x, const float* Mmat, void* z, int split, int N, int T, int V, int C, afb_stream s) {
   AFB_REQUIRE(x && Mmat && z && N > 0 && T > 0 && V > 0 && V <= 48 && C > 0 && C % 64 == 0, "agcn_aggregate_fwd_mma: bad args (V <= 48, C %% 64 == 0)");
-  const int VP = V <= 32 ? 32 : 48, UP = VP + 8, groups = (T + kWarps - 1) / kWarps;
-  const size_t smem = ((size_t)(split ? 2 : 1) * 3 * VP * UP + (size_t)kWarps * VP * CP) * 2;
+  const int VP = V <= 32 ? 32 : 48, UP = VP + 8, per_cta = kWarps * kFwdFramesPerWarp, groups = (T + per_cta - 1) / per_cta;
+  const size_t smem = ((size_t)(split ? 2 : 1) * 3 * VP * UP + (size_t)kWarps * VP * CP + (size_t)kWarps * (split ? 2 : 1) * 16 * CP) * 2;
   int rc;
 #define LAUNCH(VP_, EX_)                                                                                              \
   do {                                                                                                                \

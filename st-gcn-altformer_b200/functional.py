@@ -109,6 +109,29 @@ def w_fwd3(p):
     return _derived(p, "split_b", lambda w: ops.split3(w.reshape(w.shape[0], -1).contiguous(), 1))
 
 
+def hi_lo_cat(w32):
+    """fp32 [N, K] -> bf16 [N, 2K] = (hi | lo): B operand of a two-"tap" GEMM over a bf16 A operand (tap_row_stride 0: both
+    taps read the same A rows), i.e. A @ (hi + lo)^T with fp32 accumulation -- the product of bf16 activations with fp32
+    weights at fp32 accuracy without materialising a split copy of the activations."""
+    N, K = w32.shape
+    s3 = ops.split3(w32.contiguous(), 1)                      # (hi | hi | lo)
+    out = torch.empty((N, 2 * K), device=w32.device, dtype=torch.bfloat16)
+    ops.copy2d(s3, out, N, K, 3 * K, 2 * K)
+    ops.copy2d(s3, out, N, K, 3 * K, 2 * K, src_off=2 * K, dst_off=K)
+    return out
+
+
+def w_fwd2(p):
+    return _derived(p, "hi_lo", lambda w: hi_lo_cat(w.reshape(w.shape[0], -1).float()))
+
+
+def gemm_hi_lo(x, w2, N, **epi):
+    """x [M, K] bf16 @ (hi + lo)^T -> fp32 [M, N]  (see hi_lo_cat)."""
+    M, K = x.shape
+    return ops.gemm_tn(x, w2, N, k_per_tap=K, taps=2, tap_row_stride=0, tap_pad=0, rows_per_batch=M, batches=1,
+                       out_dtype=torch.float32, **epi)
+
+
 def w_dx(p):
     """MN-major B operand of dx = dy W: W itself [N, K] (bf16), or row-stacked (hi;hi;lo) [3N, K]."""
     if _PRECISION[0] == "bf16":
@@ -716,13 +739,13 @@ def _agcn_stacked(wa, ba, wb, bb, wd, bd):
         if _PRECISION[0] == "bf16":
             ab_f, dc_f = ops.cast(Wab, torch.bfloat16), ops.cast(Wdc, torch.bfloat16)
             ab_x, dc_x = ab_f, dc_f
-            if exact_bn_mask():   # forward operands of the exact-mask forward (hi|hi|lo)
-                ab_f3, dc_f3 = ops.split3(Wab, 1), ops.split3(Wdc, 1)
+            if exact_bn_mask():   # forward operands of the exact-mask forward: (hi|lo) for the bf16 input, (hi|hi|lo) for z
+                ab_f3, dc_f3 = hi_lo_cat(Wab), ops.split3(Wdc, 1)
         else:
             ab_f, dc_f = ops.split3(Wab, 1), ops.split3(Wdc, 1)
             ab_x = ops.split3(Wab, 2).view(3 * ldt, Cin)
             dc_x = ops.split3(Wdc, 2).view(3 * Cout, 3 * Cin)
-        out = dict(ldt=ldt, bab=bab, bdc=bdc, ab_f=ab_f, dc_f=dc_f, ab_x=ab_x, dc_x=dc_x, ab_f3=ab_f3, dc_f3=dc_f3)
+        out = dict(ldt=ldt, bab=bab, bdc=bdc, ab_f=ab_f, dc_f=dc_f, ab_x=ab_x, dc_x=dc_x, ab_f3=ab_f3, dc_f3=dc_f3, Wab32=Wab)
     slot["agcn_stack"] = (ver, out)
     return out
 
@@ -781,9 +804,14 @@ class AgcnFn(torch.autograd.Function):
                    and os.environ.get("AFB_AGCN_MMA", "1")[0] != "0")
         xs = None
         if exact:
-            x32 = ops.cast(x, torch.float32)
-            xs = ops.split3(x32, 0)
-            thph32 = ops.gemm_tn(xs, st["ab_f3"], ldt, bias=st["bab"], out_dtype=torch.float32)
+            can2 = Cin % 64 == 0      # two-tap form needs whole 64-column K blocks
+            x32 = None
+            if can2:
+                thph32 = gemm_hi_lo(x, st["ab_f3"], ldt, bias=st["bab"])
+            else:
+                x32 = ops.cast(x, torch.float32)
+                xs = ops.split3(x32, 0)
+                thph32 = ops.gemm_tn(xs, ops.split3(st["Wab32"], 1), ldt, bias=st["bab"], out_dtype=torch.float32)
             ops._call("afb_agcn_scores_fwd_mma" if use_mma else "afb_agcn_scores_fwd", ops.ptr(thph32), ops.dt(thph32), ldt, ops.ptr(A),
                       ops.ptr(PA.detach()), ops.ptr(P), ops.ptr(Mmat), N, T, V, IC, ops.stream())
             thph = ops.cast(thph32, torch.bfloat16)
@@ -793,6 +821,8 @@ class AgcnFn(torch.autograd.Function):
                 ops._call("afb_agcn_aggregate_fwd_mma", ops.ptr(x), ops.ptr(Mmat), ops.ptr(z), 1, N, T, V, Cin, ops.stream())
                 h_raw = ops.gemm_tn(z, st["dc_f3"], Cout, bias=st["bdc"], out_dtype=torch.float32)
             else:
+                if x32 is None:
+                    x32 = ops.cast(x, torch.float32)
                 z32 = torch.empty((M, 3 * Cin), device=x.device, dtype=torch.float32)
                 ops._call("afb_agcn_aggregate_fwd", ops.ptr(x32), ops.ptr(Mmat), ops.ptr(z32), ops.dt(x32), N, T, V, Cin, ops.stream())
                 h_raw = ops.gemm_tn(ops.split3(z32, 0), st["dc_f3"], Cout, bias=st["bdc"], out_dtype=torch.float32)
@@ -812,7 +842,10 @@ class AgcnFn(torch.autograd.Function):
         stats_h = _bn_forward(h_raw, bng, bnb, bufs[0], bufs[1], training, momentum, eps)
         if has_down:
             wdn, bdn, dng, dnb = params[20:24]
-            if exact:
+            if exact and Cin % 64 == 0:
+                d_raw = gemm_hi_lo(x, w_fwd2(wdn), Cout, bias=bdn.detach())
+            elif exact:
+                xs = xs if xs is not None else ops.split3(ops.cast(x, torch.float32), 0)
                 d_raw = ops.gemm_tn(xs, w_fwd3(wdn), Cout, bias=bdn.detach(), out_dtype=torch.float32)
                 xs = None
             else:
