@@ -342,6 +342,13 @@ int afb_motion_stream(const float* x, float* y, int N, int T, int V, afb_stream 
 /* y = x - x[:, 0, joint, :] per sequence: palm-centre normalisation (data_process/Hand_Dataset.py:61, joint = 1); out of place */
 int afb_palm_center(const float* x, float* y, int N, int T, int V, int joint, afb_stream s);
 int afb_axpby(const float* a, float wa, const float* b, float wb, float* out, int64_t n, afb_stream s);
+/* Phase tensors of a strided temporal convolution (Unit2D stride (s, 1), model/net.py:24-27; TCN_GCN_unit stride 2 and its
+ * down1, model/ST_TR/ST_TR_new.py:362-374).  scatter == 0: dst [N, To, V, C] = src[n, j * stride + phase, v, :] (zero past T);
+ * scatter == 1: dst [N, T, V, C] (frames j * stride + phase) = src [N, To, V, C]. */
+int afb_frame_phase(const void* src, void* dst, int dtype, int scatter, int N, int T, int To, int V, int C, int stride, int phase,
+                    afb_stream s);
+/* y = a * b elementwise (same dtype; n % 4 == 0): applies an explicit dropout mask, nn.Dropout of model/net.py:40,48 */
+int afb_mul(const void* a, const void* b, void* y, int dtype, int64_t n, afb_stream s);
 
 #ifdef __cplusplus
 }

@@ -280,12 +280,14 @@ def boundary_bf16(x):
     return x + (x.detach().bfloat16().to(x.dtype) - x.detach())
 
 
-def tcn_gcn_forward(x, p, prefix, A, training=False, boundary=None):
-    """tcn1(gcn1(x)) + x  (C_in == C_out, stride 1).  ST_TR_new.py:376-385."""
+def tcn_gcn_forward(x, p, prefix, A, training=False, boundary=None, stride=1):
+    """tcn1(gcn1(x)) + (x | down1(x)).  ST_TR_new.py:376-385; down1 = Unit2D(k=1, stride) exists when the channel count or
+    the stride changes (:369-374) -- present here iff its weights are in `p`."""
     h = agcn_forward(x, p, prefix + "gcn1.", A, training)
     if boundary is not None:
         h = boundary(h)
-    return unit2d_forward(h, p, prefix + "tcn1.", training) + x
+    res = unit2d_forward(x, p, prefix + "down1.", training, stride) if prefix + "down1.conv.weight" in p else x
+    return unit2d_forward(h, p, prefix + "tcn1.", training, stride) + res
 
 
 def mlp_forward(x, p, prefix):

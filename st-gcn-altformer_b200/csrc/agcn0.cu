@@ -894,20 +894,20 @@ __global__ void gcn0_bwd_fin1_kernel(const afb_gcn0_bwd_t b) {
 
 // pass 2 (one CTA per sample): dz -> dM -> dPA, dS -> Gram-form gradients of theta/phi
 template <typename TY, int CPL>
-__global__ void __launch_bounds__(kThreads) gcn0_bwd_dz_kernel(const afb_gcn0_bwd_t b) {
+__global__ void __launch_bounds__(kThreads) gcn0_bwd_dz_kernel(const afb_gcn0_bwd_t b, int TCK) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const afb_gcn0_fwd_t& p = b.f;
   const int V = p.V, T = p.T, Cout = p.Cout, n = blockIdx.x;
-  float* xs = reinterpret_cast<float*>(smraw);   // [T*V*3]
+  float* xs = reinterpret_cast<float*>(smraw);   // [T*V*3]   the whole sample (the Gram pass at the end needs every frame)
   float* Ms = xs + T * V * 3;                    // [3VV]
-  float* dM = Ms + 3 * V * V;                    // [3VV]
-  float* dz = dM + 3 * V * V;                    // [T*V][9]
-  float* cK = dz + T * V * 9;                    // c[9], pad to 16, K[81], E[12]
+  float* dM = Ms + 3 * V * V;                    // [3VV]     accumulated over the frame chunks
+  float* dz = dM + 3 * V * V;                    // [TCK*V][9] one chunk of TCK frames at a time (T = 180, V = 46 would need 300 KB)
+  float* cK = dz + TCK * V * 9;                  // c[9], pad to 16, K[81], E[12]
   float* red = cK + 16 + 96 + 16;                // [8][48]
   const float* xg = p.x + (int64_t)n * T * V * 3;
   for (int i = threadIdx.x; i < T * V * 3; i += blockDim.x) xs[i] = xg[i];
   const float* Mg = p.Mmat + (int64_t)n * 3 * V * V;
-  for (int i = threadIdx.x; i < 3 * V * V; i += blockDim.x) Ms[i] = Mg[i];
+  for (int i = threadIdx.x; i < 3 * V * V; i += blockDim.x) { Ms[i] = Mg[i]; dM[i] = 0.f; }
   for (int i = threadIdx.x; i < 16 + 96; i += blockDim.x) cK[i] = b.ws[ws_c(Cout) + i];
   if (threadIdx.x < 16) cK[16 + 96 + threadIdx.x] = threadIdx.x < NR ? p.stats[threadIdx.x] : 0.f;
   const float* cvec = cK;
@@ -922,11 +922,12 @@ __global__ void __launch_bounds__(kThreads) gcn0_bwd_dz_kernel(const afb_gcn0_bw
   __syncthreads();
   const TY* dy = reinterpret_cast<const TY*>(b.dy) + (int64_t)n * T * V * Cout;
   const TY* y = reinterpret_cast<const TY*>(p.y) + (int64_t)n * T * V * Cout;
-  // centred z of every position, all threads (the old per-position recompute ran on 9 lanes, 22 serial steps each);
-  // it is parked in dz[] and replaced by the finished dz below
-  for (int it = threadIdx.x; it < T * V * 3; it += blockDim.x) {
+  for (int t0 = 0; t0 < T; t0 += TCK) {
+  const int tc = min(TCK, T - t0), npos = tc * V;
+  // centred z of every position of the chunk, all threads; it is parked in dz[] and replaced by the finished dz below
+  for (int it = threadIdx.x; it < npos * 3; it += blockDim.x) {
     const int pos = it / 3, i = it % 3, tl = pos / V, v = pos % V;
-    const float* xt = xs + tl * V * 3;
+    const float* xt = xs + (t0 + tl) * V * 3;
     float z0 = 0.f, z1 = 0.f, z2 = 0.f;
     for (int u = 0; u < V; ++u) {
       const float m = Ms[(i * V + u) * V + v];
@@ -937,16 +938,16 @@ __global__ void __launch_bounds__(kThreads) gcn0_bwd_dz_kernel(const afb_gcn0_bw
   __syncthreads();
   // dz[pos][j] = sum_c relu'(y) dy[pos][c] U[c][j] - c_j - sum_k zc_k K[k][j]; two positions per warp step so both
   // rows' loads are in flight together
-  for (int pos0 = warp * 2; pos0 < T * V; pos0 += 2 * (kThreads / 32)) {
+  for (int pos0 = warp * 2; pos0 < npos; pos0 += 2 * (kThreads / 32)) {
     float part[2][9];
     float yv[2][CPL], gv[2][CPL];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int pos = min(pos0 + h, T * V - 1);
+      const int64_t gpos = (int64_t)t0 * V + min(pos0 + h, npos - 1);
 #pragma unroll
       for (int q = 0; q < CPL; q += 2) {
-        ld2f<TY>(y + (int64_t)pos * Cout + lane * CPL + q, yv[h][q], yv[h][q + 1]);
-        ld2f<TY>(dy + (int64_t)pos * Cout + lane * CPL + q, gv[h][q], gv[h][q + 1]);
+        ld2f<TY>(y + gpos * Cout + lane * CPL + q, yv[h][q], yv[h][q + 1]);
+        ld2f<TY>(dy + gpos * Cout + lane * CPL + q, gv[h][q], gv[h][q + 1]);
       }
     }
 #pragma unroll
@@ -965,7 +966,7 @@ __global__ void __launch_bounds__(kThreads) gcn0_bwd_dz_kernel(const afb_gcn0_bw
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int pos = pos0 + h;
-      if (pos < T * V && lane < 9) {
+      if (pos < npos && lane < 9) {
         float corr = 0.f;
 #pragma unroll
         for (int k = 0; k < 9; ++k) corr = fmaf(dz[pos * 9 + k], Kmat[k * 9 + lane], corr);
@@ -978,18 +979,20 @@ __global__ void __launch_bounds__(kThreads) gcn0_bwd_dz_kernel(const afb_gcn0_bw
     }
   }
   __syncthreads();
-  // dM_i[u][v] = sum_{t,a} x[t,u,a] * dz[(t,v)][3i+a]
+  // dM_i[u][v] += sum_{t in chunk, a} x[t,u,a] * dz[(t,v)][3i+a]
   for (int e = threadIdx.x; e < 3 * V * V; e += blockDim.x) {
     const int i = e / (V * V), u = (e / V) % V, v = e % V;
     float s = 0.f;
-    for (int t = 0; t < T; ++t) {
-      const float* xu = xs + (t * V + u) * 3;
+    for (int t = 0; t < tc; ++t) {
+      const float* xu = xs + ((t0 + t) * V + u) * 3;
       const float* d = dz + (t * V + v) * 9 + i * 3;
       s += xu[0] * d[0] + xu[1] * d[1] + xu[2] * d[2];
     }
-    dM[e] = s;
-    atomicAdd(b.dPA + e, s);
+    dM[e] += s;
   }
+  __syncthreads();   // the next chunk overwrites dz
+  }
+  for (int e = threadIdx.x; e < 3 * V * V; e += blockDim.x) atomicAdd(b.dPA + e, dM[e]);
   __syncthreads();
   // dS = P * (dM - sum_u P*dM) per column (i, v);  P = M - (A + PA)
   for (int col = threadIdx.x; col < 3 * V; col += blockDim.x) {
@@ -1193,12 +1196,16 @@ extern "C" int afb_gcn0_bwd(const afb_gcn0_bwd_t* b, afb_stream s) {
   gcn0_bwd_fin1_kernel<<<1, 256, (size_t)Cout * 12 * sizeof(float), st>>>(*b);
   if ((rc = check_launch("gcn0_bwd_fin1"))) return rc;
   {
-    const size_t smem = ((size_t)T * V * 3 + 6 * V * V + (size_t)T * V * 9 + 16 + 96 + 16 + 8 * 48) * sizeof(float);
-    AFB_REQUIRE(smem <= 220 * 1024, "gcn0_bwd: T*V too large for the per-sample shared-memory stage (%zu B)", smem);
+    // the sample's x stays whole in shared memory; dz is processed in chunks of TCK frames sized to the budget
+    const size_t fixed = ((size_t)T * V * 3 + 6 * V * V + 16 + 96 + 16 + 8 * 48) * sizeof(float);
+    AFB_REQUIRE(fixed + (size_t)V * 9 * sizeof(float) <= 200 * 1024, "gcn0_bwd: T*V too large for the per-sample shared-memory stage (%zu B)", fixed);
+    int TCK = (int)((200 * 1024 - fixed) / ((size_t)V * 9 * sizeof(float)));
+    if (TCK > T) TCK = T;
+    const size_t smem = fixed + (size_t)TCK * V * 9 * sizeof(float);
 #define LAUNCH_DZ(TYPE, CPL_)                                                              \
   do {                                                                                     \
     if ((rc = set_smem(gcn0_bwd_dz_kernel<TYPE, CPL_>, smem, "gcn0_bwd_dz"))) return rc;   \
-    gcn0_bwd_dz_kernel<TYPE, CPL_><<<p->N, kThreads, smem, st>>>(*b);                      \
+    gcn0_bwd_dz_kernel<TYPE, CPL_><<<p->N, kThreads, smem, st>>>(*b, TCK);                 \
   } while (0)
     const int cpl = Cout / 32;
     AFB_REQUIRE(cpl == 2 || cpl == 4 || cpl == 8, "gcn0_bwd: Cout=%d unsupported (64, 128 or 256)", Cout);

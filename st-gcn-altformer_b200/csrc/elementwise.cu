@@ -654,6 +654,38 @@ __global__ void motion_kernel(const float* __restrict__ x, float* __restrict__ y
     y[i] = t + 1 < T ? x[i + frame] - x[i] : 0.f;
   }
 }
+// strided temporal convolution = sum over phases of stride-1 convolutions on phase tensors:
+//   gather : y[n, j, v, :] = x[n, j * stride + phase, v, :]  (zero when that frame is >= T)      y: [N, To, V, C]
+//   scatter: x[n, j * stride + phase, v, :] = y[n, j, v, :]  for the frames that exist           (inverse, backward pass)
+template <typename T, bool SCATTER>
+__global__ void __launch_bounds__(kBlock) frame_phase_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int Tn, int To, int V,
+                                                             int C, int stride, int phase) {
+  const int c4n = C >> 2;
+  const int64_t total = (int64_t)N * To * V * c4n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4n);
+    const int64_t r = i / c4n;                 // (n, j, v) row of the phase tensor
+    const int v = (int)(r % V);
+    const int j = (int)((r / V) % To);
+    const int n = (int)(r / ((int64_t)V * To));
+    const int f = j * stride + phase;
+    const int64_t full = (((int64_t)n * Tn + f) * V + v) * C + 4 * c4, ph = r * C + 4 * c4;
+    if (SCATTER) {
+      if (f < Tn) st4<T>(dst + full, ld4<T>(src + ph));
+    } else {
+      st4<T>(dst + ph, f < Tn ? ld4<T>(src + full) : make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+}
+
+// y = a * b elementwise, 4 elements per thread (dropout mask application, net.py:48)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) mul_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 u = ld4<T>(a + 4 * i), v = ld4<T>(b + 4 * i);
+    st4<T>(y + 4 * i, make_float4(u.x * v.x, u.y * v.y, u.z * v.z, u.w * v.w));
+  }
+}
 __global__ void axpby_kernel(const float* __restrict__ a, float wa, const float* __restrict__ b, float wb, float* __restrict__ out,
                              int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -965,6 +997,23 @@ extern "C" int afb_palm_center(const float* x, float* y, int N, int T, int V, in
   const int64_t per_seq = (int64_t)T * V * 3;
   palm_center_kernel<<<grid_for(N * per_seq, kBlock), kBlock, 0, as_stream(s)>>>(x, y, N * per_seq, per_seq, joint);
   return check_launch("palm_center");
+}
+extern "C" int afb_frame_phase(const void* src, void* dst, int dt, int scatter, int N, int T, int To, int V, int C, int stride, int phase,
+                               afb_stream s) {
+  AFB_REQUIRE(src && dst && N > 0 && T > 0 && To > 0 && V > 0 && C % 4 == 0 && stride >= 1 && phase >= 0 && phase < stride,
+              "frame_phase: bad args");
+  const int g = grid_for((int64_t)N * To * V * (C / 4), kBlock);
+  if (scatter) {
+    DISPATCH_DT(dt, T_, (frame_phase_kernel<T_, true><<<g, kBlock, 0, as_stream(s)>>>((const T_*)src, (T_*)dst, N, T, To, V, C, stride, phase)));
+  } else {
+    DISPATCH_DT(dt, T_, (frame_phase_kernel<T_, false><<<g, kBlock, 0, as_stream(s)>>>((const T_*)src, (T_*)dst, N, T, To, V, C, stride, phase)));
+  }
+  return check_launch("frame_phase");
+}
+extern "C" int afb_mul(const void* a, const void* b, void* y, int dt, int64_t n, afb_stream s) {
+  AFB_REQUIRE(a && b && y && n > 0 && n % 4 == 0, "mul: bad args (n must be a multiple of 4)");
+  DISPATCH_DT(dt, T, (mul_kernel<T><<<grid_for(n / 4, kBlock), kBlock, 0, as_stream(s)>>>((const T*)a, (const T*)b, (T*)y, n / 4)));
+  return check_launch("mul");
 }
 extern "C" int afb_axpby(const float* a, float wa, const float* b, float wb, float* out, int64_t n, afb_stream s) {
   AFB_REQUIRE(a && b && out && n > 0, "axpby: bad args");

@@ -517,42 +517,101 @@ def _bn_forward(raw, bn_w, bn_b, rm, rv, training, momentum, eps):
     return ops.bn_finalize(acc, M, bn_w.detach(), bn_b.detach(), rm, rv, momentum, eps, training)
 
 
+def conv_out_frames(T, k, stride):
+    """frames produced by Conv2d((k,1), padding ((k-1)//2, 0), stride (stride,1)) -- model/net.py:19-27"""
+    return (T + 2 * ((k - 1) // 2) - k) // stride + 1
+
+
+def _phase_plan(k, stride):
+    """Strided k x 1 convolution as a sum of stride-1 convolutions on phase tensors: tap q = tap - pad = o*stride + phase reads
+    x_phase[t' + o].  Returns [(phase, [taps in order of increasing o], o_min)] for the phases that own a tap."""
+    pad = (k - 1) // 2
+    plan = []
+    for phase in range(stride):
+        taps = [t for t in range(k) if (t - pad) % stride == phase]
+        if taps:
+            plan.append((phase, taps, (taps[0] - pad - phase) // stride))
+    return plan
+
+
+def _sub_packs(conv_w, taps):
+    """(fwd, fwd_lo or None, bwd) GEMM operands of the sub-kernel made of `taps` (tiny tensors: torch indexing is layout plumbing)."""
+    w = conv_w.detach()[:, :, taps, :].contiguous()
+    co, ci, kk = w.shape[:3]
+    if _PRECISION[0] == "bf16":
+        fwd, bwd = ops.conv_weight_pack(w)
+        lo = None
+        if exact_bn_mask():
+            hi32 = ops.cast(ops.cast(w, torch.bfloat16), torch.float32)
+            lo = ops.conv_weight_pack(ops.axpby(w, 1.0, hi32, -1.0))[0]
+        return fwd, lo, bwd
+    w3 = w.reshape(co, ci, kk)
+    f32_fwd = w3.permute(0, 2, 1).contiguous().view(co * kk, ci)
+    f32_bwd = w3.flip(2).permute(1, 2, 0).contiguous().view(ci * kk, co)
+    return ops.split3(f32_fwd, 1).view(co, kk * 3 * ci), None, ops.split3(f32_bwd, 1).view(ci, kk * 3 * co)
+
+
 class Unit2DFn(torch.autograd.Function):
     """x tokens [N*T*V, Cin] -> relu(bn(conv_kx1(x))) (+ res_post); optionally also the (n,v,t)-ordered
-    copy the TS stage consumes.  model/net.py:47-57."""
+    copy the TS stage consumes.  model/net.py:47-57.  stride > 1 (net.py:24-27): the output has conv_out_frames(T) frames;
+    the convolution runs as one implicit GEMM per phase tensor (see _phase_plan), all accumulating into one pre-activation."""
 
     @staticmethod
-    def forward(ctx, x, dims, conv_w, conv_b, bn_w, bn_b, rm, rv, training, momentum, eps, res_post, want_perm):
+    def forward(ctx, x, dims, conv_w, conv_b, bn_w, bn_b, rm, rv, training, momentum, eps, res_post, want_perm, stride=1):
         N, T, V = dims
         x = _as_act(x)
         co, ci, k = conv_w.shape[:3]
-        fwd_w, _ = conv_packs(conv_w)
         three = 1 if get_precision() == "bf16" else 3
-        a = x if three == 1 else ops.split3(x, 0)
         exact = exact_bn_mask()
-        geo = dict(k_per_tap=three * ci, taps=k, tap_row_stride=V, tap_pad=(k - 1) // 2, rows_per_batch=T * V, batches=N)
-        raw = ops.gemm_tn(a, fwd_w, co, bias=None if conv_b is None else conv_b.detach(),
-                          out_dtype=torch.float32 if exact else act_dtype(), **geo)
-        if exact:   # + x * (w - bf16(w)): the pre-activation is now the fp32 conv of the bf16 activations
-            ops.gemm_tn(a, conv_pack_lo(conv_w), co, residual=raw, out=raw, out_dtype=torch.float32, **geo)
+        bias = None if conv_b is None else conv_b.detach()
+        To = conv_out_frames(T, k, stride)
+        if stride == 1:
+            fwd_w, _ = conv_packs(conv_w)
+            a = x if three == 1 else ops.split3(x, 0)
+            geo = dict(k_per_tap=three * ci, taps=k, tap_row_stride=V, tap_pad=(k - 1) // 2, rows_per_batch=T * V, batches=N)
+            raw = ops.gemm_tn(a, fwd_w, co, bias=bias, out_dtype=torch.float32 if exact else act_dtype(), **geo)
+            if exact:   # + x * (w - bf16(w)): the pre-activation is now the fp32 conv of the bf16 activations
+                ops.gemm_tn(a, conv_pack_lo(conv_w), co, residual=raw, out=raw, out_dtype=torch.float32, **geo)
+            phases = None
+        else:
+            raw, phases = None, []
+            for phase, taps, o_min in _phase_plan(k, stride):
+                xp = ops.frame_gather(x, N, T, To, V, stride, phase)
+                fwd_w, lo_w, _ = _sub_packs(conv_w, taps)
+                a = xp if three == 1 else ops.split3(xp, 0)
+                geo = dict(k_per_tap=three * ci, taps=len(taps), tap_row_stride=V, tap_pad=-o_min, rows_per_batch=To * V, batches=N)
+                if len(taps) == 1:   # a single tap needs no K blocking by taps (k_per_tap may then be any multiple of 8)
+                    geo.update(taps=1, tap_row_stride=0, tap_pad=0)
+                    if o_min != 0:
+                        raise RuntimeError("altformer_b200.Unit2D: a single-tap phase with a frame offset is not built")
+                for w_op in ((fwd_w, lo_w) if lo_w is not None else (fwd_w,)):
+                    if raw is None:
+                        raw = ops.gemm_tn(a, w_op, co, bias=bias, out_dtype=torch.float32 if exact else act_dtype(), **geo)
+                    else:
+                        ops.gemm_tn(a, w_op, co, residual=raw, out=raw, out_dtype=raw.dtype, **geo)
+                phases.append(xp)
         stats = _bn_forward(raw, bn_w, bn_b, rm, rv, training, momentum, eps)
-        y, y2 = ops.bn_act_fwd(raw, stats[2], stats[3], True, res_post=res_post, T=T, V=V, want_perm=want_perm,
+        y, y2 = ops.bn_act_fwd(raw, stats[2], stats[3], True, res_post=res_post, T=To, V=V, want_perm=want_perm,
                                out_dtype=act_dtype())
-        ctx.save_for_backward(x, raw, stats, conv_w, conv_b, bn_w, bn_b)
-        ctx.cfg = (N, T, V, training, res_post is not None, want_perm)
+        if phases is None:
+            ctx.save_for_backward(x, raw, stats, conv_w, conv_b, bn_w, bn_b)
+        else:
+            ctx.save_for_backward(x, raw, stats, conv_w, conv_b, bn_w, bn_b, *phases)
+        ctx.cfg = (N, T, V, training, res_post is not None, want_perm, stride, To)
         if want_perm:
             return y, y2
         return y
 
     @staticmethod
     def backward(ctx, dy, dy2=None):
-        x, raw, stats, conv_w, conv_b, bn_w, bn_b = ctx.saved_tensors
-        N, T, V, training, has_res, want_perm = ctx.cfg
+        x, raw, stats, conv_w, conv_b, bn_w, bn_b = ctx.saved_tensors[:7]
+        phases = ctx.saved_tensors[7:]
+        N, T, V, training, has_res, want_perm, stride, To = ctx.cfg
         co, ci, k = conv_w.shape[:3]
         dy = None if dy is None else _as_act(dy.contiguous())
         dy2 = None if dy2 is None else _as_act(dy2.contiguous())
         sg, sb = _grad_sink(bn_w), _grad_sink(bn_b)
-        draw, _ = ops.bn_bwd(dy, dy2, raw, stats, bn_w.detach(), bn_b.detach(), True, training, sg[0], sb[0], T=T, V=V)
+        draw, _ = ops.bn_bwd(dy, dy2, raw, stats, bn_w.detach(), bn_b.detach(), True, training, sg[0], sb[0], T=To, V=V)
         gcb, scb = None, None
         if conv_b is not None:   # bias gradient = column sums of draw: rides on the first weight-gradient launch
             scb = _grad_sink(conv_b)
@@ -561,6 +620,29 @@ class Unit2DFn(torch.autograd.Function):
         sw = _grad_sink(conv_w)
         flat = sw[0].view(-1)
         pad = (k - 1) // 2
+        three = 1 if get_precision() == "bf16" else 3
+        if stride != 1:
+            # dW[:, :, tap] = sum_rows draw[row]^T x_phase[row + o V];  dx_phase = sum_taps draw[row - o V] W[:, :, tap]
+            plan = _phase_plan(k, stride)
+            dx = None
+            if ctx.needs_input_grad[0]:   # frames of a phase no tap reads (k < stride, e.g. the 1 x 1 down1) get zero gradient
+                dx = torch.empty_like(x) if len(plan) == stride else torch.zeros_like(x)
+            first = True
+            for (phase, taps, o_min), xp in zip(plan, phases):
+                for j, tap in enumerate(taps):
+                    mm_dw(draw, xp, flat[tap:], N1=co, N2=ci, rows_per_batch=To * V, batches=N, ld1=ci * k, ld2=k,
+                          x_row_shift=(o_min + j) * V, dbias=db if first else None)
+                    first = False
+                if dx is not None:
+                    _, _, bwd_w = _sub_packs(conv_w, taps)
+                    g = draw if three == 1 else ops.split3(draw, 0)
+                    geo = dict(k_per_tap=three * co, taps=len(taps), tap_row_stride=V, tap_pad=o_min + len(taps) - 1,
+                               rows_per_batch=To * V, batches=N)
+                    if len(taps) == 1:
+                        geo.update(taps=1, tap_row_stride=0, tap_pad=0)
+                    dxp = ops.gemm_tn(g, bwd_w, ci, out_dtype=act_dtype(), **geo)
+                    ops.frame_scatter(dxp, dx, N, T, To, V, stride, phase)
+            return dx, None, _ret(sw), gcb, _ret(sg), _ret(sb), None, None, None, None, None, (dy if has_res else None), None, None
         # dW[co, ci, tap] = sum_rows draw[row, co] * x[row + (tap - pad) V, ci]
         if co <= 128 and ci <= 128 and ci % 64 == 0:
             # three taps per launch share every dY tile; the tap-major scratch keeps gradient rows contiguous
@@ -579,15 +661,14 @@ class Unit2DFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             _, bwd_w = conv_packs(conv_w)
-            three = 1 if get_precision() == "bf16" else 3
             g = draw if three == 1 else ops.split3(draw, 0)
             dx = ops.gemm_tn(g, bwd_w, ci, k_per_tap=three * co, taps=k, tap_row_stride=V, tap_pad=pad,
                              rows_per_batch=T * V, batches=N, out_dtype=act_dtype())
-        return dx, None, _ret(sw), gcb, _ret(sg), _ret(sb), None, None, None, None, None, (dy if has_res else None), None
+        return dx, None, _ret(sw), gcb, _ret(sg), _ret(sb), None, None, None, None, None, (dy if has_res else None), None, None
 
 
-def unit2d(x, dims, conv_w, conv_b, bn_w, bn_b, rm, rv, training, momentum, eps, res_post=None, want_perm=False):
-    return Unit2DFn.apply(x, dims, conv_w, conv_b, bn_w, bn_b, rm, rv, training, momentum, eps, res_post, want_perm)
+def unit2d(x, dims, conv_w, conv_b, bn_w, bn_b, rm, rv, training, momentum, eps, res_post=None, want_perm=False, stride=1):
+    return Unit2DFn.apply(x, dims, conv_w, conv_b, bn_w, bn_b, rm, rv, training, momentum, eps, res_post, want_perm, stride)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -938,6 +1019,27 @@ def to_act(x):
     """Bring a tensor to the activation dtype of the current precision mode (tracked by autograd)."""
     want = act_dtype()
     return x if x.dtype == want else CastFn.apply(x, want)
+
+
+class DropoutFn(torch.autograd.Function):
+    """y = x * mask with an explicit mask (values 0 or 1 / (1 - p)): nn.Dropout in training mode (model/net.py:40,48).
+    The mask is a tensor so parity tests can pin it; the module draws it with torch's RNG."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        x = _as_act(x)
+        mask = mask if mask.dtype == x.dtype else ops.cast(mask.contiguous(), x.dtype)
+        ctx.save_for_backward(mask)
+        return ops.mul(x.contiguous(), mask.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return ops.mul(_as_act(g.contiguous()), mask), None
+
+
+def dropout(x, mask):
+    return DropoutFn.apply(x, mask)
 
 
 class ScaleRowsFn(torch.autograd.Function):

@@ -26,21 +26,34 @@ class Unit2D(nn.Module):
         self.relu = nn.ReLU()
         self.dropout = nn.Dropout(dropout, inplace=False)
         self.dim, self.stride, self.p_drop = dim, stride, dropout
+        self.pinned_dropout_mask = None     # tests: a (rows, D_in) tensor used instead of a fresh draw
         conv_init(self.conv)
 
+    def dropout_mask(self, tok):
+        """Inverted-dropout mask as nn.Dropout applies it (net.py:40,48): Bernoulli(1 - p) / (1 - p) per element."""
+        if self.pinned_dropout_mask is not None:
+            return self.pinned_dropout_mask
+        keep = 1.0 - self.p_drop
+        return torch.empty(tok.shape, device=tok.device, dtype=torch.float32).bernoulli_(keep).div_(keep)  # RNG plumbing
+
+    def out_dims(self, dims):
+        """(N, T, V) of the output tokens: stride (s, 1) shortens the frame axis (net.py:24-27)."""
+        N, T, V = dims
+        return N, AF.conv_out_frames(T, self.conv.kernel_size[0], self.stride), V
+
     def forward_tokens(self, tok, dims, res_post=None, want_perm=False):
-        if self.dim != 2 or self.stride != 1:
-            raise RuntimeError("altformer_b200.Unit2D: only dim=2, stride=1 (the AltFormer / agcn-stack use) is built")
+        if self.dim != 2:
+            raise RuntimeError("altformer_b200.Unit2D: dim=3 (convolution along the joints, unused by the AltFormer / ST-GCN stacks) is not built")
         if self.p_drop > 0 and self.training:
-            raise RuntimeError("altformer_b200.Unit2D: training-mode dropout > 0 is not built (AltFormer uses dropout=0)")
+            tok = AF.dropout(tok, self.dropout_mask(tok))
         if self.training and self.bn.track_running_stats:
             self.bn.num_batches_tracked += 1
         return AF.unit2d(tok, dims, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias, self.bn.running_mean,
-                         self.bn.running_var, self.training, self.bn.momentum, self.bn.eps, res_post, want_perm)
+                         self.bn.running_var, self.training, self.bn.momentum, self.bn.eps, res_post, want_perm, self.stride)
 
     def forward(self, x):
         tok, dims = to_tokens(x)
-        return from_tokens(self.forward_tokens(tok, dims), dims)
+        return from_tokens(self.forward_tokens(tok, dims), self.out_dims(dims))
 
 
 def conv_init(module):

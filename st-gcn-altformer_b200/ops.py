@@ -356,6 +356,31 @@ def bone_stream(x, parent):
     return y
 
 
+def frame_gather(x, N, T, To, V, stride, phase):
+    """tokens [N*T*V, C] -> phase tensor [N*To*V, C]: frame j holds frame j*stride+phase of x (zeros past T)."""
+    need_cuda(x)
+    C_ = x.shape[1]
+    y = torch.empty((N * To * V, C_), device=x.device, dtype=x.dtype)
+    _call("afb_frame_phase", ptr(x), ptr(y), dt(x), 0, N, T, To, V, C_, stride, phase, stream())
+    return y
+
+
+def frame_scatter(yp, out, N, T, To, V, stride, phase):
+    """inverse of frame_gather into the preallocated tokens `out` [N*T*V, C] (only the frames of this phase are written)."""
+    need_cuda(yp, out)
+    _call("afb_frame_phase", ptr(yp), ptr(out), dt(yp), 1, N, T, To, V, yp.shape[1], stride, phase, stream())
+    return out
+
+
+def mul(a, b):
+    need_cuda(a, b)
+    if a.dtype != b.dtype or a.numel() != b.numel():
+        raise RuntimeError("mul: operands must have the same dtype and size")
+    y = torch.empty_like(a)
+    _call("afb_mul", ptr(a), ptr(b), ptr(y), dt(a), a.numel(), stream())
+    return y
+
+
 def palm_center(x, joint=1):
     need_cuda(x)
     N, T, V, _ = x.shape
