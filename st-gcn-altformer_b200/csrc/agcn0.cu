@@ -852,6 +852,34 @@ __global__ void gcn0_bwd_fin1_kernel(const afb_gcn0_bwd_t b) {
     float dgam = 0.f, dgam_d = 0.f;
     for (int j = 0; j < 9; ++j) dgam += w[j] * Q[j];
     for (int j = 9; j < 12; ++j) dgam_d += w[j] * Q[j];
+    if (!p.training) {
+      // running-statistics BatchNorm (eval): h - rm = w.(r - E) + (ctr - rm) with ctr = w.E + b the pre-BN value at the
+      // centre the Q sums were taken around (E = 0 after the fused forward, the batch mean after the two-kernel one);
+      // mean and variance are constants, so no statistics terms: dW_j = g rstd sum g1 r_j, db = g rstd dbeta
+      float ctr_h = p.bd[0][o] + p.bd[1][o] + p.bd[2][o], ctr_d = p.bdn[o];
+      for (int j = 0; j < 9; ++j) ctr_h += w[j] * E[j];
+      for (int j = 9; j < 12; ++j) ctr_d += w[j] * E[j];
+      const float mean_h = p.stats[NSTAT + o], mean_d = p.stats[NSTAT + 2 * Cout + o];
+      dgam = (dgam + (ctr_h - mean_h) * dbeta) * rstd_h;
+      dgam_d = (dgam_d + (ctr_d - mean_d) * dbeta) * rstd_d;
+      atomicAdd(b.dbn_g + o, dgam);
+      atomicAdd(b.dbn_b + o, dbeta);
+      atomicAdd(b.ddn_g + o, dgam_d);
+      atomicAdd(b.ddn_b + o, dbeta);
+      for (int j = 0; j < 9; ++j) atomicAdd(b.dWd[j / 3] + o * 3 + (j % 3), ga * rstd_h * (Q[j] + E[j] * dbeta));
+      for (int j = 9; j < 12; ++j) atomicAdd(b.dWdn + o * 3 + (j - 9), gd * rstd_d * (Q[j] + E[j] * dbeta));
+      for (int i = 0; i < 3; ++i) atomicAdd(b.dbd[i] + o, ga * rstd_h * dbeta);
+      atomicAdd(b.dbdn + o, gd * rstd_d * dbeta);
+      float* U = b.ws + ws_U(Cout) + o * 16;
+      for (int j = 0; j < 9; ++j) {
+        U[j] = ga * rstd_h * w[j];
+        shm[o * 12 + j] = w[j];
+      }
+      for (int j = 9; j < 16; ++j) U[j] = 0.f;
+      shm[o * 12 + 9] = 0.f;    // no K / c corrections: the statistics do not depend on the batch
+      shm[o * 12 + 10] = 0.f;
+      continue;
+    }
     dgam *= rstd_h;
     dgam_d *= rstd_d;
     atomicAdd(b.dbn_g + o, dgam);
@@ -1175,7 +1203,6 @@ extern "C" int afb_gcn0_bwd(const afb_gcn0_bwd_t* b, afb_stream s) {
   const afb_gcn0_fwd_t* p = &b->f;
   int rc = check_fwd_args(p);
   if (rc) return rc;
-  AFB_REQUIRE(p->training, "gcn0_bwd: only training-mode BatchNorm is differentiated");
   AFB_REQUIRE(kThreads % p->Cout == 0 || p->Cout == 256, "gcn0_bwd: Cout=%d unsupported", p->Cout);
   cudaStream_t st = as_stream(s);
   const int T = p->T, V = p->V, Cout = p->Cout;

@@ -121,7 +121,7 @@ def _tols(mode, bn):
 
 # --------------------------------------------------------------------------------------------
 def grp_gcn0():
-    def case(N, T, V, training, mode, seed):
+    def case(N, T, V, training, mode, seed, eval_bwd=False):
         with precision(mode):
             ftol, _, gtol = _tols(mode, True)
             tiny = N * T * V < 2000   # tiny batches: BN statistics over < 2000 positions amplify rounding (and single
@@ -138,6 +138,11 @@ def grp_gcn0():
             y = mod(x.to(DEV).permute(0, 3, 1, 2))
             tag = f"gcn0 N={N} T={T} V={V} train={training} {mode}"
             report(tag + " fwd", y.float(), yr, ftol)
+            if eval_bwd:   # running-statistics BatchNorm differentiated (fine-tuning with frozen statistics)
+                (y.float() * cot.to(DEV)).sum().backward()
+                # bf16: 1.5e-2 -- the theta/phi bias gradients are ~1e-3 of their weight gradients and sums of cancelling terms
+                # (worst tensor conv_b.0.bias 1.4e-2, every other tensor <= 7e-3)
+                grad_report(tag + " eval-mode", mod, params, 1.5e-2 if mode == "bf16" else gtol, training=False, l2_only=mode == "bf16" or tiny)
             if training:
                 (y.float() * cot.to(DEV)).sum().backward()
                 grad_report(tag, mod, params, gtol, l2_only=mode == "bf16" or tiny)
@@ -151,6 +156,8 @@ def grp_gcn0():
                  # the reference's LMDHG default (LMDHG_sttran.py: num_frame = 180, 46 joints): backward processes dz in frame chunks
                  (2, 180, 46, True, "fp32", 17), (2, 180, 46, True, "bf16", 17)):
         check(lambda a=args: case(*a))
+    for args in ((4, 8, 22, False, "fp32", 21), (16, 32, 22, False, "bf16", 22), (3, 6, 46, False, "fp32", 23), (3, 12, 46, False, "bf16", 23)):
+        check(lambda a=args: case(*a, eval_bwd=True))
 
 
 def grp_modules():
