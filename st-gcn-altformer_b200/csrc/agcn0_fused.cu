@@ -578,10 +578,10 @@ __global__ void __launch_bounds__(kThreads, 2) gcn0_fused_kernel(const __grid_co
   stamp(0);
 
   // ---- prologue: every global read of the first sample is requested up front (one exposed miss latency) -----------
-  if (tid == 0) {
-    s_gen = training ? ld_acquire_u32(fa.ctrl + 1) : 0u;
-    s_par = training ? ld_acquire_u32(fa.ctrl + 2) : 0u;
-  }
+  // (the two control words were published by the previous launch; two different warps read them so neither load waits for
+  // the other, and thread 0 is left free to issue the sample's bulk copy first)
+  if (tid == 32) s_gen = training ? ld_acquire_u32(fa.ctrl + 1) : 0u;
+  if (tid == 64) s_par = training ? ld_acquire_u32(fa.ctrl + 2) : 0u;
   // x[n] (T*V*12 contiguous bytes) -> shared memory by ONE bulk copy issued before anything else: S1 then reads it at
   // shared-memory latency instead of paying an L2 round trip per round.  (16-byte size / alignment: else direct loads.)
   __shared__ __align__(8) unsigned long long xbar;
