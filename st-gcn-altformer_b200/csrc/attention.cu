@@ -12,6 +12,9 @@ namespace afb {
 // tensor-core path (attention_mma.cu)
 bool attention_mma_supported(int L, int heads, int dh);
 int attention_fwd_mma(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, const float* out_scale, cudaStream_t st);
+bool attention_tc_supported(int L, int heads, int dh);
+int attention_fwd_tc(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, const float* out_scale, int variant,
+                     cudaStream_t st);
 int attention_bwd_mma(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st);
 
 namespace {
@@ -360,6 +363,13 @@ extern "C" int afb_attention_fwd(const void* qkv, void* o, int dt, int64_t B, in
       attn_long_fwd_kernel<float><<<(unsigned)(B * heads), kLongWarps * 32, smem, as_stream(s)>>>((const float*)qkv, (float*)o, L, heads, dh, scale, out_scale);
     }
     return check_launch("attention_long_fwd");
+  }
+  // AFB_ATTN_TC (read per call so one process can compare the paths): 1 = tcgen05 / TMEM / TMA forward (attention_tc.cu),
+  // 2 = its whole-box P V variant, unset / 0 = warp-level MMA forward (attention_mma.cu)
+  if (dt == AFB_BF16 && attention_tc_supported(L, heads, dh)) {
+    const char* tc = getenv("AFB_ATTN_TC");
+    if (tc != nullptr && (tc[0] == '1' || tc[0] == '2'))
+      return attention_fwd_tc(qkv, o, B, L, heads, dh, scale, out_scale, tc[0] == '2' ? 1 : 0, as_stream(s));
   }
   if (use_mma(dt, L, heads, dh)) return attention_fwd_mma(qkv, o, B, L, heads, dh, scale, out_scale, as_stream(s));
   const int per_warp = 3 * L * (dh + 1) + L + 3;

@@ -1,0 +1,450 @@
+// Short-sequence multi-head attention forward on the Blackwell paths: TMA loads, tcgen05.mma with the scores and the
+// output in TMEM, softmax out of tcgen05.ld, TMA stores.  (reference: model/AltFormer/model_ST.py:49-67, q @ k^T -> softmax
+// -> @ v per (sequence, head); L = 22 joints / 32 frames on SHREC, 46 / 64 on LMDHG.)
+//
+// One problem is far smaller than an MMA (22 x 22 scores per head), so G = 128 / LP sequences are PACKED into one
+// 128-row tile, each padded to LP = 32 or 64 rows:
+//   * the TMA box is (64 feature columns = one 128-byte swizzle span = two heads at dh 32, LP rows, G sequences) of the
+//     3-D view (3D features, L tokens, B sequences) of qkv: rows l >= L of every sequence are out of bounds in the token
+//     dimension and arrive as ZEROS, so the padded tile needs no masking of q / k / v and the token rows of sequence g sit
+//     at tile rows g*LP .. g*LP + L - 1;
+//   * S = Q K^T is ONE tcgen05.mma chain per head (M = 128, N = 128, K = dh): only the G diagonal LP x LP blocks mean
+//     anything (the tensor pipe is otherwise idle in this HBM-bound kernel, the G-fold redundant FLOPs are free);
+//   * tile row r = TMEM lane r, and the keys of ITS sequence are the LP consecutive TMEM columns (r / LP) * LP ..: each
+//     softmax warp owns one lane quarter, so its 32 rows belong to one sequence and ONE warp-uniform tcgen05.ld hands
+//     every thread exactly its own row of scores -- the softmax is thread-local (no shuffles, no shared memory);
+//   * P goes back to shared memory as the block-diagonal A operand [128 x 128] (bf16, K-major, 128B swizzle; the
+//     off-diagonal blocks are zeroed once per CTA and never written), O = P V is a second MMA chain (N = dh, K = 128,
+//     V read in place from its TMA box as an MN-major B operand), the finished 128 x dh tile is read back with
+//     tcgen05.ld, scaled by 1 / rowsum (and the optional DropPath factor), staged and written with a TMA store whose
+//     box clips the padded rows.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM owner), 2..5 = softmax / epilogue (thread = tile row).  S, P and
+// O are double-buffered so the softmax of head h+1 overlaps the P V product of head h.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace afb {
+
+int make_tensor_map_bf16_box3(void* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
+                              uint32_t box0, uint32_t box1, uint32_t box2);
+
+namespace attn_tc {
+
+constexpr int kThreads = 192;
+constexpr int kStages = 3;
+constexpr int kBoxBytes = 128 * 128;          // one (64 columns x 128 rows) bf16 box
+constexpr int kStageBytes = 3 * kBoxBytes;    // q | k | v boxes of one head group
+constexpr int kPBytes = 128 * 128 * 2;        // block-diagonal probabilities, two 64-key k-blocks
+constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;
+
+// ---- PTX wrappers (same conventions as gemm_tcgen05.cu) ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// bounded: a protocol bug traps (a launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 1023u) == 0 && global_ns() - t0 > kWaitTimeoutNs) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane = tile row); no wait
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four softmax warps
+
+// shared-memory matrix descriptor, 128B swizzle (see gemm_tcgen05.cu:make_desc)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcArgs {
+  long long B;
+  int L, heads, D;
+  int tiles;              // ceil(B / G)
+  float scale_log2;       // softmax scale * log2(e)
+  const float* out_scale; // optional [B]
+};
+
+// PVN64 (dh 32 only): the P V product covers the whole 64-column box (both heads' value columns, N = 64, the other
+// head's half is discarded) instead of a 32-column N slice that starts in the middle of the 128-byte swizzle span.
+template <int LP, int DH, bool PVN64>
+struct Cfg {
+  static constexpr int G = 128 / LP;            // sequences per tile
+  static constexpr int HB = 64 / DH;            // heads per 128-byte box
+  static constexpr int KS_S = DH / 16;          // k-steps of the scores MMA
+  static constexpr int PVN = (PVN64 || DH == 64) ? 64 : DH;
+  static constexpr int kOCols = 64;             // TMEM columns reserved per O buffer
+  static constexpr int kTmemCols = 512;         // S[2] at 0 / 128, O[2] at 256 / 320
+  static constexpr int kSmem = 1024 /*align*/ + kStages * kStageBytes + 2 * kPBytes + kBoxBytes /*staging*/ + 256 /*barriers*/;
+};
+
+template <int LP, int DH, bool PVN64>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmO, const TcArgs a) {
+  using C = Cfg<LP, DH, PVN64>;
+  constexpr int G = C::G, HB = C::HB;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sStage = base;
+  const uint32_t sP = base + kStages * kStageBytes;
+  const uint32_t sOut = sP + 2 * kPBytes;
+  const uint32_t sBar = sOut + kBoxBytes;
+  uint8_t* pP = smem + kStages * kStageBytes;
+  uint8_t* pOut = pP + 2 * kPBytes;
+  // barriers (8 bytes each)
+  auto full_bar = [&](int s) { return sBar + 8 * s; };
+  auto empty_bar = [&](int s) { return sBar + 8 * (kStages + s); };
+  auto sfull_bar = [&](int b) { return sBar + 8 * (2 * kStages + b); };
+  auto sfree_bar = [&](int b) { return sBar + 8 * (2 * kStages + 2 + b); };
+  auto pfull_bar = [&](int b) { return sBar + 8 * (2 * kStages + 4 + b); };
+  auto pfree_bar = [&](int b) { return sBar + 8 * (2 * kStages + 6 + b); };
+  auto ofull_bar = [&](int b) { return sBar + 8 * (2 * kStages + 8 + b); };
+  auto ofree_bar = [&](int b) { return sBar + 8 * (2 * kStages + 10 + b); };
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nbox = a.heads / HB;
+  int my_tiles = 0;
+  for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) ++my_tiles;
+  const int total = my_tiles * a.heads;   // (tile, head) items of this CTA, in order
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sfull_bar(b), 1); mbar_init(sfree_bar(b), 4);
+      mbar_init(pfull_bar(b), 4); mbar_init(pfree_bar(b), 1);
+      mbar_init(ofull_bar(b), 1); mbar_init(ofree_bar(b), 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmO);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem), C::kTmemCols);
+  // the off-diagonal blocks of both P buffers stay zero for the whole kernel
+  {
+    uint4* z = reinterpret_cast<uint4*>(pP);
+    for (int i = tid; i < (2 * kPBytes) >> 4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    // ------------------------------------------ TMA producer ---------------------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) {
+        for (int bx = 0; bx < nbox; ++bx) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), kStageBytes);
+          const uint32_t dst = sStage + stage * kStageBytes;
+#pragma unroll
+          for (int s = 0; s < 3; ++s) tma_load_3d(&tmQ, full_bar(stage), dst + s * kBoxBytes, s * a.D + bx * 64, 0, t * G);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------ MMA issuer -----------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc(128, C::PVN, 0, 1);
+      auto stage_of = [&](int item, uint32_t& ph) {
+        const int box = item / HB;
+        ph = (uint32_t)((box / kStages) & 1);
+        return box % kStages;
+      };
+      for (int i = 0; i <= total; ++i) {
+        if (i < total) {   // S(i) = Q K^T of item i
+          uint32_t ph;
+          const int stage = stage_of(i, ph);
+          const int slot = i % HB, b = i & 1;
+          if (slot == 0) mbar_wait(full_bar(stage), ph);
+          mbar_wait(sfree_bar(b), (uint32_t)(((i >> 1) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t q_addr = sStage + stage * kStageBytes + slot * (DH * 2);
+          const uint32_t k_addr = q_addr + kBoxBytes;
+#pragma unroll
+          for (int k = 0; k < C::KS_S; ++k)
+            umma_bf16(tmem + (uint32_t)(b * 128), make_desc(q_addr + k * 32, 16, 1024), make_desc(k_addr + k * 32, 16, 1024), idesc_s,
+                      k != 0 ? 1u : 0u);
+          umma_commit(sfull_bar(b));
+        }
+        if (i >= 1) {      // O(j) = P(j) V of the previous item
+          const int j = i - 1;
+          uint32_t ph;
+          const int stage = stage_of(j, ph);
+          const int slot = j % HB, b = j & 1;
+          mbar_wait(pfull_bar(b), (uint32_t)((j >> 1) & 1));
+          mbar_wait(ofree_bar(b), (uint32_t)(((j >> 1) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t p_addr = sP + b * kPBytes;
+          const uint32_t v_addr = sStage + stage * kStageBytes + 2 * kBoxBytes + (C::PVN == 64 ? 0 : slot * (DH * 2));
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_bf16(tmem + 256u + (uint32_t)(b * C::kOCols), make_desc(p_addr + (ks >> 2) * kBoxBytes + (ks & 3) * 32, 16, 1024),
+                      make_desc(v_addr + ks * 2048, 8192, 1024), idesc_o, ks != 0 ? 1u : 0u);
+          umma_commit(ofull_bar(b));
+          umma_commit(pfree_bar(b));
+          if (slot == HB - 1) umma_commit(empty_bar(stage));   // q | k | v boxes of this head group are consumed
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------ softmax / epilogue (thread = tile row) -------------------------
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may read
+    const int r = quarter * 32 + lane;          // tile row
+    const int g = r / LP;                       // sequence inside the tile
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int L = a.L;
+    // P destination of this row: keys g*LP .. g*LP + LP - 1 of k-block (g*LP) / 64
+    const int key0 = g * LP;
+    uint8_t* prow0 = pP + (key0 >> 6) * kBoxBytes + r * 128;
+    const int pchunk0 = (key0 & 63) >> 3;
+    uint8_t* orow = pOut + r * 128;
+    const bool elected = (warp == 2 && lane == 0);
+    // O phase of item j: read the finished 128 x dh tile back, scale by inv (1 / rowsum of that item), stage, store
+    auto o_phase = [&](int j, float inv) {
+      const int bo = j & 1, slot = j % HB;
+      const int tile = blockIdx.x + (j / a.heads) * gridDim.x, bx = (j % a.heads) / HB;
+      mbar_wait(ofull_bar(bo), (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      uint32_t orr[DH];
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c)
+        tmem_ld32_issue(lane_addr + 256u + (uint32_t)(bo * C::kOCols + ((C::PVN == 64 && DH == 32) ? slot * 32 : 0) + c * 32), orr + c * 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ofree_bar(bo));
+      float sc = inv;
+      if (a.out_scale != nullptr) {   // DropPath keep factor of the row's sequence
+        const long long bq = (long long)tile * G + g;
+        sc *= bq < a.B ? a.out_scale[bq] : 0.f;
+      }
+      if (slot == 0) {   // the previous store out of the staging buffer must have finished reading it
+        if (elected) bulk_wait_read0();
+        epi_bar();
+      }
+#pragma unroll
+      for (int c = 0; c < DH / 8; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          w[q] = pack_bf16x2(__uint_as_float(orr[8 * c + 2 * q]) * sc, __uint_as_float(orr[8 * c + 2 * q + 1]) * sc);
+        *reinterpret_cast<uint4*>(orow + (((slot * (DH / 8) + c) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      if (slot == HB - 1) {
+        fence_async_smem();
+        epi_bar();
+        if (elected) {
+          tma_store_3d(&tmO, sOut, bx * 64, 0, tile * G);
+          bulk_commit();
+        }
+      }
+    };
+    float inv_prev = 0.f;
+    for (int i = 0; i < total; ++i) {
+      const int b = i & 1;
+      mbar_wait(sfull_bar(b), (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      uint32_t sr[LP];
+#pragma unroll
+      for (int c = 0; c < LP / 32; ++c) tmem_ld32_issue(lane_addr + (uint32_t)(b * 128 + key0 + c * 32), sr + c * 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sfree_bar(b));
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < LP; ++j)
+        if (j < L) mx = fmaxf(mx, __uint_as_float(sr[j]));
+      const float off = mx * a.scale_log2;
+      float sum = 0.f;
+      uint32_t pk[LP / 2];
+#pragma unroll
+      for (int j = 0; j < LP; j += 2) {
+        const float p0 = j < L ? ex2(fmaf(__uint_as_float(sr[j]), a.scale_log2, -off)) : 0.f;
+        const float p1 = j + 1 < L ? ex2(fmaf(__uint_as_float(sr[j + 1]), a.scale_log2, -off)) : 0.f;
+        sum += p0 + p1;
+        pk[j >> 1] = pack_bf16x2(p0, p1);
+      }
+      mbar_wait(pfree_bar(b), (uint32_t)(((i >> 1) & 1) ^ 1));
+      uint8_t* prow = prow0 + b * kPBytes;
+#pragma unroll
+      for (int c = 0; c < LP / 8; ++c)
+        *reinterpret_cast<uint4*>(prow + (((pchunk0 + c) ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pfull_bar(b));
+      // the P V product of this item now runs on the tensor pipe: read back the PREVIOUS item's output meanwhile
+      if (i >= 1) o_phase(i - 1, inv_prev);
+      inv_prev = 1.0f / sum;
+    }
+    if (total > 0) o_phase(total - 1, inv_prev);
+    if (elected) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::kTmemCols);
+  }
+}
+
+template <int LP, int DH, bool PVN64>
+int launch(const void* qkv, void* o, int64_t B, int L, int heads, float scale, const float* out_scale, cudaStream_t st) {
+  using C = Cfg<LP, DH, PVN64>;
+  auto kern = attn_fwd_tc_kernel<LP, DH, PVN64>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    if (e != cudaSuccess) {
+      set_error("attention_tc: cudaFuncSetAttribute(%d) failed: %s", C::kSmem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int D = heads * DH;
+  CUtensorMap tmQ, tmO;
+  int rc;
+  if ((rc = make_tensor_map_bf16_box3(&tmQ, qkv, (uint64_t)3 * D, (uint64_t)L, (uint64_t)B, (uint64_t)3 * D, (uint64_t)L * 3 * D, 64, LP, C::G)))
+    return rc;
+  if ((rc = make_tensor_map_bf16_box3(&tmO, o, (uint64_t)D, (uint64_t)L, (uint64_t)B, (uint64_t)D, (uint64_t)L * D, 64, LP, C::G)))
+    return rc;
+  TcArgs a;
+  a.B = B; a.L = L; a.heads = heads; a.D = D;
+  a.tiles = (int)((B + C::G - 1) / C::G);
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.out_scale = out_scale;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = a.tiles < sms ? a.tiles : sms;
+  kern<<<grid, kThreads, C::kSmem, st>>>(tmQ, tmO, a);
+  return check_launch("attention_fwd_tc");
+}
+
+}  // namespace attn_tc
+
+// shapes the tcgen05 forward covers: bf16, dh 32 / 64, L <= 64, whole 128-byte boxes of heads, 16-byte aligned rows
+bool attention_tc_supported(int L, int heads, int dh) {
+  return (dh == 32 || dh == 64) && L >= 1 && L <= 64 && (heads * dh) % 64 == 0;
+}
+
+// variant: 0 = N-slice P V (dh columns of the head), 1 = whole-box P V (dh 32: N = 64, half discarded)
+int attention_fwd_tc(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, const float* out_scale, int variant,
+                     cudaStream_t st) {
+  if (((uintptr_t)qkv & 15) != 0 || ((uintptr_t)o & 15) != 0) {
+    set_error("attention_fwd_tc: qkv / o must be 16-byte aligned");
+    return AFB_ERR_INVALID;
+  }
+  const bool wide = variant == 1;
+  if (dh == 32) {
+    if (L <= 32) return wide ? attn_tc::launch<32, 32, true>(qkv, o, B, L, heads, scale, out_scale, st)
+                             : attn_tc::launch<32, 32, false>(qkv, o, B, L, heads, scale, out_scale, st);
+    return wide ? attn_tc::launch<64, 32, true>(qkv, o, B, L, heads, scale, out_scale, st)
+                : attn_tc::launch<64, 32, false>(qkv, o, B, L, heads, scale, out_scale, st);
+  }
+  if (L <= 32) return attn_tc::launch<32, 64, false>(qkv, o, B, L, heads, scale, out_scale, st);
+  return attn_tc::launch<64, 64, false>(qkv, o, B, L, heads, scale, out_scale, st);
+}
+
+}  // namespace afb

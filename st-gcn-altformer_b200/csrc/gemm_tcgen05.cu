@@ -1110,7 +1110,7 @@ EncodeTiledFn get_encode() {
 
 // tensor [d2][d1][d0] (d0 contiguous), strides in elements; 128B swizzle; OOB reads give zero, OOB writes are clipped.
 int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
-             uint32_t box0, uint32_t box1, int rank, int dtype = AFB_BF16) {
+             uint32_t box0, uint32_t box1, int rank, int dtype = AFB_BF16, uint32_t box2 = 1) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled unavailable (driver too old?)");
@@ -1119,7 +1119,7 @@ int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64
   cuuint64_t dims[3] = {d0, d1, d2};
   const uint64_t esz = dtype == AFB_BF16 ? 2 : 4;
   cuuint64_t strides[2] = {stride1 * esz, stride2 * esz};
-  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, dtype == AFB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1199,6 +1199,11 @@ int launch_dw(const CUtensorMap& tmG, const CUtensorMap& tmX, const DwArgs& a, c
 int make_tensor_map_bf16(void* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
                          uint32_t box0, uint32_t box1) {
   return make_map(reinterpret_cast<CUtensorMap*>(map), ptr, d0, d1, d2, stride1, stride2, box0, box1, 3);
+}
+// same with a box that spans several entries of the outermost dimension (packed short sequences: attention_tc.cu)
+int make_tensor_map_bf16_box3(void* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
+                              uint32_t box0, uint32_t box1, uint32_t box2) {
+  return make_map(reinterpret_cast<CUtensorMap*>(map), ptr, d0, d1, d2, stride1, stride2, box0, box1, 3, AFB_BF16, box2);
 }
 }  // namespace afb
 
