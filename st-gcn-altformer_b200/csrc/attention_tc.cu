@@ -18,8 +18,9 @@
 //     V read in place from its TMA box as an MN-major B operand), the finished 128 x dh tile is read back with
 //     tcgen05.ld, scaled by 1 / rowsum (and the optional DropPath factor), staged and written with a TMA store whose
 //     box clips the padded rows.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM owner), 2..5 = softmax / epilogue (thread = tile row).  S, P and
-// O are double-buffered so the softmax of head h+1 overlaps the P V product of head h.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM owner), 2..5 and 6..9 = two softmax / epilogue groups (thread = tile
+// row; group b owns the items i = b mod 2 and the S / P / O buffers b), so two heads are in the softmax at any time while
+// the tensor pipe works on the products either side of them.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -28,15 +29,14 @@
 namespace afb {
 
 int make_tensor_map_bf16_box3(void* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
-                              uint32_t box0, uint32_t box1, uint32_t box2);
+                              uint32_t box0, uint32_t box1, uint32_t box2, int swizzle_bytes);
 
 namespace attn_tc {
 
-constexpr int kThreads = 192;
-constexpr int kStages = 3;
+constexpr int kThreads = 64 + 256;             // producer, MMA issuer, two softmax groups of four warps
 constexpr int kBoxBytes = 128 * 128;          // one (64 columns x 128 rows) bf16 box
-constexpr int kStageBytes = 3 * kBoxBytes;    // q | k | v boxes of one head group
-constexpr int kPBytes = 128 * 128 * 2;        // block-diagonal probabilities, two 64-key k-blocks
+constexpr int kStageBytes = 3 * kBoxBytes;    // q | k | v boxes of one 64-column box (two heads at dh 32, one at dh 64)
+constexpr int kPBytes = 128 * 128 * 2;        // block-diagonal probabilities in shared memory (PTMEM = false): two 64-key k-blocks
 constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;
 
 // ---- PTX wrappers (same conventions as gemm_tcgen05.cu) ---------------------------------------------------------
@@ -127,6 +127,25 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive 32-bit columns <- 16 registers per thread
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (lane = row, two bf16 per 32-bit column) is read from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -138,7 +157,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four softmax warps
 
 // shared-memory matrix descriptor, 128B swizzle (see gemm_tcgen05.cu:make_desc)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -158,33 +176,36 @@ struct TcArgs {
   const float* out_scale; // optional [B]
 };
 
-// PVN64 (dh 32 only): the P V product covers the whole 64-column box (both heads' value columns, N = 64, the other
-// head's half is discarded) instead of a 32-column N slice that starts in the middle of the 128-byte swizzle span.
-template <int LP, int DH, bool PVN64>
+// PTMEM: the probabilities go back to TENSOR memory (tcgen05.st) and the P V product reads its A operand from there;
+// otherwise they are staged in shared memory as a K-major 128B-swizzled operand.
+template <int LP, int DH, bool PTMEM>
 struct Cfg {
   static constexpr int G = 128 / LP;            // sequences per tile
   static constexpr int HB = 64 / DH;            // heads per 128-byte box
   static constexpr int KS_S = DH / 16;          // k-steps of the scores MMA
-  static constexpr int PVN = (PVN64 || DH == 64) ? 64 : DH;
-  static constexpr int kOCols = 64;             // TMEM columns reserved per O buffer
-  static constexpr int kTmemCols = 512;         // S[2] at 0 / 128, O[2] at 256 / 320
-  static constexpr int kSmem = 1024 /*align*/ + kStages * kStageBytes + 2 * kPBytes + kBoxBytes /*staging*/ + 256 /*barriers*/;
+  static constexpr int kOutBytes = 128 * DH * 2;   // one head's output tile, staged per softmax group
+  static constexpr int kPSmem = PTMEM ? 0 : 2 * kPBytes;
+  static constexpr int kStages = PTMEM ? 4 : (DH == 32 ? 3 : 2);
+  // tensor memory: S[2] at 0 / 128 (fp32 scores, 128 columns), O[2] at 256 / 320 (dh columns), P[2] at 384 / 448
+  // (128 keys as bf16 pairs = 64 columns, off-diagonal blocks zeroed once)
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSmem = 1024 /*align*/ + kStages * kStageBytes + kPSmem + 2 * kOutBytes + 256 /*barriers*/;
 };
 
-template <int LP, int DH, bool PVN64>
+template <int LP, int DH, bool PTMEM>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmO, const TcArgs a) {
-  using C = Cfg<LP, DH, PVN64>;
-  constexpr int G = C::G, HB = C::HB;
+  using C = Cfg<LP, DH, PTMEM>;
+  constexpr int G = C::G, HB = C::HB, kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sStage = base;
   const uint32_t sP = base + kStages * kStageBytes;
-  const uint32_t sOut = sP + 2 * kPBytes;
-  const uint32_t sBar = sOut + kBoxBytes;
+  const uint32_t sOut = sP + C::kPSmem;
+  const uint32_t sBar = sOut + 2 * C::kOutBytes;
   uint8_t* pP = smem + kStages * kStageBytes;
-  uint8_t* pOut = pP + 2 * kPBytes;
+  uint8_t* pOut = pP + C::kPSmem;
   // barriers (8 bytes each)
   auto full_bar = [&](int s) { return sBar + 8 * s; };
   auto empty_bar = [&](int s) { return sBar + 8 * (kStages + s); };
@@ -214,10 +235,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmO);
   }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem), C::kTmemCols);
-  // the off-diagonal blocks of both P buffers stay zero for the whole kernel
-  {
+  if (!PTMEM) {   // the off-diagonal blocks of both P buffers stay zero for the whole kernel
     uint4* z = reinterpret_cast<uint4*>(pP);
-    for (int i = tid; i < (2 * kPBytes) >> 4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < C::kPSmem >> 4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_async_smem();
   }
   tc_fence_before();
@@ -245,7 +265,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ------------------------------------------ MMA issuer -----------------------------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc(128, C::PVN, 0, 1);
+      constexpr uint32_t idesc_o = make_idesc(128, DH, 0, 1);
       auto stage_of = [&](int item, uint32_t& ph) {
         const int box = item / HB;
         ph = (uint32_t)((box / kStages) & 1);
@@ -275,12 +295,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mbar_wait(pfull_bar(b), (uint32_t)((j >> 1) & 1));
           mbar_wait(ofree_bar(b), (uint32_t)(((j >> 1) & 1) ^ 1));
           tc_fence_after();
-          const uint32_t p_addr = sP + b * kPBytes;
-          const uint32_t v_addr = sStage + stage * kStageBytes + 2 * kBoxBytes + (C::PVN == 64 ? 0 : slot * (DH * 2));
+          const uint32_t v_addr = sStage + stage * kStageBytes + 2 * kBoxBytes + slot * (DH * 2);
+          const uint32_t d_addr = tmem + 256u + (uint32_t)(b * 64);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_bf16(tmem + 256u + (uint32_t)(b * C::kOCols), make_desc(p_addr + (ks >> 2) * kBoxBytes + (ks & 3) * 32, 16, 1024),
-                      make_desc(v_addr + ks * 2048, 8192, 1024), idesc_o, ks != 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t bdesc = make_desc(v_addr + ks * 2048, 8192, 1024);
+            if (PTMEM)
+              umma_bf16_ts(d_addr, tmem + 384u + (uint32_t)(b * 64 + ks * 8), bdesc, idesc_o, ks != 0 ? 1u : 0u);
+            else
+              umma_bf16(d_addr, make_desc(sP + b * kPBytes + (ks >> 2) * kBoxBytes + (ks & 3) * 32, 16, 1024), bdesc, idesc_o, ks != 0 ? 1u : 0u);
+          }
           umma_commit(ofull_bar(b));
           umma_commit(pfree_bar(b));
           if (slot == HB - 1) umma_commit(empty_bar(stage));   // q | k | v boxes of this head group are consumed
@@ -289,69 +313,78 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ------------------------------------------ softmax / epilogue (thread = tile row) -------------------------
+    const int grp = (warp - 2) >> 2;            // softmax group = buffer index of its items
     const int quarter = warp & 3;               // TMEM lane quarter this warp may read
     const int r = quarter * 32 + lane;          // tile row
     const int g = r / LP;                       // sequence inside the tile
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const int L = a.L;
-    // P destination of this row: keys g*LP .. g*LP + LP - 1 of k-block (g*LP) / 64
-    const int key0 = g * LP;
-    uint8_t* prow0 = pP + (key0 >> 6) * kBoxBytes + r * 128;
+    const int key0 = g * LP;                    // first key (= S column) of this row's sequence
+    // P destination of this row.  shared memory: keys key0 .. key0 + LP - 1 of k-block key0 / 64;  tensor memory:
+    // columns key0 / 2 .. of the group's P region
+    uint8_t* prow = pP + grp * kPBytes + (key0 >> 6) * kBoxBytes + r * 128;
     const int pchunk0 = (key0 & 63) >> 3;
-    uint8_t* orow = pOut + r * 128;
-    const bool elected = (warp == 2 && lane == 0);
+    const uint32_t p_taddr = lane_addr + 384u + (uint32_t)(grp * 64 + (key0 >> 1));
+    uint8_t* orow = pOut + grp * C::kOutBytes + r * (DH * 2);
+    const int oswz = DH == 64 ? (r & 7) : ((r >> 1) & 3);     // 128B / 64B swizzle of the staging rows
+    const bool elected = ((warp - 2) & 3) == 0 && lane == 0;  // one store issuer per group
+    auto grp_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
+    const uint32_t sfull = sfull_bar(grp), sfree = sfree_bar(grp), pfull = pfull_bar(grp), pfree = pfree_bar(grp);
+    const uint32_t ofull = ofull_bar(grp), ofree = ofree_bar(grp);
+    if (PTMEM) {   // zero the group's whole P region once: only the diagonal block of each row is ever rewritten
+      uint32_t z[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) z[k] = 0u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st16(lane_addr + 384u + (uint32_t)(grp * 64 + c * 16), z);
+      tmem_wait_st();
+    }
     // O phase of item j: read the finished 128 x dh tile back, scale by inv (1 / rowsum of that item), stage, store
     auto o_phase = [&](int j, float inv) {
-      const int bo = j & 1, slot = j % HB;
-      const int tile = blockIdx.x + (j / a.heads) * gridDim.x, bx = (j % a.heads) / HB;
-      mbar_wait(ofull_bar(bo), (uint32_t)((j >> 1) & 1));
+      const int tile = blockIdx.x + (j / a.heads) * gridDim.x, h = j % a.heads;
+      mbar_wait(ofull, (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       uint32_t orr[DH];
 #pragma unroll
-      for (int c = 0; c < DH / 32; ++c)
-        tmem_ld32_issue(lane_addr + 256u + (uint32_t)(bo * C::kOCols + ((C::PVN == 64 && DH == 32) ? slot * 32 : 0) + c * 32), orr + c * 32);
+      for (int c = 0; c < DH / 32; ++c) tmem_ld32_issue(lane_addr + 256u + (uint32_t)(grp * 64 + c * 32), orr + c * 32);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ofree_bar(bo));
+      if (lane == 0) mbar_arrive(ofree);
       float sc = inv;
       if (a.out_scale != nullptr) {   // DropPath keep factor of the row's sequence
         const long long bq = (long long)tile * G + g;
         sc *= bq < a.B ? a.out_scale[bq] : 0.f;
       }
-      if (slot == 0) {   // the previous store out of the staging buffer must have finished reading it
-        if (elected) bulk_wait_read0();
-        epi_bar();
-      }
+      // the group's previous store must have finished reading the staging tile
+      if (elected) bulk_wait_read0();
+      grp_bar();
 #pragma unroll
       for (int c = 0; c < DH / 8; ++c) {
         uint32_t w[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           w[q] = pack_bf16x2(__uint_as_float(orr[8 * c + 2 * q]) * sc, __uint_as_float(orr[8 * c + 2 * q + 1]) * sc);
-        *reinterpret_cast<uint4*>(orow + (((slot * (DH / 8) + c) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(orow + ((c ^ oswz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      if (slot == HB - 1) {
-        fence_async_smem();
-        epi_bar();
-        if (elected) {
-          tma_store_3d(&tmO, sOut, bx * 64, 0, tile * G);
-          bulk_commit();
-        }
+      fence_async_smem();
+      grp_bar();
+      if (elected) {
+        tma_store_3d(&tmO, sOut + grp * C::kOutBytes, h * DH, 0, tile * G);
+        bulk_commit();
       }
     };
     float inv_prev = 0.f;
-    for (int i = 0; i < total; ++i) {
-      const int b = i & 1;
-      mbar_wait(sfull_bar(b), (uint32_t)((i >> 1) & 1));
+    for (int i = grp; i < total; i += 2) {
+      mbar_wait(sfull, (uint32_t)((i >> 1) & 1));
       tc_fence_after();
       uint32_t sr[LP];
 #pragma unroll
-      for (int c = 0; c < LP / 32; ++c) tmem_ld32_issue(lane_addr + (uint32_t)(b * 128 + key0 + c * 32), sr + c * 32);
+      for (int c = 0; c < LP / 32; ++c) tmem_ld32_issue(lane_addr + (uint32_t)(grp * 128 + key0 + c * 32), sr + c * 32);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sfree_bar(b));
+      if (lane == 0) mbar_arrive(sfree);
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < LP; ++j)
@@ -366,19 +399,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         sum += p0 + p1;
         pk[j >> 1] = pack_bf16x2(p0, p1);
       }
-      mbar_wait(pfree_bar(b), (uint32_t)(((i >> 1) & 1) ^ 1));
-      uint8_t* prow = prow0 + b * kPBytes;
+      mbar_wait(pfree, (uint32_t)(((i >> 1) & 1) ^ 1));
+      if (PTMEM) {
+        tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < LP / 8; ++c)
-        *reinterpret_cast<uint4*>(prow + (((pchunk0 + c) ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      fence_async_smem();
+        for (int c = 0; c < LP / 32; ++c) tmem_st16(p_taddr + (uint32_t)(c * 16), pk + c * 16);
+        tmem_wait_st();
+        tc_fence_before();
+      } else {
+#pragma unroll
+        for (int c = 0; c < LP / 8; ++c)
+          *reinterpret_cast<uint4*>(prow + (((pchunk0 + c) ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        fence_async_smem();
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(pfull_bar(b));
-      // the P V product of this item now runs on the tensor pipe: read back the PREVIOUS item's output meanwhile
-      if (i >= 1) o_phase(i - 1, inv_prev);
+      if (lane == 0) mbar_arrive(pfull);
+      // the P V product of this item now runs on the tensor pipe: read back the group's PREVIOUS item meanwhile
+      if (i >= 2) o_phase(i - 2, inv_prev);
       inv_prev = 1.0f / sum;
     }
-    if (total > 0) o_phase(total - 1, inv_prev);
+    if (total > grp) o_phase(((total - 1 - grp) & ~1) + grp, inv_prev);
     if (elected) bulk_wait0();
   }
   tc_fence_before();
@@ -389,10 +429,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <int LP, int DH, bool PVN64>
+template <int LP, int DH, bool PTMEM>
 int launch(const void* qkv, void* o, int64_t B, int L, int heads, float scale, const float* out_scale, cudaStream_t st) {
-  using C = Cfg<LP, DH, PVN64>;
-  auto kern = attn_fwd_tc_kernel<LP, DH, PVN64>;
+  using C = Cfg<LP, DH, PTMEM>;
+  auto kern = attn_fwd_tc_kernel<LP, DH, PTMEM>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
@@ -405,9 +445,10 @@ int launch(const void* qkv, void* o, int64_t B, int L, int heads, float scale, c
   const int D = heads * DH;
   CUtensorMap tmQ, tmO;
   int rc;
-  if ((rc = make_tensor_map_bf16_box3(&tmQ, qkv, (uint64_t)3 * D, (uint64_t)L, (uint64_t)B, (uint64_t)3 * D, (uint64_t)L * 3 * D, 64, LP, C::G)))
+  if ((rc = make_tensor_map_bf16_box3(&tmQ, qkv, (uint64_t)3 * D, (uint64_t)L, (uint64_t)B, (uint64_t)3 * D, (uint64_t)L * 3 * D, 64, LP, C::G, 128)))
     return rc;
-  if ((rc = make_tensor_map_bf16_box3(&tmO, o, (uint64_t)D, (uint64_t)L, (uint64_t)B, (uint64_t)D, (uint64_t)L * D, 64, LP, C::G)))
+  // output boxes are one head wide: 64-byte rows (64B swizzle) at dh 32, 128-byte rows at dh 64
+  if ((rc = make_tensor_map_bf16_box3(&tmO, o, (uint64_t)D, (uint64_t)L, (uint64_t)B, (uint64_t)D, (uint64_t)L * D, DH, LP, C::G, DH * 2)))
     return rc;
   TcArgs a;
   a.B = B; a.L = L; a.heads = heads; a.D = D;
@@ -429,22 +470,23 @@ bool attention_tc_supported(int L, int heads, int dh) {
   return (dh == 32 || dh == 64) && L >= 1 && L <= 64 && (heads * dh) % 64 == 0;
 }
 
-// variant: 0 = N-slice P V (dh columns of the head), 1 = whole-box P V (dh 32: N = 64, half discarded)
+// variant: 0 = probabilities through tensor memory (A operand of P V read from TMEM), 1 = through shared memory
 int attention_fwd_tc(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, const float* out_scale, int variant,
                      cudaStream_t st) {
   if (((uintptr_t)qkv & 15) != 0 || ((uintptr_t)o & 15) != 0) {
     set_error("attention_fwd_tc: qkv / o must be 16-byte aligned");
     return AFB_ERR_INVALID;
   }
-  const bool wide = variant == 1;
+#define AFB_TC_LAUNCH(LP, DH)                                                                              \
+  return variant == 1 ? attn_tc::launch<LP, DH, false>(qkv, o, B, L, heads, scale, out_scale, st)          \
+                      : attn_tc::launch<LP, DH, true>(qkv, o, B, L, heads, scale, out_scale, st)
   if (dh == 32) {
-    if (L <= 32) return wide ? attn_tc::launch<32, 32, true>(qkv, o, B, L, heads, scale, out_scale, st)
-                             : attn_tc::launch<32, 32, false>(qkv, o, B, L, heads, scale, out_scale, st);
-    return wide ? attn_tc::launch<64, 32, true>(qkv, o, B, L, heads, scale, out_scale, st)
-                : attn_tc::launch<64, 32, false>(qkv, o, B, L, heads, scale, out_scale, st);
+    if (L <= 32) AFB_TC_LAUNCH(32, 32);
+    AFB_TC_LAUNCH(64, 32);
   }
-  if (L <= 32) return attn_tc::launch<32, 64, false>(qkv, o, B, L, heads, scale, out_scale, st);
-  return attn_tc::launch<64, 64, false>(qkv, o, B, L, heads, scale, out_scale, st);
+  if (L <= 32) AFB_TC_LAUNCH(32, 64);
+  AFB_TC_LAUNCH(64, 64);
+#undef AFB_TC_LAUNCH
 }
 
 }  // namespace afb

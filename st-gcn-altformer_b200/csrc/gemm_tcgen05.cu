@@ -1110,7 +1110,7 @@ EncodeTiledFn get_encode() {
 
 // tensor [d2][d1][d0] (d0 contiguous), strides in elements; 128B swizzle; OOB reads give zero, OOB writes are clipped.
 int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
-             uint32_t box0, uint32_t box1, int rank, int dtype = AFB_BF16, uint32_t box2 = 1) {
+             uint32_t box0, uint32_t box1, int rank, int dtype = AFB_BF16, uint32_t box2 = 1, int swizzle_bytes = 128) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled unavailable (driver too old?)");
@@ -1122,7 +1122,8 @@ int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64
   cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, dtype == AFB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (ptr %p dims %llu,%llu,%llu strides %llu,%llu box %u,%u)", (int)r, ptr,
@@ -1202,8 +1203,8 @@ int make_tensor_map_bf16(void* map, const void* ptr, uint64_t d0, uint64_t d1, u
 }
 // same with a box that spans several entries of the outermost dimension (packed short sequences: attention_tc.cu)
 int make_tensor_map_bf16_box3(void* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
-                              uint32_t box0, uint32_t box1, uint32_t box2) {
-  return make_map(reinterpret_cast<CUtensorMap*>(map), ptr, d0, d1, d2, stride1, stride2, box0, box1, 3, AFB_BF16, box2);
+                              uint32_t box0, uint32_t box1, uint32_t box2, int swizzle_bytes) {
+  return make_map(reinterpret_cast<CUtensorMap*>(map), ptr, d0, d1, d2, stride1, stride2, box0, box1, 3, AFB_BF16, box2, swizzle_bytes);
 }
 }  // namespace afb
 

@@ -52,9 +52,7 @@ def main():
         want = ref(qkv, B, L, H)
         keep = (torch.rand(B, device=dev) > 0.3).float() / 0.7
         line = f"B={B:5d} L={L:2d} H={H} dh={dh}:"
-        for mode in ("mma", "tc", "tc64"):
-            if mode == "tc64" and dh != 32:
-                continue
+        for mode in ("mma", "tc", "tcs"):   # tc: P through tensor memory; tcs: P through shared memory
             try:
                 got = run(mode, qkv, B, L, H)
                 torch.cuda.synchronize()
