@@ -18,7 +18,7 @@
 //     V read in place from its TMA box as an MN-major B operand), the finished 128 x dh tile is read back with
 //     tcgen05.ld, scaled by 1 / rowsum (and the optional DropPath factor), staged and written with a TMA store whose
 //     box clips the padded rows.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM owner), 2..5 and 6..9 = two softmax / epilogue groups (thread = tile
+// Warp roles: 0 = TMA producer, 1 = S issuer (+ TMEM owner), 10 = P V issuer, 2..5 and 6..9 = two softmax / epilogue groups (thread = tile
 // row; group b owns the items i = b mod 2 and the S / P / O buffers b), so two heads are in the softmax at any time while
 // the tensor pipe works on the products either side of them.
 #include <cuda.h>
@@ -33,7 +33,7 @@ int make_tensor_map_bf16_box3(void* map, const void* ptr, uint64_t d0, uint64_t 
 
 namespace attn_tc {
 
-constexpr int kThreads = 64 + 256;             // producer, MMA issuer, two softmax groups of four warps
+constexpr int kThreads = 64 + 256 + 32;        // producer, S issuer, two softmax groups of four warps, P V issuer
 constexpr int kBoxBytes = 128 * 128;          // one (64 columns x 128 rows) bf16 box
 constexpr int kStageBytes = 3 * kBoxBytes;    // q | k | v boxes of one 64-column box (two heads at dh 32, one at dh 64)
 constexpr int kPBytes = 128 * 128 * 2;        // block-diagonal probabilities in shared memory (PTMEM = false): two 64-key k-blocks
@@ -261,8 +261,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------ MMA issuer -----------------------------------------------------
+  } else if (warp == 1 || warp == 10) {
+    // ------------------------------------------ MMA issuers ----------------------------------------------------
+    // Two issuing threads so that neither product waits behind the other's barrier: warp 1 issues the scores of an item
+    // as soon as its S buffer has been read out (two items ahead of the P V product at most), warp 10 issues P V when
+    // the probabilities are in place.  They write disjoint TMEM regions; each commit covers its own thread's MMAs.
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(128, 128, 0, 0);
       constexpr uint32_t idesc_o = make_idesc(128, DH, 0, 1);
@@ -271,8 +274,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ph = (uint32_t)((box / kStages) & 1);
         return box % kStages;
       };
-      for (int i = 0; i <= total; ++i) {
-        if (i < total) {   // S(i) = Q K^T of item i
+      if (warp == 1) {
+        for (int i = 0; i < total; ++i) {   // S(i) = Q K^T of item i
           uint32_t ph;
           const int stage = stage_of(i, ph);
           const int slot = i % HB, b = i & 1;
@@ -287,8 +290,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                       k != 0 ? 1u : 0u);
           umma_commit(sfull_bar(b));
         }
-        if (i >= 1) {      // O(j) = P(j) V of the previous item
-          const int j = i - 1;
+      } else {
+        for (int j = 0; j < total; ++j) {   // O(j) = P(j) V
           uint32_t ph;
           const int stage = stage_of(j, ph);
           const int slot = j % HB, b = j & 1;
@@ -307,7 +310,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           umma_commit(ofull_bar(b));
           umma_commit(pfree_bar(b));
-          if (slot == HB - 1) umma_commit(empty_bar(stage));   // q | k | v boxes of this head group are consumed
+          // the q | k | v boxes of this head group are consumed: every S product of the box finished before its softmax,
+          // which finished before the P V products this commit covers
+          if (slot == HB - 1) umma_commit(empty_bar(stage));
         }
       }
     }
