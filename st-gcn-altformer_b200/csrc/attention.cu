@@ -364,12 +364,16 @@ extern "C" int afb_attention_fwd(const void* qkv, void* o, int dt, int64_t B, in
     }
     return check_launch("attention_long_fwd");
   }
-  // AFB_ATTN_TC (read per call so one process can compare the paths): 1 = tcgen05 / TMEM / TMA forward (attention_tc.cu),
-  // 2 = its whole-box P V variant, unset / 0 = warp-level MMA forward (attention_mma.cu)
+  // Forward on the Blackwell paths (attention_tc.cu: TMA, tcgen05.mma, scores / probabilities / output in tensor memory)
+  // wherever it is the faster kernel: dh = 32 (B200, B*L = 180k tokens: 71.5 vs 79.8 us at L = 22, 65 vs 100 us at L = 64);
+  // at dh = 64 the two tie at the HBM floor and the warp-level kernel stays.  AFB_ATTN_TC (read per call so one process
+  // can compare the paths): 0 = warp-level MMA kernel, 1 = tcgen05 kernel for every shape it covers, 2 = its variant with
+  // the probabilities staged in shared memory instead of tensor memory.
   if (dt == AFB_BF16 && attention_tc_supported(L, heads, dh)) {
     const char* tc = getenv("AFB_ATTN_TC");
-    if (tc != nullptr && (tc[0] == '1' || tc[0] == '2'))
-      return attention_fwd_tc(qkv, o, B, L, heads, dh, scale, out_scale, tc[0] == '2' ? 1 : 0, as_stream(s));
+    const char mode = tc != nullptr ? tc[0] : '\0';
+    if (mode == '1' || mode == '2' || (mode != '0' && dh == 32))
+      return attention_fwd_tc(qkv, o, B, L, heads, dh, scale, out_scale, mode == '2' ? 1 : 0, as_stream(s));
   }
   if (use_mma(dt, L, heads, dh)) return attention_fwd_mma(qkv, o, B, L, heads, dh, scale, out_scale, as_stream(s));
   const int per_warp = 3 * L * (dh + 1) + L + 3;

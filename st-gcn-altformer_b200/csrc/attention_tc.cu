@@ -95,6 +95,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -184,15 +185,18 @@ struct Cfg {
   static constexpr int HB = 64 / DH;            // heads per 128-byte box
   static constexpr int KS_S = DH / 16;          // k-steps of the scores MMA
   static constexpr int kOutBytes = 128 * DH * 2;   // one head's output tile, staged per softmax group
+  static constexpr int kOutBufs = (DH == 32 && PTMEM) ? 2 : 1;   // staging tiles per group (two: the previous store may still be reading)
   static constexpr int kPSmem = PTMEM ? 0 : 2 * kPBytes;
   static constexpr int kStages = PTMEM ? 4 : (DH == 32 ? 3 : 2);
   // tensor memory: S[2] at 0 / 128 (fp32 scores, 128 columns), O[2] at 256 / 320 (dh columns), P[2] at 384 / 448
   // (128 keys as bf16 pairs = 64 columns, off-diagonal blocks zeroed once)
   static constexpr int kTmemCols = 512;
-  static constexpr int kSmem = 1024 /*align*/ + kStages * kStageBytes + kPSmem + 2 * kOutBytes + 256 /*barriers*/;
+  static constexpr int kSmem = 1024 /*align*/ + kStages * kStageBytes + kPSmem + 2 * kOutBufs * kOutBytes + 256 /*barriers*/;
 };
 
-template <int LP, int DH, bool PTMEM>
+// LC: the sequence length as a compile-time constant (0 = read it from the arguments): the masked key columns then cost
+// nothing instead of a compare + select each, which was a sixth of the kernel's instructions.
+template <int LP, int DH, bool PTMEM, int LC>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmO, const TcArgs a) {
   using C = Cfg<LP, DH, PTMEM>;
@@ -203,7 +207,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t sStage = base;
   const uint32_t sP = base + kStages * kStageBytes;
   const uint32_t sOut = sP + C::kPSmem;
-  const uint32_t sBar = sOut + 2 * C::kOutBytes;
+  const uint32_t sBar = sOut + 2 * C::kOutBufs * C::kOutBytes;
   uint8_t* pP = smem + kStages * kStageBytes;
   uint8_t* pOut = pP + C::kPSmem;
   // barriers (8 bytes each)
@@ -323,14 +327,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int r = quarter * 32 + lane;          // tile row
     const int g = r / LP;                       // sequence inside the tile
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    const int L = a.L;
+    const int L = LC != 0 ? LC : a.L;
     const int key0 = g * LP;                    // first key (= S column) of this row's sequence
     // P destination of this row.  shared memory: keys key0 .. key0 + LP - 1 of k-block key0 / 64;  tensor memory:
     // columns key0 / 2 .. of the group's P region
     uint8_t* prow = pP + grp * kPBytes + (key0 >> 6) * kBoxBytes + r * 128;
     const int pchunk0 = (key0 & 63) >> 3;
     const uint32_t p_taddr = lane_addr + 384u + (uint32_t)(grp * 64 + (key0 >> 1));
-    uint8_t* orow = pOut + grp * C::kOutBytes + r * (DH * 2);
+    uint8_t* orow = pOut + grp * C::kOutBufs * C::kOutBytes + r * (DH * 2);
     const int oswz = DH == 64 ? (r & 7) : ((r >> 1) & 3);     // 128B / 64B swizzle of the staging rows
     const bool elected = ((warp - 2) & 3) == 0 && lane == 0;  // one store issuer per group
     auto grp_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
@@ -345,8 +349,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_wait_st();
     }
     // O phase of item j: read the finished 128 x dh tile back, scale by inv (1 / rowsum of that item), stage, store
+    // (tile, head) of the group's next O phase, advanced incrementally (items grp, grp + 2, ... in order)
+    int o_tile = blockIdx.x, o_head = grp, o_cnt = 0;
     auto o_phase = [&](int j, float inv) {
-      const int tile = blockIdx.x + (j / a.heads) * gridDim.x, h = j % a.heads;
+      const int tile = o_tile, h = o_head, ob = C::kOutBufs == 2 ? (o_cnt & 1) : 0;
+      ++o_cnt;
+      o_head += 2;
+      if (o_head >= a.heads) { o_head -= a.heads; o_tile += gridDim.x; }
       mbar_wait(ofull, (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       uint32_t orr[DH];
@@ -361,21 +370,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const long long bq = (long long)tile * G + g;
         sc *= bq < a.B ? a.out_scale[bq] : 0.f;
       }
-      // the group's previous store must have finished reading the staging tile
-      if (elected) bulk_wait_read0();
+      // the store that last used this staging tile must have finished reading it
+      if (elected) {
+        if (C::kOutBufs == 2) bulk_wait_read1(); else bulk_wait_read0();
+      }
       grp_bar();
+      uint8_t* dst = orow + ob * C::kOutBytes;
 #pragma unroll
       for (int c = 0; c < DH / 8; ++c) {
         uint32_t w[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           w[q] = pack_bf16x2(__uint_as_float(orr[8 * c + 2 * q]) * sc, __uint_as_float(orr[8 * c + 2 * q + 1]) * sc);
-        *reinterpret_cast<uint4*>(orow + ((c ^ oswz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dst + ((c ^ oswz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
       fence_async_smem();
       grp_bar();
       if (elected) {
-        tma_store_3d(&tmO, sOut + grp * C::kOutBytes, h * DH, 0, tile * G);
+        tma_store_3d(&tmO, sOut + (grp * C::kOutBufs + ob) * C::kOutBytes, h * DH, 0, tile * G);
         bulk_commit();
       }
     };
@@ -434,15 +446,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <int LP, int DH, bool PTMEM>
+template <int LP, int DH, bool PTMEM, int LC>
 int launch(const void* qkv, void* o, int64_t B, int L, int heads, float scale, const float* out_scale, cudaStream_t st) {
   using C = Cfg<LP, DH, PTMEM>;
-  auto kern = attn_fwd_tc_kernel<LP, DH, PTMEM>;
+  auto kern = attn_fwd_tc_kernel<LP, DH, PTMEM, LC>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) {
       set_error("attention_tc: cudaFuncSetAttribute(%d) failed: %s", C::kSmem, cudaGetErrorString(e));
+      (void)cudaGetLastError();
       return (int)e;
     }
     configured = true;
@@ -472,7 +485,7 @@ int launch(const void* qkv, void* o, int64_t B, int L, int heads, float scale, c
 
 // shapes the tcgen05 forward covers: bf16, dh 32 / 64, L <= 64, whole 128-byte boxes of heads, 16-byte aligned rows
 bool attention_tc_supported(int L, int heads, int dh) {
-  return (dh == 32 || dh == 64) && L >= 1 && L <= 64 && (heads * dh) % 64 == 0;
+  return (dh == 32 || dh == 64) && L >= 1 && L <= 64 && heads >= 2 && (heads * dh) % 64 == 0;
 }
 
 // variant: 0 = probabilities through tensor memory (A operand of P V read from TMEM), 1 = through shared memory
@@ -482,15 +495,22 @@ int attention_fwd_tc(const void* qkv, void* o, int64_t B, int L, int heads, int 
     set_error("attention_fwd_tc: qkv / o must be 16-byte aligned");
     return AFB_ERR_INVALID;
   }
-#define AFB_TC_LAUNCH(LP, DH)                                                                              \
-  return variant == 1 ? attn_tc::launch<LP, DH, false>(qkv, o, B, L, heads, scale, out_scale, st)          \
-                      : attn_tc::launch<LP, DH, true>(qkv, o, B, L, heads, scale, out_scale, st)
+#define AFB_TC_LAUNCH(LP, DH, LC)                                                                          \
+  return variant == 1 ? attn_tc::launch<LP, DH, false, LC>(qkv, o, B, L, heads, scale, out_scale, st)      \
+                      : attn_tc::launch<LP, DH, true, LC>(qkv, o, B, L, heads, scale, out_scale, st)
+  // the dataset lengths get their own instantiation (22 joints / 32 frames on SHREC and DHG, 46 / 64 on LMDHG)
   if (dh == 32) {
-    if (L <= 32) AFB_TC_LAUNCH(32, 32);
-    AFB_TC_LAUNCH(64, 32);
+    if (L == 22) AFB_TC_LAUNCH(32, 32, 22);
+    if (L == 32) AFB_TC_LAUNCH(32, 32, 32);
+    if (L < 32) AFB_TC_LAUNCH(32, 32, 0);
+    if (L == 46) AFB_TC_LAUNCH(64, 32, 46);
+    if (L == 64) AFB_TC_LAUNCH(64, 32, 64);
+    AFB_TC_LAUNCH(64, 32, 0);
   }
-  if (L <= 32) AFB_TC_LAUNCH(32, 64);
-  AFB_TC_LAUNCH(64, 64);
+  if (L == 32) AFB_TC_LAUNCH(32, 64, 32);
+  if (L < 32) AFB_TC_LAUNCH(32, 64, 0);
+  if (L == 64) AFB_TC_LAUNCH(64, 64, 64);
+  AFB_TC_LAUNCH(64, 64, 0);
 #undef AFB_TC_LAUNCH
 }
 

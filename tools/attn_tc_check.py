@@ -20,7 +20,7 @@ def ref(qkv, B, L, H):
 
 def run(mode, qkv, B, L, H, out_scale=None):
     if mode == "mma":
-        os.environ.pop("AFB_ATTN_TC", None)
+        os.environ["AFB_ATTN_TC"] = "0"
     else:
         os.environ["AFB_ATTN_TC"] = "1" if mode == "tc" else "2"
     return ops.attention_fwd(qkv, B, L, H, out_scale)

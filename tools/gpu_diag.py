@@ -444,7 +444,32 @@ def grp_attention():
                 keep = torch.tensor([0.0 if i % 3 == 1 else 1.25 for i in range(B)], device=DEV)
                 report(f"attention_fwd*keep B={B} L={L} dh={dh} {dtp}", ops.attention_fwd(qkv, B, L, H, out_scale=keep),
                        keep.repeat_interleave(L)[:, None] * oref.detach(), tol)
+
+    def attn_variants():
+        """every forward kernel on the shapes all of them cover (AFB_ATTN_TC: 0 = warp-level MMA, 1 = tcgen05 with the
+        probabilities in tensor memory, 2 = tcgen05 with the probabilities staged in shared memory); multi-tile batches,
+        partial last tiles, every (LP, dh) instantiation incl. the runtime-length ones"""
+        saved = os.environ.get("AFB_ATTN_TC")
+        try:
+            for (B, L, H, dh) in ((5, 22, 8, 32), (1237, 22, 8, 32), (301, 32, 8, 32), (7, 9, 4, 32), (130, 46, 8, 32),
+                                  (75, 64, 8, 32), (3, 50, 2, 32), (203, 32, 8, 64), (9, 13, 4, 64), (41, 46, 8, 64),
+                                  (66, 64, 4, 64), (5, 40, 3, 64)):
+                D = H * dh
+                qkv = g(B * L, 3 * D, seed=L + B, dtype=torch.bfloat16)
+                oref = _attn_ref(qkv.float(), B, L, H)
+                keep = torch.tensor([0.0 if i % 3 == 1 else 1.25 for i in range(B)], device=DEV)
+                for mode, name in (("0", "mma"), ("1", "tc"), ("2", "tc-smemP")):
+                    os.environ["AFB_ATTN_TC"] = mode
+                    report(f"attention_fwd[{name}] B={B} L={L} H={H} dh={dh}", ops.attention_fwd(qkv, B, L, H), oref, 1e-2)
+                    report(f"attention_fwd[{name}]*keep B={B} L={L} H={H} dh={dh}", ops.attention_fwd(qkv, B, L, H, out_scale=keep),
+                           keep.repeat_interleave(L)[:, None] * oref, 1e-2)
+        finally:
+            if saved is None:
+                os.environ.pop("AFB_ATTN_TC", None)
+            else:
+                os.environ["AFB_ATTN_TC"] = saved
     check(attn)
+    check(attn_variants)
 
 
 # --------------------------------------------------------------------------------------------

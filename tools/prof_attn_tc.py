@@ -10,7 +10,7 @@ from altformer_b200 import ops  # noqa: E402
 B, L, H, DH = (int(os.environ.get(k, d)) for k, d in (("B", 8192), ("L", 22), ("H", 8), ("DH", 32)))
 mode = os.environ.get("MODE", "tc")
 if mode == "mma":
-    os.environ.pop("AFB_ATTN_TC", None)
+    os.environ["AFB_ATTN_TC"] = "0"
 else:
     os.environ["AFB_ATTN_TC"] = "1" if mode == "tc" else "2"
 qkv = (torch.randn(B * L, 3 * H * DH, device="cuda") * 1.5).to(torch.bfloat16)
