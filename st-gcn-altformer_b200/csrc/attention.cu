@@ -13,6 +13,8 @@ namespace afb {
 bool attention_mma_supported(int L, int heads, int dh);
 int attention_fwd_mma(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, const float* out_scale, cudaStream_t st);
 bool attention_tc_supported(int L, int heads, int dh);
+bool attention_bwd_tc_supported(int L, int heads, int dh);
+int attention_bwd_tc(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st);
 int attention_fwd_tc(const void* qkv, void* o, int64_t B, int L, int heads, int dh, float scale, const float* out_scale, int variant,
                      cudaStream_t st);
 int attention_bwd_mma(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st);
@@ -413,6 +415,11 @@ extern "C" int afb_attention_bwd(const void* qkv, const void* dO, void* dqkv, in
       attn_long_bwd_kernel<float><<<(unsigned)(B * heads), kLongWarps * 32, smem, as_stream(s)>>>((const float*)qkv, (const float*)dO, (float*)dqkv, L, heads, dh, scale);
     }
     return check_launch("attention_long_bwd");
+  }
+  // AFB_ATTN_TC_BWD=1: backward on the tcgen05 / TMEM / TMA kernel (attention_tc.cu, dh 32)
+  if (dt == AFB_BF16 && attention_bwd_tc_supported(L, heads, dh)) {
+    const char* tc = getenv("AFB_ATTN_TC_BWD");
+    if (tc != nullptr && tc[0] == '1') return attention_bwd_tc(qkv, dO, dqkv, B, L, heads, dh, scale, as_stream(s));
   }
   if (use_mma(dt, L, heads, dh)) return attention_bwd_mma(qkv, dO, dqkv, B, L, heads, dh, scale, as_stream(s));
   const int per_warp = 4 * L * (dh + 1) + 2 * L * (L + 1) + 2;

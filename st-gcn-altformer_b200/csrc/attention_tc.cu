@@ -174,6 +174,7 @@ struct TcArgs {
   int L, heads, D;
   int tiles;              // ceil(B / G)
   float scale_log2;       // softmax scale * log2(e)
+  float scale;            // softmax scale (backward: folded into dS)
   const float* out_scale; // optional [B]
 };
 
@@ -472,6 +473,7 @@ int launch(const void* qkv, void* o, int64_t B, int L, int heads, float scale, c
   a.B = B; a.L = L; a.heads = heads; a.D = D;
   a.tiles = (int)((B + C::G - 1) / C::G);
   a.scale_log2 = scale * 1.4426950408889634f;
+  a.scale = scale;
   a.out_scale = out_scale;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -479,6 +481,331 @@ int launch(const void* qkv, void* o, int64_t B, int L, int heads, float scale, c
   const int grid = a.tiles < sms ? a.tiles : sms;
   kern<<<grid, kThreads, C::kSmem, st>>>(tmQ, tmO, a);
   return check_launch("attention_fwd_tc");
+}
+
+
+// ==================================================================================================================
+// Backward (dh = 32), same packed tile: per (tile, head) item five products on the tensor pipe
+//     S = Q K^T and dP = dO V^T          [128 x 128] each, K = dh                 -> TMEM (single buffer, drained at once)
+//     dV = P^T dO,  dK = dS^T Q,  dQ = dS K   [128 x dh] each, K = 128             -> TMEM (double-buffered per group)
+// Thread = tile row, so the softmax backward is thread-local too: P_j = exp2(c s_j - c m) / sum, delta = sum_j P_j dP_j,
+// dS_j = scale P_j (dP_j - delta).  P and dS are needed TRANSPOSED (keys as the M dimension): one bf16 copy in shared
+// memory read through MN-major A descriptors.  Only the diagonal blocks are non-zero -- tile rows 0..63 hold keys 0..63
+// only, rows 64..127 keys 64..127 -- so each operand keeps just the two [64 rows x 64 keys] blocks plus ONE 2 KB zero
+// block that the descriptor's leading-dimension offset substitutes for the all-zero half of every k-step (18 KB instead of
+// 32 KB per operand).  dQ = dS K needs dS un-transposed: that copy lives in tensor memory (A operand from TMEM).
+// Warp roles as in the forward: 0 = TMA producer (q|k|v|dO boxes), 1 = S / dP issuer, 10 = dV / dK / dQ issuer,
+// 2..5 and 6..9 = two softmax / epilogue groups owning alternate heads.
+// ==================================================================================================================
+constexpr int kBwdStageBytes = 4 * kBoxBytes;      // q | k | v | dO
+constexpr int kBwdStages = 2;
+constexpr int kTBlock = 64 * 128;                  // one [64 rows x 64 keys] block of a transposed operand
+constexpr int kTOperand = 2 * kTBlock + 2048;      // kb0 | zero block | kb1
+constexpr int kBwdOutTile = 128 * 64;              // one staged [128 rows x 32 channels] output tile
+
+template <int LP>
+struct BwdCfg {
+  static constexpr int G = 128 / LP;
+  static constexpr int kSmem = 1024 + kBwdStages * kBwdStageBytes + 2 * kTOperand + 2 * 3 * kBwdOutTile + 256;
+};
+
+template <int LP, int LC>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                   const __grid_constant__ CUtensorMap tmDQ, const TcArgs a) {
+  using C = BwdCfg<LP>;
+  constexpr int G = C::G, DH = 32, HB = 2, kStages = kBwdStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sStage = base;
+  const uint32_t sPT = base + kStages * kBwdStageBytes;     // P  (transposed use): kb0 | Z | kb1
+  const uint32_t sST = sPT + kTOperand;                     // dS (transposed use)
+  const uint32_t sOut = sST + kTOperand;                    // [group][dq | dk | dv] staging tiles
+  const uint32_t sBar = sOut + 2 * 3 * kBwdOutTile;
+  uint8_t* pPT = smem + kStages * kBwdStageBytes;
+  uint8_t* pST = pPT + kTOperand;
+  uint8_t* pOut = pST + kTOperand;
+  auto full_bar = [&](int st) { return sBar + 8 * st; };
+  auto empty_bar = [&](int st) { return sBar + 8 * (kStages + st); };
+  // S / dP and the P / dS operands are single buffers used by the two groups in turn, but every barrier exists once PER
+  // GROUP (index = item & 1): a waiter is then never more than one phase away from the barrier it polls
+  auto sfull_bar = [&](int b) { return sBar + 8 * (2 * kStages + b); };
+  auto sfree_bar = [&](int b) { return sBar + 8 * (2 * kStages + 2 + b); };
+  auto pfull_bar = [&](int b) { return sBar + 8 * (2 * kStages + 4 + b); };
+  auto pfree_bar = [&](int b) { return sBar + 8 * (2 * kStages + 6 + b); };
+  auto ofull_bar = [&](int b) { return sBar + 8 * (2 * kStages + 8 + b); };
+  auto ofree_bar = [&](int b) { return sBar + 8 * (2 * kStages + 10 + b); };
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nbox = a.heads / HB;
+  int my_tiles = 0;
+  for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) ++my_tiles;
+  const int total = my_tiles * a.heads;
+
+  if (tid == 0) {
+    for (int st = 0; st < kStages; ++st) { mbar_init(full_bar(st), 1); mbar_init(empty_bar(st), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sfull_bar(b), 1); mbar_init(sfree_bar(b), 4);
+      mbar_init(pfull_bar(b), 4); mbar_init(pfree_bar(b), 1);
+      mbar_init(ofull_bar(b), 1); mbar_init(ofree_bar(b), 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem), 512);
+  {   // transposed operands: everything outside the diagonal blocks (and the zero blocks) stays zero for the whole kernel
+    uint4* z = reinterpret_cast<uint4*>(pPT);
+    for (int i = tid; i < (2 * kTOperand) >> 4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  // tensor memory: S 0..127 | dP 128..255 | OUT[b] 256 + 96 b: dQ, dK, dV (32 columns each) | dS (bf16 pairs) 448..511
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) {
+        for (int bx = 0; bx < nbox; ++bx) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), kBwdStageBytes);
+          const uint32_t dst = sStage + stage * kBwdStageBytes;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) tma_load_3d(&tmQ, full_bar(stage), dst + q * kBoxBytes, q * a.D + bx * 64, 0, t * G);
+          tma_load_3d(&tmDO, full_bar(stage), dst + 3 * kBoxBytes, bx * 64, 0, t * G);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 10) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(128, 128, 0, 0);     // A, B K-major
+      constexpr uint32_t idesc_t = make_idesc(128, DH, 1, 1);      // A MN-major (transposed P / dS), B MN-major
+      constexpr uint32_t idesc_q = make_idesc(128, DH, 0, 1);      // A from TMEM (K-major), B MN-major
+      auto stage_of = [&](int item, uint32_t& ph) {
+        const int box = item / HB;
+        ph = (uint32_t)((box / kStages) & 1);
+        return box % kStages;
+      };
+      if (warp == 1) {
+        for (int i = 0; i < total; ++i) {   // S(i) = Q K^T, dP(i) = dO V^T
+          uint32_t ph;
+          const int stage = stage_of(i, ph);
+          const int slot = i % HB;
+          if (slot == 0) mbar_wait(full_bar(stage), ph);
+          if (i >= 1) mbar_wait(sfree_bar((i - 1) & 1), (uint32_t)(((i - 1) >> 1) & 1));   // item i - 1 has been read out
+          tc_fence_after();
+          const uint32_t q_addr = sStage + stage * kBwdStageBytes + slot * (DH * 2);
+          const uint32_t k_addr = q_addr + kBoxBytes, v_addr = q_addr + 2 * kBoxBytes, do_addr = q_addr + 3 * kBoxBytes;
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_bf16(tmem, make_desc(q_addr + k * 32, 16, 1024), make_desc(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_bf16(tmem + 128u, make_desc(do_addr + k * 32, 16, 1024), make_desc(v_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(sfull_bar(i & 1));
+        }
+      } else {
+        for (int j = 0; j < total; ++j) {   // dV = P^T dO, dK = dS^T Q, dQ = dS K
+          uint32_t ph;
+          const int stage = stage_of(j, ph);
+          const int slot = j % HB, b = j & 1;
+          mbar_wait(pfull_bar(b), (uint32_t)((j >> 1) & 1));
+          mbar_wait(ofree_bar(b), (uint32_t)(((j >> 1) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t q_addr = sStage + stage * kBwdStageBytes + slot * (DH * 2);
+          const uint32_t k_addr = q_addr + kBoxBytes, do_addr = q_addr + 3 * kBoxBytes;
+          const uint32_t out = tmem + 256u + (uint32_t)(b * 96);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            // A operand of k-step ks (16 tile rows): M group 0 = keys 0..63, group 1 = keys 64..127; the group that is all
+            // zero for these rows is the shared zero block (start / leading offset chosen accordingly)
+            const uint32_t t_start = ks < 4 ? (uint32_t)(ks * 2048) : (uint32_t)kTBlock;
+            const uint32_t t_lbo = ks < 4 ? (uint32_t)(kTBlock - ks * 2048) : (uint32_t)(2048 + (ks - 4) * 2048);
+            const uint64_t b_do = make_desc(do_addr + ks * 2048, 8192, 1024);
+            const uint64_t b_q = make_desc(q_addr + ks * 2048, 8192, 1024);
+            const uint64_t b_k = make_desc(k_addr + ks * 2048, 8192, 1024);
+            umma_bf16(out + 64u, make_desc(sPT + t_start, t_lbo, 1024), b_do, idesc_t, ks != 0 ? 1u : 0u);       // dV
+            umma_bf16(out + 32u, make_desc(sST + t_start, t_lbo, 1024), b_q, idesc_t, ks != 0 ? 1u : 0u);        // dK
+            umma_bf16_ts(out, tmem + 448u + (uint32_t)(ks * 8), b_k, idesc_q, ks != 0 ? 1u : 0u);                 // dQ
+          }
+          umma_commit(ofull_bar(b));
+          umma_commit(pfree_bar(b));
+          if (slot == HB - 1) umma_commit(empty_bar(stage));
+        }
+      }
+    }
+  } else {
+    const int grp = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int g = r / LP;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int L = LC != 0 ? LC : a.L;
+    const int key0 = g * LP;
+    // transposed operands: tile row r lives in block r / 64 (kb0 at 0, kb1 behind the zero block), its keys at (key0 & 63)
+    const int trow = (r >> 6) * (kTBlock + 2048) + (r & 63) * 128;
+    const int pchunk0 = (key0 & 63) >> 3;
+    const uint32_t ds_taddr = lane_addr + 448u + (uint32_t)(key0 >> 1);
+    uint8_t* orow = pOut + grp * 3 * kBwdOutTile + r * 64;
+    const int oswz = (r >> 1) & 3;
+    const bool elected = ((warp - 2) & 3) == 0 && lane == 0;
+    auto grp_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
+    const uint32_t ofull = ofull_bar(grp), ofree = ofree_bar(grp), sfull = sfull_bar(grp), sfree = sfree_bar(grp), pfull = pfull_bar(grp);
+    if (grp == 0) {   // zero the dS region of tensor memory once (each warp its lane quarter)
+      uint32_t z[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) z[k] = 0u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st16(lane_addr + 448u + (uint32_t)(c * 16), z);
+      tmem_wait_st();
+      tc_fence_before();
+    }
+    asm volatile("bar.sync 3, 256;" ::: "memory");   // both groups: the zeroing precedes every dS write
+    tc_fence_after();
+    int o_tile = blockIdx.x, o_head = grp;
+    // epilogue of item j: dQ | dK | dV rows -> bf16 -> staging -> three TMA stores into dqkv
+    auto o_phase = [&](int j) {
+      const int tile = o_tile, h = o_head;
+      o_head += 2;
+      if (o_head >= a.heads) { o_head -= a.heads; o_tile += gridDim.x; }
+      mbar_wait(ofull, (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      uint32_t orr[96];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tmem_ld32_issue(lane_addr + 256u + (uint32_t)(grp * 96 + c * 32), orr + c * 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ofree);
+      if (elected) bulk_wait_read0();   // the group's previous stores have read the staging tiles
+      grp_bar();
+#pragma unroll
+      for (int t3 = 0; t3 < 3; ++t3)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            w[q] = pack_bf16x2(__uint_as_float(orr[t3 * 32 + 8 * c + 2 * q]), __uint_as_float(orr[t3 * 32 + 8 * c + 2 * q + 1]));
+          *reinterpret_cast<uint4*>(orow + t3 * kBwdOutTile + ((c ^ oswz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      fence_async_smem();
+      grp_bar();
+      if (elected) {
+#pragma unroll
+        for (int t3 = 0; t3 < 3; ++t3)
+          tma_store_3d(&tmDQ, sOut + (grp * 3 + t3) * kBwdOutTile, t3 * a.D + h * DH, 0, tile * G);
+        bulk_commit();
+      }
+    };
+    for (int i = grp; i < total; i += 2) {
+      if (i >= 2) o_phase(i - 2);   // drains OUT[grp] before the products of item i need it
+      mbar_wait(sfull, (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      uint32_t sr[LP], dr[LP];
+#pragma unroll
+      for (int c = 0; c < LP / 32; ++c) {
+        tmem_ld32_issue(lane_addr + (uint32_t)(key0 + c * 32), sr + c * 32);
+        tmem_ld32_issue(lane_addr + 128u + (uint32_t)(key0 + c * 32), dr + c * 32);
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sfree);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < LP; ++j)
+        if (j < L) mx = fmaxf(mx, __uint_as_float(sr[j]));
+      const float off = mx * a.scale_log2;
+      float sum = 0.f, dot = 0.f;
+      float pv[LP];
+#pragma unroll
+      for (int j = 0; j < LP; ++j) {
+        pv[j] = j < L ? ex2(fmaf(__uint_as_float(sr[j]), a.scale_log2, -off)) : 0.f;
+        sum += pv[j];
+        dot = fmaf(pv[j], __uint_as_float(dr[j]), dot);
+      }
+      const float inv = 1.0f / sum;
+      const float delta = dot * inv;                 // sum_j P_j dP_j
+      const float sinv = inv * a.scale;              // softmax scale folded into dS
+      uint32_t pk[LP / 2], dk[LP / 2];
+#pragma unroll
+      for (int j = 0; j < LP; j += 2) {
+        pk[j >> 1] = pack_bf16x2(pv[j] * inv, pv[j + 1] * inv);
+        dk[j >> 1] = pack_bf16x2(pv[j] * sinv * (__uint_as_float(dr[j]) - delta), pv[j + 1] * sinv * (__uint_as_float(dr[j + 1]) - delta));
+      }
+      if (i >= 1) mbar_wait(pfree_bar((i - 1) & 1), (uint32_t)(((i - 1) >> 1) & 1));   // the products of item i - 1 have read P / dS
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < LP / 8; ++c) {
+        const int off16 = ((pchunk0 + c) ^ (r & 7)) << 4;
+        *reinterpret_cast<uint4*>(pPT + trow + off16) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        *reinterpret_cast<uint4*>(pST + trow + off16) = make_uint4(dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
+      }
+#pragma unroll
+      for (int c = 0; c < LP / 32; ++c) tmem_st16(ds_taddr + (uint32_t)(c * 16), dk + c * 16);
+      tmem_wait_st();
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pfull);
+    }
+    // the group's last item (every earlier one was drained at the top of a later iteration)
+    const int last = total > grp ? ((total - 1 - grp) & ~1) + grp : -1;
+    if (last >= 0) o_phase(last);
+    if (elected) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int LP, int LC>
+int launch_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int heads, float scale, cudaStream_t st) {
+  using C = BwdCfg<LP>;
+  auto kern = attn_bwd_tc_kernel<LP, LC>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    if (e != cudaSuccess) {
+      set_error("attention_bwd_tc: cudaFuncSetAttribute(%d) failed: %s", C::kSmem, cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int D = heads * 32;
+  CUtensorMap tmQ, tmDO, tmDQ;
+  int rc;
+  if ((rc = make_tensor_map_bf16_box3(&tmQ, qkv, (uint64_t)3 * D, (uint64_t)L, (uint64_t)B, (uint64_t)3 * D, (uint64_t)L * 3 * D, 64, LP, C::G, 128)))
+    return rc;
+  if ((rc = make_tensor_map_bf16_box3(&tmDO, dO, (uint64_t)D, (uint64_t)L, (uint64_t)B, (uint64_t)D, (uint64_t)L * D, 64, LP, C::G, 128)))
+    return rc;
+  if ((rc = make_tensor_map_bf16_box3(&tmDQ, dqkv, (uint64_t)3 * D, (uint64_t)L, (uint64_t)B, (uint64_t)3 * D, (uint64_t)L * 3 * D, 32, LP, C::G, 64)))
+    return rc;
+  TcArgs a;
+  a.B = B; a.L = L; a.heads = heads; a.D = D;
+  a.tiles = (int)((B + C::G - 1) / C::G);
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.scale = scale;
+  a.out_scale = nullptr;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = a.tiles < sms ? a.tiles : sms;
+  kern<<<grid, kThreads, C::kSmem, st>>>(tmQ, tmDO, tmDQ, a);
+  return check_launch("attention_bwd_tc");
 }
 
 }  // namespace attn_tc
@@ -512,6 +839,23 @@ int attention_fwd_tc(const void* qkv, void* o, int64_t B, int L, int heads, int 
   if (L == 64) AFB_TC_LAUNCH(64, 64, 64);
   AFB_TC_LAUNCH(64, 64, 0);
 #undef AFB_TC_LAUNCH
+}
+
+// backward on the same paths: dh 32, even head count (two heads per 128-byte box)
+bool attention_bwd_tc_supported(int L, int heads, int dh) { return dh == 32 && L >= 1 && L <= 64 && heads >= 2 && heads % 2 == 0; }
+
+int attention_bwd_tc(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int heads, int dh, float scale, cudaStream_t st) {
+  if (((uintptr_t)qkv & 15) != 0 || ((uintptr_t)dO & 15) != 0 || ((uintptr_t)dqkv & 15) != 0) {
+    set_error("attention_bwd_tc: operands must be 16-byte aligned");
+    return AFB_ERR_INVALID;
+  }
+  (void)dh;
+  if (L == 22) return attn_tc::launch_bwd<32, 22>(qkv, dO, dqkv, B, L, heads, scale, st);
+  if (L == 32) return attn_tc::launch_bwd<32, 32>(qkv, dO, dqkv, B, L, heads, scale, st);
+  if (L < 32) return attn_tc::launch_bwd<32, 0>(qkv, dO, dqkv, B, L, heads, scale, st);
+  if (L == 46) return attn_tc::launch_bwd<64, 46>(qkv, dO, dqkv, B, L, heads, scale, st);
+  if (L == 64) return attn_tc::launch_bwd<64, 64>(qkv, dO, dqkv, B, L, heads, scale, st);
+  return attn_tc::launch_bwd<64, 0>(qkv, dO, dqkv, B, L, heads, scale, st);
 }
 
 }  // namespace afb

@@ -70,6 +70,39 @@ def main():
         if B >= 1024:
             line += f"   (HBM floor {B * L * 4 * D * 2 / 6542.1e3:.1f}us)"
         print(line, flush=True)
+        if dh == 32 and H % 2 == 0:   # backward: tcgen05 kernel vs warp-level kernel vs torch autograd
+            qr = qkv.float().requires_grad_(True)
+            do = (torch.randn(B * L, D, device=dev)).to(torch.bfloat16)
+            ref(qr, B, L, H).backward(do.float())
+            line = f"      backward:"
+            for mode in ("mma", "tc"):
+                os.environ["AFB_ATTN_TC_BWD"] = "1" if mode == "tc" else "0"
+                try:
+                    got = ops.attention_bwd(qkv, do, B, L, H)
+                    torch.cuda.synchronize()
+                    e = rel(got, qr.grad)
+                    parts = [rel(got[:, k * D:(k + 1) * D], qr.grad[:, k * D:(k + 1) * D]) for k in range(3)]
+                    ok = e < 1e-2
+                    bad += 0 if ok or mode == "mma" else 1
+                    line += f"  {mode} {e:.2e} (dq {parts[0]:.1e} dk {parts[1]:.1e} dv {parts[2]:.1e}){'' if ok else ' FAIL'}"
+                    if B >= 1024:
+                        for _ in range(3):
+                            ops.attention_bwd(qkv, do, B, L, H)
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        torch.cuda.synchronize()
+                        e0.record()
+                        for _ in range(10):
+                            ops.attention_bwd(qkv, do, B, L, H)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        line += f" {100 * e0.elapsed_time(e1):6.1f}us"
+                except Exception as ex:  # noqa: BLE001
+                    bad += 1
+                    line += f"  {mode} ERROR {str(ex)[:120]}"
+            os.environ.pop("AFB_ATTN_TC_BWD", None)
+            if B >= 1024:
+                line += f"   (HBM floor {B * L * 7 * D * 2 / 6542.1e3:.1f}us)"
+            print(line, flush=True)
     print("attn_tc_check:", "ok" if bad == 0 else f"{bad} FAILED")
     return bad
 
