@@ -463,7 +463,21 @@ def grp_attention():
                     report(f"attention_fwd[{name}] B={B} L={L} H={H} dh={dh}", ops.attention_fwd(qkv, B, L, H), oref, 1e-2)
                     report(f"attention_fwd[{name}]*keep B={B} L={L} H={H} dh={dh}", ops.attention_fwd(qkv, B, L, H, out_scale=keep),
                            keep.repeat_interleave(L)[:, None] * oref, 1e-2)
+            # backward: warp-level kernel vs tcgen05 kernel (dh 32) vs torch autograd
+            for (B, L, H, dh) in ((5, 22, 8, 32), (1237, 22, 8, 32), (301, 32, 8, 32), (7, 9, 4, 32), (130, 46, 8, 32), (75, 64, 8, 32),
+                                  (3, 50, 2, 32)):
+                D = H * dh
+                qkv = g(B * L, 3 * D, seed=L + B, dtype=torch.bfloat16)
+                do = g(B * L, D, seed=5, dtype=torch.bfloat16)
+                qr = qkv.float().requires_grad_(True)
+                _attn_ref(qr, B, L, H).backward(do.float())
+                for mode, name in (("0", "mma"), ("1", "tc")):
+                    os.environ["AFB_ATTN_TC_BWD"] = mode
+                    got = ops.attention_bwd(qkv, do, B, L, H)
+                    for k, part in enumerate(("dq", "dk", "dv")):
+                        report(f"attention_bwd[{name}] {part} B={B} L={L} H={H} dh={dh}", got[:, k * D:(k + 1) * D], qr.grad[:, k * D:(k + 1) * D], 1e-2)
         finally:
+            os.environ.pop("AFB_ATTN_TC_BWD", None)
             if saved is None:
                 os.environ.pop("AFB_ATTN_TC", None)
             else:
