@@ -519,6 +519,32 @@ def train_leg(env, cfg, B, steps, warmup, use_graph=True, seed_off=0):
                 h2d=x_pin.numel() * 4 + y_pin.numel() * 8, d2h=4, last_loss=st["last"])
 
 
+def dropin_leg(cfg, dev, B, steps=10, warmup=3):
+    """The drop-in path of INTEGRATION.md section 2 WITHOUT the trainer: the reference's own loop (train_sttran.py:89-102 --
+    model(x), CrossEntropyLoss, loss.backward(), torch.optim.AdamW.step(), zero_grad) on the CUDA modules, stock autograd,
+    no CUDA graph, no flat buffers.  Reported beside the trainer's step so the cost of staying on stock torch is on record."""
+    from altformer_b200 import ops
+    model = build_model(cfg, dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, weight_decay=0.1)
+    x, y = synthetic_batch(B, cfg["T"], cfg["V"], cfg["cls"], 4321)
+    x, y = x.to(dev), y.to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(model(x), y)
+        loss.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    ops.LAUNCHES[0] = 0
+    step()
+    launches = ops.LAUNCHES[0]
+    ms, med = timed(step, steps, False, dev)
+    return {"value": B / (ms * 1e-3), "unit": "seq/s", "ms_per_step": ms, "ms_per_step_median": med, "own_kernel_launches": launches,
+            "sample": f"{steps} steps of batch {B}: model(x) + cross_entropy + loss.backward() + torch.optim.AdamW, stock autograd, no trainer, no CUDA graph"}
+
+
 def run_train(env, cfg, args):
     B = args.batch or cfg["per_gpu_batch"]
     leg = train_leg(env, cfg, B, args.steps, args.warmup, use_graph=not args.no_graph)
@@ -566,6 +592,11 @@ def run_train(env, cfg, args):
         # N = 1 only: under torchrun the other ranks would idle in a barrier while rank 0 runs the CPU leg
         if cfg is CONFIGS[2] and not args.no_eager:
             del leg
+            torch.cuda.empty_cache()
+            try:
+                out["dropin_autograd"] = dropin_leg(cfg, env.dev, B)
+            except Exception as e:  # noqa: BLE001
+                out["dropin_autograd"] = {"unavailable": repr(e)[:200]}
             torch.cuda.empty_cache()
             try:
                 out["eager_gpu_baseline"] = eager_gpu_baseline(cfg, env.dev, B)

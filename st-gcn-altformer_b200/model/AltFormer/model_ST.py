@@ -20,12 +20,17 @@ class DropPath(nn.Module):
         super().__init__()
         self.drop_prob = float(drop_prob)
         self.pinned = None
+        self.queue = []
 
     def row_scale(self, B, device):
         if self.pinned is not None:
             return self.pinned
         if self.drop_prob == 0.0 or not self.training:
             return None
+        if self.queue:                      # drawn for the whole forward by prefill_drop_paths
+            m = self.queue.pop(0)
+            if m.shape[0] == B and m.device == device:
+                return m
         keep = 1.0 - self.drop_prob
         return torch.empty(B, device=device, dtype=torch.float32).bernoulli_(keep).div_(keep)  # RNG plumbing
 
@@ -35,6 +40,36 @@ class DropPath(nn.Module):
             return x
         flat = x.reshape(x.shape[0], -1)
         return AF.scale_rows_fn(flat, s).view_as(x)
+
+
+_KEEP_CACHE = {}
+
+
+def prefill_drop_paths(stages, device):
+    """Draw every DropPath mask of one forward (two per Block) with ONE uniform draw + compare + scale instead of a
+    bernoulli_ + div_ pair per mask (40 tiny launches per cfg2 step).  `stages` = [(blocks, B), ...]; each live DropPath gets
+    its two (B,) masks of 0 / 1/(1-p) queued in the order Block.forward_rows consumes them.  Same distribution as timm's
+    per-call bernoulli (reference: model_ST.py:84-87 via timm DropPath); tests pin masks through `pinned` as before."""
+    live = []
+    for blocks, B in stages:
+        for blk in blocks:
+            dp = blk.drop_path
+            if isinstance(dp, DropPath):
+                dp.queue = []
+                if dp.pinned is None and dp.drop_prob > 0.0 and dp.training:
+                    live.append((dp, B))
+    if not live:
+        return
+    key = (tuple((dp.drop_prob, B) for dp, B in live), str(device))
+    vec = _KEEP_CACHE.get(key)
+    if vec is None:
+        keep = torch.cat([torch.full((2 * B,), 1.0 - dp.drop_prob) for dp, B in live]).to(device)
+        vec = _KEEP_CACHE[key] = (keep, 1.0 / keep)
+    masks = (torch.rand(vec[0].shape[0], device=device) < vec[0]) * vec[1]
+    off = 0
+    for dp, B in live:
+        dp.queue = [masks[off:off + B], masks[off + B:off + 2 * B]]
+        off += 2 * B
 
 
 def _rows(x):
@@ -155,6 +190,7 @@ class ST(nn.Module):
         N, T, V = dims
         if V != self.num_joints or T != self.num_frame:
             raise RuntimeError(f"ST built for num_frame={self.num_frame}, num_joints={self.num_joints}; got T={T}, V={V}")
+        prefill_drop_paths([(self.Spatial_blocks, N * T), (self.blocks, N)], tok.device)
         e = self.Spatial_patch_to_embedding
         h = AF.linear(tok, e.weight, e.bias, pos=self.Spatial_pos_embed)
         for blk in self.Spatial_blocks:

@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from altformer_b200 import functional as AF
-from .model_ST import Attention, Block, DropPath, Mlp, _head  # noqa: F401  (same classes as model_ST)
+from .model_ST import Attention, Block, DropPath, Mlp, _head, prefill_drop_paths  # noqa: F401  (same classes as model_ST)
 from .._tokens import to_tokens
 
 
@@ -49,6 +49,7 @@ class TS(nn.Module):
         N, T, V = dims
         if V != self.num_joints or T != self.num_frame:
             raise RuntimeError(f"TS built for num_frame={self.num_frame}, num_joints={self.num_joints}; got T={T}, V={V}")
+        prefill_drop_paths([(self.blocks, N * V), (self.Spatial_blocks, N)], tok.device)
         e = self.temporal_patch_to_embedding
         h = AF.linear(tok, e.weight, e.bias, pos=self.Temporal_pos_embed)
         for blk in self.blocks:
