@@ -14,5 +14,6 @@ from .model.AltFormer.model_TS import TS  # noqa: E402,F401
 from .model.AltFormer.ST_GCN_AltFormer import ST_GCN_AltFormer  # noqa: E402,F401
 from .trainer import DataParallelTrainer  # noqa: E402,F401
 from . import streams  # noqa: E402,F401
+from .STR_TTR import STR, TTR, STR_TTR  # noqa: E402,F401
 
 unit_gcn = unit_agcn  # north_star alias; the reference only defines unit_agcn (model/unit_agcn.py:31)

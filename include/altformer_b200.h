@@ -341,6 +341,9 @@ int afb_bone_stream(const float* x, const int32_t* parent, float* y, int64_t NT,
 int afb_motion_stream(const float* x, float* y, int N, int T, int V, afb_stream s);
 /* y = x - x[:, 0, joint, :] per sequence: palm-centre normalisation (data_process/Hand_Dataset.py:61, joint = 1); out of place */
 int afb_palm_center(const float* x, float* y, int N, int T, int V, int joint, afb_stream s);
+/* Hand_Dataset.data_aug for a batch on the device (data_process/Hand_Dataset.py:84-157): kind[n] in {0 scale, 1 shift, 2 noise on
+ * four joints, 3 time_interpolate, other = copy}, params[n][16] = factor | offset xyz | 4 joint ids + 4 x xyz | r; out of place */
+int afb_augment(const float* x, float* y, int64_t N, int T, int V, const int* kind, const float* params, afb_stream s);
 int afb_axpby(const float* a, float wa, const float* b, float wb, float* out, int64_t n, afb_stream s);
 /* Phase tensors of a strided temporal convolution (Unit2D stride (s, 1), model/net.py:24-27; TCN_GCN_unit stride 2 and its
  * down1, model/ST_TR/ST_TR_new.py:362-374).  scatter == 0: dst [N, To, V, C] = src[n, j * stride + phase, v, :] (zero past T);

@@ -364,6 +364,53 @@ def ts_forward(x, p, prefix, heads=8, keeps=None):
     return _head(h.mean(dim=1), p, prefix)
 
 
+def str_spec(prefix, cls, T, V, cin=128, d1=256, depth=6):
+    """state_dict of the reference's STR (STR_TTR/STR.py:89-148): ST's entries plus linear1."""
+    s = st_spec(prefix, cls, T, V, cin, d1, depth)
+    s[prefix + "linear1.weight"] = (2 * d1, d1)
+    s[prefix + "linear1.bias"] = (2 * d1,)
+    return s
+
+
+def strttr_spec(style, channel=3, cls=28, T=32, V=22, backbone=128):
+    """STR_TTR assembly (STR_TTR/STR_TTR.py:11-60): gcn, tcn and modelA = STR (style 'STR') or modelB = TTR (same entries as TS)."""
+    s = OrderedDict()
+    s.update(agcn_spec("gcn.", channel, backbone, V))
+    s.update(unit2d_spec("tcn.", backbone, backbone, 9))
+    s.update(str_spec("modelA.", cls, T, V, backbone) if style == "STR" else ts_spec("modelB.", cls, T, V, backbone))
+    return s
+
+
+def str_forward(x, p, prefix, heads=8, keeps=None):
+    """STR.forward (STR_TTR/STR.py:150-191): spatial stage -> mean over joints -> linear1 -> mean over frames -> (N, 2 d1)."""
+    N, C, T, V = x.shape
+    tok = x.permute(0, 2, 3, 1).reshape(N * T, V, C)
+    h = _stage(tok, p, prefix + "Spatial_patch_to_embedding", prefix + "Spatial_pos_embed",
+               prefix + "Spatial_blocks", _depth(p, prefix + "Spatial_blocks"), heads, keeps)
+    h = h.mean(dim=1).view(N, T, -1)
+    h = F.linear(h, p[prefix + "linear1.weight"], p[prefix + "linear1.bias"])
+    return h.mean(dim=1)
+
+
+def ttr_forward(x, p, prefix, heads=8, keeps=None):
+    """TTR.forward (STR_TTR/TTR.py:151-221): temporal stage -> max over frames -> Spatial_patch_to_embedding (no positional
+    term) -> mean over joints -> mlp_head."""
+    N, C, T, V = x.shape
+    tok = x.permute(0, 3, 2, 1).reshape(N * V, T, C)
+    h = _stage(tok, p, prefix + "temporal_patch_to_embedding", prefix + "Temporal_pos_embed",
+               prefix + "blocks", _depth(p, prefix + "blocks"), heads, keeps)
+    h = h.max(dim=1).values.view(N, V, -1)
+    h = F.linear(h, p[prefix + "Spatial_patch_to_embedding.weight"], p[prefix + "Spatial_patch_to_embedding.bias"])
+    return _head(h.mean(dim=1), p, prefix)
+
+
+def strttr_forward(x, p, A, style="STR", training=False, keeps=None):
+    """STR_TTR.forward (STR_TTR/STR_TTR.py:62-84): x (N,T,V,3) -> STR features (N, 512) | TTR logits (N, cls)."""
+    x = x.permute(0, 3, 1, 2).contiguous()
+    f = unit2d_forward(agcn_forward(x, p, "gcn.", A, training), p, "tcn.", training)
+    return str_forward(f, p, "modelA.", keeps=keeps) if style == "STR" else ttr_forward(f, p, "modelB.", keeps=keeps)
+
+
 def backbone_forward(x, p, A, training=False, boundary=None):
     """(N,T,V,3) -> (N,128,T,V): gcn0 then tcn0."""
     x = x.permute(0, 3, 1, 2).contiguous()
@@ -401,6 +448,27 @@ def motion_stream(x):
     """x (N,T,V,3): next frame minus this frame, last frame zero (Hand_Dataset.py:183-198)."""
     out = torch.zeros_like(x)
     out[:, :-1] = x[:, 1:] - x[:, :-1]
+    return out
+
+
+def augment(x, kind, params):
+    """Hand_Dataset.data_aug with the random draws made explicit (data_process/Hand_Dataset.py:84-157).  x (N, T, V, 3);
+    kind (N,) ints: 0 scale (:86-96) | 1 shift (:98-107) | 2 noise on four joints (:109-123) | 3 time_interpolate (:125-142);
+    params (N, 16): factor | offset xyz | 4 joint ids + 4 x xyz offsets | r."""
+    out = x.clone()
+    N, T, V, _ = x.shape
+    for n in range(N):
+        k, p = int(kind[n]), params[n]
+        if k == 0:
+            out[n] = x[n] * p[0]
+        elif k == 1:
+            out[n] = x[n] + p[:3]
+        elif k == 2:
+            for q in range(4):
+                out[n, :, int(p[q])] += p[4 + 3 * q: 7 + 3 * q]
+        elif k == 3 and T > 1:
+            res = x[n, :-1] + p[0] * (x[n, 1:] - x[n, :-1])          # T - 1 interpolated frames ...
+            out[n] = torch.cat([res, res[-1:]], 0)                    # ... padded with the last one to time_len
     return out
 
 

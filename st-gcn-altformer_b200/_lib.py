@@ -118,6 +118,7 @@ def _declare(L):
         "afb_bone_stream": [vp, vp, vp, i64, i32, vp],
         "afb_motion_stream": [vp, vp, i32, i32, i32, vp],
         "afb_palm_center": [vp, vp, i32, i32, i32, i32, vp],
+        "afb_augment": [vp, vp, i64, i32, i32, vp, vp, vp],
         "afb_mul": [vp, vp, vp, i32, i64, vp],
         "afb_frame_phase": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "afb_axpby": [vp, f32, vp, f32, vp, i64, vp],

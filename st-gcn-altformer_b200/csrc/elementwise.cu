@@ -992,6 +992,46 @@ __global__ void __launch_bounds__(kBlock) palm_center_kernel(const float* __rest
     y[i] = x[i] - __ldg(x + n * per_seq + joint * 3 + c);
   }
 }
+// Hand_Dataset.data_aug (data_process/Hand_Dataset.py:84-157) for a whole batch on the device: one of four transforms per
+// sample, chosen and parameterised by the caller (kind[n], params[n][16]):
+//   0 scale            y = x * p[0]                                            (:86-96,  factor ~ U(0.8, 1.2))
+//   1 shift            y = x + p[0..2]                                         (:98-107, offset ~ U(-0.1, 0.1)^3)
+//   2 noise            y[:, j_k, :] = x + p[4 + 3k .. 6 + 3k] for the four joints j_k = p[k]   (:109-123)
+//   3 time_interpolate y[t] = x[t] + p[0] (x[t+1] - x[t]) for t < T - 1, last frame = the one before it   (:125-142)
+//   anything else      y = x
+__global__ void augment_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total, int T, int V,
+                               const int* __restrict__ kind, const float* __restrict__ params) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % 3);
+  const int v = (int)((i / 3) % V);
+  const int t = (int)((i / (3 * (int64_t)V)) % T);
+  const int64_t n = i / (3 * (int64_t)V * T);
+  const float* p = params + n * 16;
+  const int k = kind[n];
+  float val = x[i];
+  if (k == 0) {
+    val *= p[0];
+  } else if (k == 1) {
+    val += p[c];
+  } else if (k == 2) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if ((int)p[q] == v) val += p[4 + 3 * q + c];
+  } else if (k == 3 && T > 1) {
+    const int ts = t < T - 1 ? t : T - 2;                 // the padded last frame repeats frame T - 2's result
+    const int64_t j = i + (int64_t)(ts - t) * V * 3;
+    const float a = x[j], b = x[j + (int64_t)V * 3];
+    val = a + (b - a) * p[0];
+  }
+  y[i] = val;
+}
+extern "C" int afb_augment(const float* x, float* y, int64_t N, int T, int V, const int* kind, const float* params, afb_stream s) {
+  AFB_REQUIRE(x && y && x != y && kind && params && N > 0 && T > 0 && V > 0, "augment: bad args (out of place only)");
+  const int64_t total = N * T * V * 3;
+  augment_kernel<<<grid_for(total, kBlock), kBlock, 0, as_stream(s)>>>(x, y, total, T, V, kind, params);
+  return check_launch("augment");
+}
 extern "C" int afb_palm_center(const float* x, float* y, int N, int T, int V, int joint, afb_stream s) {
   AFB_REQUIRE(x && y && x != y && N > 0 && T > 0 && joint >= 0 && joint < V, "palm_center: bad args (out of place only)");
   const int64_t per_seq = (int64_t)T * V * 3;

@@ -389,6 +389,17 @@ def palm_center(x, joint=1):
     return y
 
 
+def augment(x, kind, params):
+    """x (N, T, V, 3) fp32, kind (N,) int32, params (N, 16) fp32 -> augmented copy (afb_augment)."""
+    need_cuda(x, kind, params)
+    N, T, V, _ = x.shape
+    if kind.dtype != torch.int32 or kind.shape != (N,) or params.dtype != torch.float32 or params.shape != (N, 16):
+        raise ValueError("augment: kind must be int32 (N,), params float32 (N, 16)")
+    y = torch.empty_like(x)
+    _call("afb_augment", ptr(x), ptr(y), N, T, V, ptr(kind), ptr(params), stream())
+    return y
+
+
 def motion_stream(x):
     need_cuda(x)
     N, T, V, _ = x.shape

@@ -304,3 +304,85 @@ def test_streams_against_reference_hand_dataset_gpu():
     assert torch.allclose(palm[0].cpu(), case["palm"], atol=1e-6)
     assert torch.allclose(ab.streams.motion(palm)[0].cpu(), case["motion"], atol=1e-6)
     assert torch.allclose(ab.streams.bone(palm)[0].cpu(), case["bone"], atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_augment_against_reference_data_aug_gpu():
+    """Hand_Dataset.data_aug on the device (afb_augment) vs the reference's own outputs for recorded draws
+    (augment_22.pt) and vs the oracle on a larger seeded batch; random_augment draws stay inside the reference's ranges."""
+    import altformer_b200 as ab
+    from oracle import altformer_oracle as O
+    from tests import goldenlib as G
+    case = G.load("augment_22")
+    y = ab.streams.augment(case["x"].cuda(), case["kind"].cuda(), case["params"].cuda())
+    assert torch.allclose(y.cpu(), case["y"], atol=1e-6)
+    g = torch.Generator().manual_seed(3)
+    N, T, V = 67, 32, 22
+    x = torch.randn(N, T, V, 3, generator=g)
+    kind = torch.randint(-1, 5, (N,), generator=g, dtype=torch.int32)          # incl. "no transform" values
+    params = torch.rand(N, 16, generator=g)
+    params[:, :4] = torch.rand(N, V, generator=g).argsort(1)[:, :4].float()    # distinct joints for the noise transform
+    got = ab.streams.augment(x.cuda(), kind.cuda(), params.cuda()).cpu()
+    p_noise = params.clone()
+    want = O.augment(x, kind, torch.where((kind == 2)[:, None], p_noise, params))
+    # kinds other than noise read params[:, :3] as factor / offset / r -- the joint ids written above are just numbers there
+    assert torch.allclose(got, want, atol=1e-6)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    xa, k, p = ab.streams.random_augment(x.cuda(), generator=gen)
+    assert xa.shape == x.shape and set(k.cpu().tolist()) <= {0, 1, 2, 3} and len(set(k.cpu().tolist())) == 4
+    pc, kc = p.cpu(), k.cpu()
+    assert ((pc[kc == 0, 0] >= 0.8) & (pc[kc == 0, 0] <= 1.2)).all() and (pc[kc == 1, :3].abs() <= 0.1).all()
+    assert (pc[kc == 2, 4:].abs() <= 0.1).all() and ((pc[kc == 3, 0] >= 0) & (pc[kc == 3, 0] <= 1)).all()
+    j = pc[kc == 2, :4]
+    assert ((j >= 0) & (j < V)).all() and all(len(set(r.tolist())) == 4 for r in j)
+    assert torch.allclose(xa.cpu(), O.augment(x, kc, pc), atol=1e-6)
+
+
+@pytest.mark.parametrize("style", ["STR", "TTR"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_strttr_against_reference_golden(style, mode):
+    """the STR / TTR ablation models (altformer_b200.STR_TTR, drop-in for STR_TTR/STR_TTR.py) on the CUDA kernels
+    vs the unmodified reference's train-mode output and parameter gradients (strttr_*_22.pt); strict state_dict load."""
+    import altformer_b200 as ab
+    from oracle import altformer_oracle as O
+    from tests import goldenlib as G
+    from tools.gpu_diag_modules import is_zero_class
+    d = G.load(f"strttr_{style}_22")
+    N, T, V, cls = d["shape"]
+    st = O.random_state(O.strttr_spec(style, 3, cls, T, V), d["state_seed"])
+    ab.set_precision(mode)
+    try:
+        m = ab.STR_TTR(3, cls, num_frame=T, num_joints=V, style=style, graph="graph.SHRE", graph_args={"labeling_mode": "spatial"})
+        res = m.load_state_dict(st, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        for mod in m.modules():
+            if type(mod).__name__ == "DropPath":
+                mod.drop_prob = 0.0
+        m = m.cuda().train()
+        x, _ = O.synthetic_batch(N, T, V, cls, d["batch_seed"])
+        y = m(x.cuda())
+        assert y.dtype == torch.float32 and tuple(y.shape) == tuple(d["y"].shape)
+        tol_y, tol_g = (1e-4, 2e-3) if mode == "fp32" else (2e-2, 1.5e-1)
+        G.check_entry(d["y"], y, tol_y, f"{style} output")
+        (y * d["w"].cuda()).sum().backward()
+        errs = []
+        for k, p in m.named_parameters():
+            g = d["grads"].get(k)
+            if g is None or p.grad is None:
+                continue
+            ref_norm = float(g.double().norm()) if torch.is_tensor(g) else g["norm"]
+            if ref_norm < 1e-6 or is_zero_class(k, True):   # biases in front of a batch-stat BatchNorm: exact gradient 0
+                continue
+            got = p.grad.detach().cpu()
+            if torch.is_tensor(g):
+                errs.append((float((got.double() - g.double()).norm() / g.double().norm()), k))
+            else:
+                flat = got.reshape(-1)
+                errs.append((float((flat[::g["stride"]].double() - g["sample"].double()).norm() / g["sample"].double().norm()), k))
+        errs.sort()
+        assert len(errs) > 80
+        print(f"{style} {mode}: output ok, {len(errs)} gradient tensors, median {errs[len(errs) // 2][0]:.3e}, worst {errs[-1][0]:.3e} ({errs[-1][1]})")
+        assert errs[len(errs) // 2][0] <= (2e-4 if mode == "fp32" else 3e-2), errs[len(errs) // 2]
+        assert errs[-1][0] <= tol_g, errs[-3:]
+    finally:
+        ab.set_precision("bf16")

@@ -158,3 +158,33 @@ def test_streams_against_reference_hand_dataset():
     assert torch.allclose(palm[0], case["palm"], atol=1e-6)
     assert torch.allclose(O.motion_stream(palm)[0], case["motion"], atol=1e-6)
     assert torch.allclose(O.bone_stream(palm)[0], case["bone"], atol=1e-6)
+
+
+def test_augment_against_reference_data_aug():
+    """The oracle's explicit-parameter augmentation vs Hand_Dataset.data_aug run on the reference class with its random draws
+    recorded (augment_22.pt, tests/golden/make_golden_aug.py): scale, shift, noise on four joints, time_interpolate."""
+    case = G.load("augment_22")
+    y = O.augment(case["x"], case["kind"], case["params"])
+    assert set(case["kind"].tolist()) == {0, 1, 2, 3}
+    assert torch.allclose(y, case["y"], atol=1e-6)
+    # an unknown kind leaves the sample untouched
+    assert torch.equal(O.augment(case["x"][:1], torch.tensor([7]), case["params"][:1]), case["x"][:1])
+
+
+@pytest.mark.parametrize("style", ["STR", "TTR"])
+def test_strttr_against_reference(style):
+    """The oracle's STR / TTR restatement (STR_TTR/STR.py:150-191, TTR.py:151-221, STR_TTR.py:62-84) vs the unmodified
+    reference run in train mode (tests/golden/make_golden_strttr.py): output and every parameter gradient."""
+    d = G.load(f"strttr_{style}_22")
+    N, T, V, cls = d["shape"]
+    st = O.random_state(O.strttr_spec(style, 3, cls, T, V), d["state_seed"])
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in st.items()}
+    x, _ = O.synthetic_batch(N, T, V, cls, d["batch_seed"])
+    y = O.strttr_forward(x, p, O.spatial_graph(V), style, True)
+    G.check_entry(d["y"], y, 1e-5, f"{style} output")
+    (y * d["w"]).sum().backward()
+    assert len(d["grads"]) > 100
+    for k, g in d["grads"].items():
+        ref_norm = float(g.double().norm()) if torch.is_tensor(g) else g["norm"]
+        if ref_norm > 1e-6:
+            G.check_entry(g, p[k].grad, 1e-4, f"{style} grad {k}")
