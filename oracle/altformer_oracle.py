@@ -265,10 +265,15 @@ def agcn_forward(x, p, prefix, A, training=False):
 
 
 def unit2d_forward(x, p, prefix, training=False, stride=1):
-    """Conv(k x 1, pad (k-1)//2) -> BN -> ReLU; dropout p=0.  model/net.py:47-57."""
+    """Conv(k x 1, pad (k-1)//2) -> BN -> ReLU; dropout p=0.  model/net.py:47-57.  A (1, k) weight is the dim=3 variant
+    (convolution along the joints, net.py:29-36)."""
     w = p[prefix + "conv.weight"]
-    k = w.shape[2]
-    y = F.conv2d(x, w, p.get(prefix + "conv.bias"), stride=(stride, 1), padding=((k - 1) // 2, 0))
+    if w.shape[2] == 1 and w.shape[3] > 1:
+        k = w.shape[3]
+        y = F.conv2d(x, w, p.get(prefix + "conv.bias"), stride=(1, stride), padding=(0, (k - 1) // 2))
+    else:
+        k = w.shape[2]
+        y = F.conv2d(x, w, p.get(prefix + "conv.bias"), stride=(stride, 1), padding=((k - 1) // 2, 0))
     return torch.relu(_bn(y, p, prefix + "bn.", training))
 
 

@@ -37,13 +37,35 @@ class Unit2D(nn.Module):
         return torch.empty(tok.shape, device=tok.device, dtype=torch.float32).bernoulli_(keep).div_(keep)  # RNG plumbing
 
     def out_dims(self, dims):
-        """(N, T, V) of the output tokens: stride (s, 1) shortens the frame axis (net.py:24-27)."""
+        """(N, T, V) of the output tokens: stride (s, 1) shortens the frame axis (net.py:24-27), (1, s) the joint axis (:29-36)."""
         N, T, V = dims
+        if self.dim == 3:
+            return N, T, AF.conv_out_frames(V, self.conv.kernel_size[1], self.stride)
         return N, AF.conv_out_frames(T, self.conv.kernel_size[0], self.stride), V
+
+    def _forward_tokens_dim3(self, tok, dims, res_post, want_perm):
+        """dim=3 (net.py:29-36): a 1 x k convolution along the JOINTS is the k x 1 convolution of the tensor with frames and
+        joints swapped, and BatchNorm statistics do not care about the order of positions -- so this variant (constructed
+        nowhere in the reference's models) runs the same kernels between two token re-orderings instead of owning a second
+        tap geometry."""
+        if res_post is not None or want_perm:
+            raise RuntimeError("altformer_b200.Unit2D(dim=3): fused residual / permuted output are only built for dim=2")
+        N, T, V = dims
+        C = tok.shape[1]
+        swapped = tok.view(N, T, V, C).permute(0, 2, 1, 3).reshape(N * V * T, C)            # (n, v, t) order
+        if self.p_drop > 0 and self.training:
+            mask = self.dropout_mask(tok)
+            swapped = AF.dropout(swapped, mask.view(N, T, V, C).permute(0, 2, 1, 3).reshape(N * V * T, C).contiguous())
+        if self.training and self.bn.track_running_stats:
+            self.bn.num_batches_tracked += 1
+        y = AF.unit2d(swapped, (N, V, T), self.conv.weight.transpose(2, 3), self.conv.bias, self.bn.weight, self.bn.bias,
+                      self.bn.running_mean, self.bn.running_var, self.training, self.bn.momentum, self.bn.eps, None, False, self.stride)
+        Vo = self.out_dims(dims)[2]
+        return y.view(N, Vo, T, -1).permute(0, 2, 1, 3).reshape(N * T * Vo, -1)
 
     def forward_tokens(self, tok, dims, res_post=None, want_perm=False):
         if self.dim != 2:
-            raise RuntimeError("altformer_b200.Unit2D: dim=3 (convolution along the joints, unused by the AltFormer / ST-GCN stacks) is not built")
+            return self._forward_tokens_dim3(tok, dims, res_post, want_perm)
         if self.p_drop > 0 and self.training:
             tok = AF.dropout(tok, self.dropout_mask(tok))
         if self.training and self.bn.track_running_stats:

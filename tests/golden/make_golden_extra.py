@@ -6,6 +6,8 @@
                            performs (the parameter gets its own storage, `self.A` stays the 1e-6 constant).  Eval-mode logits
                            for a seeded state_dict; tests load the same state with 'module.'-prefixed keys
                            (SHREC/ST_TS/emsemble.py:99-104) into the CUDA model.
+  unit2d_dim3_*.pt         the reference's Unit2D(dim=3) (model/net.py:29-36), stride 1 and 2, train mode: y, dx, parameter gradients,
+                           running statistics.
   streams_22.pt            Hand_Dataset.motion / Hand_Dataset.bone (data_process/Hand_Dataset.py:183-217) and the palm-centre
                            normalisation (:61) on a seeded skeleton, called on the reference class itself.
 
@@ -46,6 +48,20 @@ def main():
     torch.save({"y": y.clone(), "state_seed": seed, "batch_seed": seed + 100, "shape": (N, T, V, cls)},
                os.path.join(OUT, "model_ST_22_refckpt.pt"))
     print("model_ST_22_refckpt: logits", tuple(y.shape), float(y.norm()))
+
+    # Unit2D(dim=3): 1 x k convolution along the joints (model/net.py:29-36), stride 1 and 2, train mode, dx + parameter grads
+    from tests.golden.make_golden import run_module
+    for name, stride, seed in (("unit2d_dim3_train", 1, 41), ("unit2d_dim3_s2_train", 2, 42)):
+        cin, cout, k, Nn, Tt, Vv = 64, 64, 3, 2, 6, 22
+        spec = O.unit2d_spec("", cin, cout, k)
+        spec["conv.weight"] = (cout, cin, 1, k)
+        st2 = O.random_state(spec, seed)
+        m2 = ref.Unit2D(cin, cout, kernel_size=k, stride=stride, dim=3)
+        gx = torch.Generator().manual_seed(seed + 100)
+        case = run_module(m2, st2, torch.randn(Nn, cin, Tt, Vv, generator=gx), True, True)
+        case.update({"seed": seed, "shape": (cin, cout, k, Nn, Tt, Vv, stride)})
+        torch.save(case, os.path.join(OUT, name + ".pt"))
+        print(name, tuple(case["y"].shape))
 
     hd = importlib.import_module("data_process.Hand_Dataset").Hand_Dataset
     g = torch.Generator().manual_seed(5)

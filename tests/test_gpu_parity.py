@@ -386,3 +386,50 @@ def test_strttr_against_reference_golden(style, mode):
         assert errs[-1][0] <= tol_g, errs[-3:]
     finally:
         ab.set_precision("bf16")
+
+
+@pytest.mark.parametrize("name", ["unit2d_dim3_train", "unit2d_dim3_s2_train"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_unit2d_dim3_against_reference_golden(name, mode):
+    """Unit2D(dim=3) (convolution along the joints, model/net.py:29-36), stride 1 and 2, train mode: output, input
+    gradient, parameter gradients, running statistics.  fp32 mode vs the reference class's golden (1e-4); bf16 mode vs the
+    oracle (pinned by the same golden) on the bf16-rounded input the module actually consumes, rel-L2 1e-2 / 2e-2 -- an
+    input that is not bf16-representable moves ReLU masks, which is the input's rounding, not the kernels'."""
+    import altformer_b200 as ab
+    from oracle import altformer_oracle as O
+    from tests import goldenlib as G
+    case = G.load(name)
+    cin, cout, k, N, T, V, stride = case["shape"]
+    spec = O.unit2d_spec("", cin, cout, k)
+    spec["conv.weight"] = (cout, cin, 1, k)
+    st = O.random_state(spec, case["seed"])
+    x0 = torch.randn(N, cin, T, V, generator=torch.Generator().manual_seed(case["seed"] + 100))
+    cot = torch.randn(case["y"].shape, generator=torch.Generator().manual_seed(7))
+    if mode == "bf16":
+        x0 = x0.bfloat16().float()
+        p = {kk: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in kk else v.clone()) for kk, v in st.items()}
+        xr = x0.clone().requires_grad_(True)
+        yr = O.unit2d_forward(xr, p, "", True, stride)
+        (yr * cot).sum().backward()
+        want = {"y": yr.detach(), "dx": xr.grad, "grad.conv.weight": p["conv.weight"].grad, "grad.bn.weight": p["bn.weight"].grad,
+                "grad.bn.bias": p["bn.bias"].grad, "buf.bn.running_mean": p["bn.running_mean"], "buf.bn.running_var": p["bn.running_var"]}
+    else:
+        want = case
+    ab.set_precision(mode)
+    try:
+        m = ab.Unit2D(cin, cout, kernel_size=k, stride=stride, dim=3)
+        m.load_state_dict(st, strict=True)
+        m = m.cuda().train()
+        x = x0.cuda().requires_grad_(True)
+        y = m(x)
+        (y.float() * cot.cuda()).sum().backward()
+        got = {"y": y.float(), "dx": x.grad, "grad.conv.weight": m.conv.weight.grad, "grad.bn.weight": m.bn.weight.grad,
+               "grad.bn.bias": m.bn.bias.grad, "buf.bn.running_mean": m.bn.running_mean, "buf.bn.running_var": m.bn.running_var}
+        for key, g in got.items():
+            if mode == "fp32":
+                G.check_entry(want[key], g, 1e-3 if key.startswith("buf.") else 1e-4, key)
+            else:
+                e = float((g.detach().cpu().double() - want[key].double()).norm() / want[key].double().norm())
+                assert e <= (1e-2 if key in ("y", "buf.bn.running_mean", "buf.bn.running_var") else 2e-2), (key, e)
+    finally:
+        ab.set_precision("bf16")

@@ -188,3 +188,16 @@ def test_strttr_against_reference(style):
         ref_norm = float(g.double().norm()) if torch.is_tensor(g) else g["norm"]
         if ref_norm > 1e-6:
             G.check_entry(g, p[k].grad, 1e-4, f"{style} grad {k}")
+
+
+@pytest.mark.parametrize("name", ["unit2d_dim3_train", "unit2d_dim3_s2_train"])
+def test_unit2d_dim3(name):
+    """Unit2D(dim=3): 1 x k convolution along the joints (model/net.py:29-36), stride 1 and 2, vs the reference class."""
+    case = G.load(name)
+    cin, cout, k, N, T, V, stride = case["shape"]
+    spec = O.unit2d_spec("", cin, cout, k)
+    spec["conv.weight"] = (cout, cin, 1, k)
+    st = O.random_state(spec, case["seed"])
+    x = torch.randn(N, cin, T, V, generator=torch.Generator().manual_seed(case["seed"] + 100))
+    y, gx, params = _run(lambda x, p: O.unit2d_forward(x, p, "", True, stride), st, x, True)
+    _compare(case, y, gx, params)
