@@ -10,6 +10,9 @@ kernels accumulate straight into the flat gradient buffer.  BatchNorm statistics
 is what DataParallel does.  The forward+backward of a fixed shape can be captured in a
 CUDA graph (`use_graph=True`) so the ~300 launches of a step cost one host call.
 """
+import contextlib
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -48,6 +51,23 @@ class FlatBuffers:
     def view(self, flat, name):
         off, n, shape = self.index[name]
         return flat[off:off + n].view(shape)
+
+
+_NVTX = os.environ.get("AFB_NVTX", "0") == "1"
+
+
+@contextlib.contextmanager
+def _nvtx(name):
+    """NVTX range around a phase of the step (tracing), enabled by AFB_NVTX=1 for an nsys / ncu --nvtx
+    timeline; a no-op otherwise (and inside CUDA-graph replay, where only the captured kernels run)."""
+    if not _NVTX:
+        yield
+        return
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 class GradReducer:
@@ -147,12 +167,18 @@ class DataParallelTrainer:
     # -- one training step -------------------------------------------------------------------
     def _fwd_bwd(self, x, labels):
         self.flat_g.zero_()                      # model.zero_grad() (train_sttran.py:187); memset plumbing
-        logits = self.model(x)
-        loss = AF.cross_entropy(logits, labels)
-        loss.backward()
+        with _nvtx("afb.forward"):
+            logits = self.model(x)
+            loss = AF.cross_entropy(logits, labels)
+        with _nvtx("afb.backward"):
+            loss.backward()
         return loss.detach(), logits.detach()
 
     def _optimize(self, shard_weight=1.0):
+        with _nvtx("afb.reduce+adamw"):
+            self._optimize_impl(shard_weight)
+
+    def _optimize_impl(self, shard_weight=1.0):
         if shard_weight != 1.0:
             ops.axpby(self.flat_g, shard_weight, self.flat_g, 0.0, out=self.flat_g)
         if self.flat_g_low is not None:      # reduced-precision exchange: cast, one all-reduce of half the bytes, cast back
