@@ -453,7 +453,7 @@ def grp_attention():
         try:
             for (B, L, H, dh) in ((5, 22, 8, 32), (1237, 22, 8, 32), (301, 32, 8, 32), (7, 9, 4, 32), (130, 46, 8, 32),
                                   (75, 64, 8, 32), (3, 50, 2, 32), (203, 32, 8, 64), (9, 13, 4, 64), (41, 46, 8, 64),
-                                  (66, 64, 4, 64), (5, 40, 3, 64)):
+                                  (66, 64, 4, 64), (5, 40, 3, 64), (1, 1, 2, 32), (2, 33, 6, 32), (1, 64, 2, 32), (1, 2, 2, 64)):
                 D = H * dh
                 qkv = g(B * L, 3 * D, seed=L + B, dtype=torch.bfloat16)
                 oref = _attn_ref(qkv.float(), B, L, H)
@@ -465,7 +465,7 @@ def grp_attention():
                            keep.repeat_interleave(L)[:, None] * oref, 1e-2)
             # backward: warp-level kernel vs tcgen05 kernel (dh 32) vs torch autograd
             for (B, L, H, dh) in ((5, 22, 8, 32), (1237, 22, 8, 32), (301, 32, 8, 32), (7, 9, 4, 32), (130, 46, 8, 32), (75, 64, 8, 32),
-                                  (3, 50, 2, 32)):
+                                  (3, 50, 2, 32), (1, 1, 2, 32), (2, 33, 6, 32), (1, 64, 2, 32)):
                 D = H * dh
                 qkv = g(B * L, 3 * D, seed=L + B, dtype=torch.bfloat16)
                 do = g(B * L, D, seed=5, dtype=torch.bfloat16)
