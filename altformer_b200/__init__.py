@@ -13,6 +13,7 @@ from .model.AltFormer.model_ST import ST, Mlp, Attention, Block  # noqa: E402,F4
 from .model.AltFormer.model_TS import TS  # noqa: E402,F401
 from .model.AltFormer.ST_GCN_AltFormer import ST_GCN_AltFormer  # noqa: E402,F401
 from .trainer import DataParallelTrainer  # noqa: E402,F401
+from .inference import GraphedInference  # noqa: E402,F401
 from . import streams  # noqa: E402,F401
 from .STR_TTR import STR, TTR, STR_TTR  # noqa: E402,F401
 

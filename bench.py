@@ -617,21 +617,32 @@ def run_infer(env, cfg, args):
     x_dev = x_pin.to(dev)
     host_out = torch.empty((B, cfg["cls"]), dtype=torch.float32).pin_memory()
 
+    use_graph = not args.no_graph
+    from altformer_b200 import ops
+    with torch.no_grad():
+        model(x_dev)                   # first call: derived-weight casts, lazy inits
+        ops.LAUNCHES[0] = 0
+        model(x_dev)
+    launches = ops.LAUNCHES[0]
+    graphed = ab.GraphedInference(model, x_dev) if use_graph else None   # the public fixed-shape serving call
+
     def fwd_resident():
-        with torch.no_grad():
-            model(x_dev)
+        if use_graph:
+            graphed(x_dev)
+        else:
+            with torch.no_grad():
+                model(x_dev)
 
     def fwd_e2e():
-        with torch.no_grad():
-            y = model(x_pin.to(dev, non_blocking=True))
-            host_out.copy_(y.float(), non_blocking=True)
+        if use_graph:
+            host_out.copy_(graphed(x_pin), non_blocking=True)
+        else:
+            with torch.no_grad():
+                y = model(x_pin.to(dev, non_blocking=True))
+                host_out.copy_(y.float(), non_blocking=True)
 
     for _ in range(max(args.warmup, 3)):
         fwd_resident()
-    from altformer_b200 import ops
-    ops.LAUNCHES[0] = 0
-    fwd_resident()
-    launches = ops.LAUNCHES[0]
     with ClockSampler(env.local) as clk:
         ms, med = timed(fwd_resident, args.steps, env.dist_on, dev)
     ms_e2e, _ = timed(fwd_e2e, args.steps, env.dist_on, dev)
@@ -641,13 +652,13 @@ def run_infer(env, cfg, args):
     tf = flops_per_sample_fwd(cfg["T"], cfg["V"], cfg["cls"], cfg["style"]) * B / (ms * 1e-3) / 1e12
     out = {"metric": cfg["metric"], "value": gb / (ms * 1e-3), "unit": "seq/s", "n_gpus": env.world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms, "ms_per_step_median": med, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-           "data": "synthetic", "config": {"workload": cfg["workload"], "per_gpu_batch": B, "global_batch": gb, "cuda_graph": False,
-                                           "l2": "batch 32 is launch-bound (no graph): the activations fit L2, nothing is flushed"},
+           "data": "synthetic", "config": {"workload": cfg["workload"], "per_gpu_batch": B, "global_batch": gb, "cuda_graph": use_graph,
+                                           "l2": "batch 32: the activations fit L2, nothing is flushed (a 12 MB working set cannot be made HBM-bound honestly)"},
            "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "seq/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": x_pin.numel() * 4,
                    "d2h_bytes_per_step": host_out.numel() * 4},
            "gpu_launches": launches, "clocks": clk.summary(),
            "roofline": {"bound": "tensor", "achieved": tf, "peak": env.pk["tf"], "unit": "TFLOP/s", "frac": tf / env.pk["tf"],
-                        "note": "forward FLOPs of the batch; at batch 32 the pass is bound by ~250 kernel launches, not by the roofline"}}
+                        "note": "forward FLOPs of the batch; at batch 32 the pass is bound by the latency of ~95 dependent small kernels, not by the roofline"}}
     if env.world == 1 and not args.no_cpu_baseline:
         c = cpu_leg(cfg)
         out["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -433,3 +433,25 @@ def test_unit2d_dim3_against_reference_golden(name, mode):
                 assert e <= (1e-2 if key in ("y", "buf.bn.running_mean", "buf.bn.running_var") else 2e-2), (key, e)
     finally:
         ab.set_precision("bf16")
+
+
+def test_graphed_inference_matches_eager_eval():
+    """ab.GraphedInference (CUDA-graph replay of the eval forward) returns the eager eval logits (to the 1-ulp run-to-run
+    jitter the eager forward itself has from its atomically-accumulated reductions), for device and pinned-host inputs, and
+    rejects another shape."""
+    import altformer_b200 as ab
+    from oracle import altformer_oracle as O
+    N, T, V, cls = 8, 16, 22, 14
+    torch.manual_seed(0)
+    m = ab.ST_GCN_AltFormer(3, cls, num_frame=T, num_joints=V, style="ST", graph="graph.SHRE", graph_args={"labeling_mode": "spatial"}).cuda().eval()
+    x1, _ = O.synthetic_batch(N, T, V, cls, 5)
+    x2, _ = O.synthetic_batch(N, T, V, cls, 6)
+    with torch.no_grad():
+        want1, want2 = m(x1.cuda()).clone(), m(x2.cuda()).clone()
+    g = ab.GraphedInference(m, x1.cuda())
+    assert torch.allclose(g(x1.cuda()).clone(), want1, atol=1e-6, rtol=0)
+    assert torch.allclose(g(x2.pin_memory()).clone(), want2, atol=1e-6, rtol=0)
+    assert torch.allclose(g(x1.cuda()), want1, atol=1e-6, rtol=0)
+    assert not torch.allclose(want1, want2, atol=1e-3)
+    with pytest.raises(RuntimeError):
+        g(x1[:4].cuda())
