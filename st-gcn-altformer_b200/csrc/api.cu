@@ -1,6 +1,7 @@
 // Error plumbing and device checks for the C ABI.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -21,6 +22,18 @@ int check_launch(const char* what) {
     return (int)e;
   }
   return 0;
+}
+// Ping-pong traversal order of the streaming kernels: every kernel of the step reads what its predecessor wrote, each tensor
+// (92-370 MB) is larger than the 126 MB L2, and all kernels used to walk their rows in ascending order -- so a consumer's first
+// rows had long been evicted while the LAST third its producer wrote (still in L2) was overwritten before the consumer got
+// there.  Alternating the direction launch by launch makes every consumer start where its producer stopped.
+// AFB_PINGPONG=0 keeps every kernel ascending (read per call).
+static int g_dir = 0;
+int next_stream_dir() {
+  const char* v = getenv("AFB_PINGPONG");
+  if (v != nullptr && v[0] == '0') return 0;
+  g_dir ^= 1;
+  return g_dir;
 }
 }  // namespace afb
 

@@ -176,6 +176,7 @@ struct TcArgs {
   float scale_log2;       // softmax scale * log2(e)
   float scale;            // softmax scale (backward: folded into dS)
   const float* out_scale; // optional [B]
+  int rev;                // tiles visited in descending order (ping-pong traversal, api.cu:next_stream_dir)
 };
 
 // PTMEM: the probabilities go back to TENSOR memory (tcgen05.st) and the P V product reads its A operand from there;
@@ -255,7 +256,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) {
+      for (int ti = blockIdx.x; ti < a.tiles; ti += gridDim.x) {
+        const int t = a.rev ? a.tiles - 1 - ti : ti;
         for (int bx = 0; bx < nbox; ++bx) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), kStageBytes);
@@ -353,7 +355,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // (tile, head) of the group's next O phase, advanced incrementally (items grp, grp + 2, ... in order)
     int o_tile = blockIdx.x, o_head = grp, o_cnt = 0;
     auto o_phase = [&](int j, float inv) {
-      const int tile = o_tile, h = o_head, ob = C::kOutBufs == 2 ? (o_cnt & 1) : 0;
+      const int tile = a.rev ? a.tiles - 1 - o_tile : o_tile, h = o_head, ob = C::kOutBufs == 2 ? (o_cnt & 1) : 0;
       ++o_cnt;
       o_head += 2;
       if (o_head >= a.heads) { o_head -= a.heads; o_tile += gridDim.x; }
@@ -475,6 +477,7 @@ int launch(const void* qkv, void* o, int64_t B, int L, int heads, float scale, c
   a.scale_log2 = scale * 1.4426950408889634f;
   a.scale = scale;
   a.out_scale = out_scale;
+  a.rev = next_stream_dir();
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -572,7 +575,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) {
+      for (int ti = blockIdx.x; ti < a.tiles; ti += gridDim.x) {
+        const int t = a.rev ? a.tiles - 1 - ti : ti;
         for (int bx = 0; bx < nbox; ++bx) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), kBwdStageBytes);
@@ -673,7 +677,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     int o_tile = blockIdx.x, o_head = grp;
     // epilogue of item j: dQ | dK | dV rows -> bf16 -> staging -> three TMA stores into dqkv
     auto o_phase = [&](int j) {
-      const int tile = o_tile, h = o_head;
+      const int tile = a.rev ? a.tiles - 1 - o_tile : o_tile, h = o_head;
       o_head += 2;
       if (o_head >= a.heads) { o_head -= a.heads; o_tile += gridDim.x; }
       mbar_wait(ofull, (uint32_t)((j >> 1) & 1));
@@ -800,6 +804,7 @@ int launch_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, in
   a.scale_log2 = scale * 1.4426950408889634f;
   a.scale = scale;
   a.out_scale = nullptr;
+  a.rev = next_stream_dir();
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

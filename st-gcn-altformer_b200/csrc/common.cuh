@@ -13,6 +13,7 @@ using bf16 = __nv_bfloat16;
 // ---- host-side error plumbing ------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);  // returns 0 or a cudaError code, records message
+int next_stream_dir();                // 0 = ascending, 1 = descending row order for this launch (api.cu)
 
 #define AFB_REQUIRE(cond, ...)          \
   do {                                  \

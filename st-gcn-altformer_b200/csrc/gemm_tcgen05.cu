@@ -243,6 +243,7 @@ template <int BN, bool STAT> struct TnCfg {
 struct TnArgs {
   int m_tiles_per_batch, n_tiles, total_m_tiles, k_blocks;
   int stages;   // ring depth actually used (stationary mode: as many A stages as fit beside the weight panel)
+  int rev;      // visit the m-tiles in descending order (ping-pong traversal, api.cu:next_stream_dir)
   int rows_per_batch, batches, N;
   int kb_per_tap, tap_row_stride, tap_pad;
   int out_dtype, act, has_c2;
@@ -265,31 +266,35 @@ struct TnArgs {
 // the CTA keeps n-block (blockIdx.x % n_tiles) and walks m-tiles with stride grid / n_tiles.
 template <bool STAT>
 struct TileWalk {
-  int n_blk, mt, mt_stride, mt_end, n_tiles, lin, lin_stride, lin_end;
+  // k = position of the m-tile in visiting order, mt = the m-tile itself (descending when p.rev: see next_stream_dir())
+  int n_blk, mt, k, k_stride, k_end, n_tiles, lin, lin_stride, lin_end, last;
   __device__ __forceinline__ TileWalk(const TnArgs& p) {
     n_tiles = p.n_tiles;
+    last = p.rev ? p.total_m_tiles - 1 : -1;
     if (STAT) {
       n_blk = blockIdx.x % p.n_tiles;
-      mt = blockIdx.x / p.n_tiles;
-      mt_stride = gridDim.x / p.n_tiles;
-      mt_end = p.total_m_tiles;
+      k = blockIdx.x / p.n_tiles;
+      k_stride = gridDim.x / p.n_tiles;
+      k_end = p.total_m_tiles;
     } else {
       lin = blockIdx.x;
       lin_stride = gridDim.x;
       lin_end = p.total_m_tiles * p.n_tiles;
       n_blk = lin % n_tiles;
-      mt = lin / n_tiles;
+      k = lin / n_tiles;
     }
+    mt = last >= 0 ? last - k : k;
   }
-  __device__ __forceinline__ bool valid() const { return STAT ? mt < mt_end : lin < lin_end; }
+  __device__ __forceinline__ bool valid() const { return STAT ? k < k_end : lin < lin_end; }
   __device__ __forceinline__ void next() {
     if (STAT) {
-      mt += mt_stride;
+      k += k_stride;
     } else {
       lin += lin_stride;
       n_blk = lin % n_tiles;
-      mt = lin / n_tiles;
+      k = lin / n_tiles;
     }
+    mt = last >= 0 ? last - k : k;
   }
 };
 
@@ -880,6 +885,7 @@ struct DwArgs {
   const float* dbias_rs;   // optional per-row factor of the bias gradient (smem column-sum path only)
   int rs_div;
   long long rows_per_batch;
+  int rev;   // row blocks visited in descending order (ping-pong traversal)
 };
 
 template <int BN1, int BN2, int TAPS>
@@ -944,7 +950,8 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int rb = rb_begin; rb < rb_end; ++rb) {
+        for (int rb_i = rb_begin; rb_i < rb_end; ++rb_i) {
+          const int rb = p.rev ? p.total_row_blocks - 1 - rb_i : rb_i;
           const int batch = rb / p.row_blocks_per_batch;
           const int r0 = (rb % p.row_blocks_per_batch) * 64;
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -1004,7 +1011,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
         for (int i = 0; i < n_rb; ++i) {
           float sc0 = 1.f, sc1 = 1.f;   // factors of tile rows `lane` and `lane + 32` (rows past the batch are zero-filled)
           if (p.dbias_rs != nullptr) {
-            const int rb = rb_begin + i;
+            const int rb = p.rev ? p.total_row_blocks - 1 - (rb_begin + i) : rb_begin + i;
             const long long bat = rb / p.row_blocks_per_batch;
             const long long r0 = (long long)(rb % p.row_blocks_per_batch) * 64 + lane;
             const long long ra = bat * p.rows_per_batch + min(r0, p.rows_per_batch - 1);
@@ -1260,6 +1267,7 @@ extern "C" int afb_gemm_tn(const afb_gemm_tn_t* p, afb_stream s) {
   a.kb_per_tap = kb_per_tap;
   a.k_blocks = k_blocks;
   a.stages = 0;
+  a.rev = next_stream_dir();
   if (stat) {
     a.stages = BN == 256 ? TnCfg<256, true>::stat_stages(k_blocks) : (BN == 128 ? TnCfg<128, true>::stat_stages(k_blocks) : TnCfg<64, true>::stat_stages(k_blocks));
     AFB_REQUIRE(a.stages >= 2, "gemm_tn: internal: stationary panel leaves no room for the A ring");
@@ -1350,6 +1358,7 @@ extern "C" int afb_gemm_dw(const afb_gemm_dw_t* p, afb_stream s) {
   a.dbias_rs = p->dbias != nullptr ? p->dbias_row_scale : nullptr;
   a.rs_div = p->row_scale_div > 0 ? p->row_scale_div : 1;
   a.rows_per_batch = p->rows_per_batch;
+  a.rev = next_stream_dir();
   AFB_REQUIRE(a.dbias_rs == nullptr || BN1 == 256, "gemm_dw: dbias_row_scale needs N1 %% 256 == 0 (N1=%d)", p->N1);
   CUtensorMap tmG, tmX;
   int rc = make_map(&tmG, p->G, (uint64_t)p->N1, (uint64_t)p->rows_per_batch, (uint64_t)p->batches, (uint64_t)p->ldg,

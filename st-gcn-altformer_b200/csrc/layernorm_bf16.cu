@@ -35,7 +35,7 @@ __device__ __forceinline__ void load8f(const float* p, float (&o)[8]) {
 template <int NC>
 __global__ void __launch_bounds__(kBlock) ln_fwd_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, bf16* __restrict__ y, float* __restrict__ mean,
-                                                             float* __restrict__ rstd, int64_t rows, float eps) {
+                                                             float* __restrict__ rstd, int64_t rows, float eps, int rev) {
   constexpr int D = NC * 256;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -47,9 +47,11 @@ __global__ void __launch_bounds__(kBlock) ln_fwd_bf16_kernel(const bf16* __restr
     load8f(beta + c * 256 + lane * 8, b[c]);
   }
   // two rows per iteration: both rows' loads are issued before either reduction starts (twice the bytes in flight)
-  for (int64_t row = warp0; row < rows; row += 2 * nwarps) {
-    const int64_t row2 = row + nwarps;
-    const bool has2 = row2 < rows;
+  // rev: rows visited in descending order (ping-pong traversal, api.cu:next_stream_dir)
+  for (int64_t ri = warp0; ri < rows; ri += 2 * nwarps) {
+    const bool has2 = ri + nwarps < rows;
+    const int64_t row = rev ? rows - 1 - ri : ri;
+    const int64_t row2 = has2 ? (rev ? rows - 1 - (ri + nwarps) : ri + nwarps) : row;
     uint4 ra[NC], rb[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(kBlock) ln_bwd_bf16_kernel(const bf16* __restr
                                                              const float* __restrict__ gamma, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, const bf16* __restrict__ dres,
                                                              bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                             int64_t rows) {
+                                                             int64_t rows, int rev) {
   constexpr int D = NC * 256;
   __shared__ float red[2][D];
   const int lane = threadIdx.x & 31;
@@ -116,7 +118,8 @@ __global__ void __launch_bounds__(kBlock) ln_bwd_bf16_kernel(const bf16* __restr
     for (int i = 0; i < 8; ++i) { ag[c][i] = 0.f; ab[c][i] = 0.f; }
   }
   __syncthreads();
-  for (int64_t row = warp0; row < rows; row += nwarps) {
+  for (int64_t ri = warp0; ri < rows; ri += nwarps) {
+    const int64_t row = rev ? rows - 1 - ri : ri;
     uint4 rdy[NC], rx[NC], rres[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {   // all loads of the row first (memory-level parallelism)
@@ -185,22 +188,24 @@ inline int grid_rows(int64_t rows, int max_blocks, int rows_per_warp = 1) {
 int layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows, int D,
                        float eps, cudaStream_t st) {
   const int grid = grid_rows(rows, 148 * 8, 2);
+  const int rev = next_stream_dir();
   if (D == 256)
-    ln_fwd_bf16_kernel<1><<<grid, kBlock, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, rows, eps);
+    ln_fwd_bf16_kernel<1><<<grid, kBlock, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, rows, eps, rev);
   else
-    ln_fwd_bf16_kernel<2><<<grid, kBlock, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, rows, eps);
+    ln_fwd_bf16_kernel<2><<<grid, kBlock, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, rows, eps, rev);
   return check_launch("layernorm_fwd_bf16");
 }
 
 int layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
                        void* dx, float* dgamma, float* dbeta, int64_t rows, int D, cudaStream_t st) {
   const int grid = grid_rows(rows, 148 * 6, 8);   // every block ends with 2*D global atomics
+  const int rev = next_stream_dir();
   if (D == 256)
     ln_bwd_bf16_kernel<1><<<grid, kBlock, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (const bf16*)dres, (bf16*)dx, dgamma,
-                                                    dbeta, rows);
+                                                    dbeta, rows, rev);
   else
     ln_bwd_bf16_kernel<2><<<grid, kBlock, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (const bf16*)dres, (bf16*)dx, dgamma,
-                                                    dbeta, rows);
+                                                    dbeta, rows, rev);
   return check_launch("layernorm_bwd_bf16");
 }
 

@@ -13,7 +13,7 @@ Tolerances, as max|d|/max|ref| and relative L2:
                       TCN_GCN_unit is compared with the oracle quantising the gcn1 -> tcn1 activation to bf16 exactly
                       as the module boundary stores it (O.boundary_bf16).  Max-abs is informational for bf16 gradients.
   whole model:        fp32: logits 2e-4, gradients median 2e-4 / worst tensor 3e-2 (a max-pool arg-max near-tie
-                      re-routes single gradient entries).  bf16: logits and every gradient tensor <= max(1e-2, 1.5 x
+                      re-routes single gradient entries).  bf16 (rel-L2): logits and every gradient tensor <= max(1e-2, 1.5 x
                       the error of the reference math under torch.autocast(bf16) on the same case), from
                       tests/golden/autocast_floor.json (tools/autocast_floor.py)
   analytically-zero gradients (conv_a bias; conv biases feeding a batch-stat BN): absolute, relative to the
@@ -436,7 +436,12 @@ def grp_model():
             # pre-LN blocks amplify operand rounding exactly as they do for the reference under autocast (floor file)
             floor = autocast_floor(f"{style}_N{N}_T{T}_V{V}") if mode == "bf16" else None
             ltol = 2e-4 if mode == "fp32" else (max(1e-2, 1.5 * floor["logits"]) if floor else 2e-2)
-            report(tag + " logits", y.float(), yr, ltol)
+            if mode == "fp32":
+                report(tag + " logits", y.float(), yr, ltol)
+            else:
+                # rel-L2 decides (north_star's metric); the max-norm of 4 x 28 logits moves by +-30 % from run to run with the
+                # order of the atomically accumulated BatchNorm / weight-gradient sums (seen: 0.9e-2 ... 1.3e-2 for rel-L2 0.94-0.96e-2)
+                report_l2(tag + " logits", y.float(), yr, ltol)
             if training:
                 (y.float() * cot.to(DEV)).sum().backward()
                 if mode == "fp32":
