@@ -337,6 +337,10 @@ def step_kernel_rooflines(M, dev, pk, iters=10):
     """The kernels that carry the step's time (spatial stage, D = 256, M = per-GPU tokens), each timed live with CUDA
     events over `iters` back-to-back launches on tensors far larger than L2: algorithmic bytes / time vs the HBM peak."""
     from altformer_b200 import ops
+    # the same launch repeated on the same tensors must not profit from the ping-pong traversal order (each repetition would
+    # start on the lines the previous one left in L2, which no kernel of the real step does for its whole input)
+    saved_pp = os.environ.get("AFB_PINGPONG")
+    os.environ["AFB_PINGPONG"] = "0"
     mk = lambda r, c: (0.5 * torch.randn(r, c, device=dev)).to(torch.bfloat16)  # noqa: E731
     x256, x512, g768, res = mk(M, 256), mk(M, 512), mk(M, 768), mk(M, 256)
     wqkv, wfc2 = mk(768, 256), mk(256, 512)
@@ -366,6 +370,10 @@ def step_kernel_rooflines(M, dev, pk, iters=10):
         us = 1e3 * e0.elapsed_time(e1) / iters
         gbs = nbytes / us / 1e3
         out.append({"kernel": name, "us": round(us, 1), "achieved": round(gbs, 1), "unit": "GB/s", "frac": round(gbs / pk["hbm"], 3)})
+    if saved_pp is None:
+        os.environ.pop("AFB_PINGPONG", None)
+    else:
+        os.environ["AFB_PINGPONG"] = saved_pp
     return out
 
 
