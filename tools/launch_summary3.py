@@ -34,7 +34,7 @@ def main(path):
     T = sum(a[0] for a in agg.values())
     MB = sum(a[1] + a[2] for a in agg.values())
     print(f"# last full step: {len(step)} launches, {T / 1e3:.2f} ms (ncu-serialised, cold cache), DRAM traffic {MB / 1e3:.2f} GB "
-          f"(= {MB / T / 1e3 * 1e3:.0f} GB/s averaged over the kernel time)")
+          f"(= {MB / T * 1e3:.0f} GB/s averaged over the kernel time; ncu runs every kernel alone with cold caches, so part of each output is still in L2 when the kernel ends: written MB are under-counted)")
     print(f"{'total_us':>10} {'share':>6} {'n':>4} {'avg_us':>8} {'rd_MB':>8} {'wr_MB':>8} {'GB/s':>7}  kernel   (MB per launch)")
     for n, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         print(f"{a[0]:10.1f} {100 * a[0] / T:5.1f}% {a[3]:4d} {a[0] / a[3]:8.1f} {a[1] / a[3]:8.1f} {a[2] / a[3]:8.1f} {(a[1] + a[2]) / a[0] * 1e3:7.0f}  {n}")
