@@ -104,6 +104,10 @@ bench("fc2   tn 256x512 +bias+residual", lambda: ops.gemm_tn(x512, wfc2, 256, bi
 bench("dX    mn 768->256", lambda: ops.gemm_tn(g768, wqkv, 256, b_mn_major=True), 2 * M * 768 * 256, M * (768 + 256) * 2)
 bench("dpre  mn 256->512 gelu_bwd", lambda: ops.gemm_tn(x256, wfc2, 512, b_mn_major=True, act=ops.ACT_GELU_BWD, aux=x512),
       2 * M * 256 * 512, M * (256 + 1024) * 2)
+bench("dx1   mn 512->256 (fc1 dX)", lambda: ops.gemm_tn(g512, wfc1, 256, b_mn_major=True), 2 * M * 512 * 256, M * (512 + 256) * 2)
+bench("dao   mn 256->256 (proj dX)", lambda: ops.gemm_tn(x256, wproj, 256, b_mn_major=True), 2 * M * 256 * 256, M * (256 + 256) * 2)
+x128e, wemb = mk(M, 128), mk(256, 128, s=0.05)
+bench("embed tn 256x128 +bias", lambda: ops.gemm_tn(x128e, wemb, 256, bias=b256), 2 * M * 256 * 128, M * (128 + 256) * 2)
 bench("dW    768x256", lambda: ops.gemm_dw(g768, x256, dW), 2 * M * 768 * 256, M * 1024 * 2)
 db768, db512, db256 = torch.zeros(768, device=dev), torch.zeros(512, device=dev), torch.zeros(256, device=dev)
 dW2, dW3, dW4 = torch.zeros(256, 256, device=dev), torch.zeros(512, 256, device=dev), torch.zeros(256, 512, device=dev)
