@@ -28,6 +28,15 @@ int check_launch(const char* what) {
 // rows had long been evicted while the LAST third its producer wrote (still in L2) was overwritten before the consumer got
 // there.  Alternating the direction launch by launch makes every consumer start where its producer stopped.
 // AFB_PINGPONG=0 keeps every kernel ascending (read per call).
+// AFB_PDL: 0 = never, 1 = every supported launch, unset = the short launches only (read per call)
+bool pdl_enabled() {
+  const char* v = getenv("AFB_PDL");
+  return v == nullptr || v[0] != '0';
+}
+bool pdl_force_all() {
+  const char* v = getenv("AFB_PDL");
+  return v != nullptr && v[0] == '1';
+}
 static int g_dir = 0;
 int next_stream_dir() {
   const char* v = getenv("AFB_PINGPONG");

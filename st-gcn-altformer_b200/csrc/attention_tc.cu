@@ -224,6 +224,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
   const int nbox = a.heads / HB;
   int my_tiles = 0;
   for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) ++my_tiles;
@@ -250,6 +251,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  pdl_wait();   // programmatic dependent launch (common.cuh): global memory only from here on
 
   if (warp == 0) {
     // ------------------------------------------ TMA producer ---------------------------------------------------
@@ -482,7 +484,12 @@ int launch(const void* qkv, void* o, int64_t B, int L, int heads, float scale, c
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.tiles < sms ? a.tiles : sms;
-  kern<<<grid, kThreads, C::kSmem, st>>>(tmQ, tmO, a);
+  cudaError_t le = launch_pdl(pdl_force_all() || a.tiles <= 4 * sms, kern, dim3(grid), dim3(kThreads), (size_t)C::kSmem, st, tmQ, tmO, a);
+  if (le != cudaSuccess) {
+    set_error("attention_fwd_tc: launch failed: %s", cudaGetErrorString(le));
+    (void)cudaGetLastError();
+    return (int)le;
+  }
   return check_launch("attention_fwd_tc");
 }
 
@@ -542,6 +549,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
   const int nbox = a.heads / HB;
   int my_tiles = 0;
   for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) ++my_tiles;
@@ -569,6 +577,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  pdl_wait();   // programmatic dependent launch (common.cuh): global memory only from here on
   // tensor memory: S 0..127 | dP 128..255 | OUT[b] 256 + 96 b: dQ, dK, dV (32 columns each) | dS (bf16 pairs) 448..511
 
   if (warp == 0) {
@@ -809,7 +818,12 @@ int launch_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, in
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.tiles < sms ? a.tiles : sms;
-  kern<<<grid, kThreads, C::kSmem, st>>>(tmQ, tmDO, tmDQ, a);
+  cudaError_t le = launch_pdl(pdl_force_all() || a.tiles <= 4 * sms, kern, dim3(grid), dim3(kThreads), (size_t)C::kSmem, st, tmQ, tmDO, tmDQ, a);
+  if (le != cudaSuccess) {
+    set_error("attention_bwd_tc: launch failed: %s", cudaGetErrorString(le));
+    (void)cudaGetLastError();
+    return (int)le;
+  }
   return check_launch("attention_bwd_tc");
 }
 

@@ -26,6 +26,33 @@ int next_stream_dir();                // 0 = ascending, 1 = descending row order
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// In the small-batch regimes (batch 32 inference, one 256-sequence batch split over 8 GPUs) the step is ~260 launches of
+// 5-15 us each, most of them one-CTA-per-SM kernels with a 2-4 us prologue (barrier init, TMEM allocation, descriptor
+// prefetch).  Launched with the programmatic-stream-serialization attribute, a kernel's CTAs become resident as soon as the
+// previous kernel's CTAs leave their SMs, run that prologue, and block in pdl_wait() until the previous grid has completed
+// and flushed; EVERY thread calls pdl_wait() before its first access to global memory.  pdl_launch_dependents() (first
+// instruction of a kernel) lets the next launch do the same to us.  Both are no-ops in a normally launched grid.
+// AFB_PDL=0 launches everything the ordinary way; `small` = the launch is short enough for its prologue to matter.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+bool pdl_force_all();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool small, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (small && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- typed global load/store (fp32 math everywhere) ---------------------------------------
 template <typename T> __device__ __forceinline__ float ldf(const T* p);
 template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }

@@ -554,6 +554,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -575,6 +576,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // everything above touched only this CTA's shared / tensor memory; global memory from here on
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------------------
@@ -910,6 +912,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   // work decomposition: blockIdx.x = (tile, split)
   const int split = blockIdx.x % p.splits;
@@ -944,6 +947,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // global memory (operands, the dW / dbias accumulators) only from here on
 
   if (n_rb > 0) {
     if (warp == 0) {
@@ -1174,7 +1178,13 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     const int tiles = a.total_m_tiles * a.n_tiles;
     grid = tiles < num_sms() ? tiles : num_sms();
   }
-  gemm_tn_kernel<BN, B_MN, STAT><<<grid, kTnThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmC, tmC2, a);
+  const bool small = pdl_force_all() || a.total_m_tiles * a.n_tiles <= 4 * num_sms();
+  cudaError_t le = launch_pdl(small, gemm_tn_kernel<BN, B_MN, STAT>, dim3(grid), dim3(kTnThreads), (size_t)Cfg::kSmemBytes, st, tmA, tmB, tmC, tmC2, a);
+  if (le != cudaSuccess) {
+    set_error("gemm_tn: launch failed: %s", cudaGetErrorString(le));
+    (void)cudaGetLastError();
+    return (int)le;
+  }
   return check_launch("gemm_tn");
 }
 
@@ -1197,7 +1207,13 @@ int launch_dw(const CUtensorMap& tmG, const CUtensorMap& tmX, const DwArgs& a, c
     configured = true;
   }
   const int grid = a.n1_tiles * a.n2_tiles * a.splits;
-  gemm_dw_kernel<BN1, BN2, TAPS><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmG, tmX, a);
+  const bool small = pdl_force_all() || a.total_row_blocks <= 16 * num_sms();
+  cudaError_t le = launch_pdl(small, gemm_dw_kernel<BN1, BN2, TAPS>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, tmG, tmX, a);
+  if (le != cudaSuccess) {
+    set_error("gemm_dw: launch failed: %s", cudaGetErrorString(le));
+    (void)cudaGetLastError();
+    return (int)le;
+  }
   return check_launch("gemm_dw");
 }
 

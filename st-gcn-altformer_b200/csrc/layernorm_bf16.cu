@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(kBlock) ln_fwd_bf16_kernel(const bf16* __restr
                                                              const float* __restrict__ beta, bf16* __restrict__ y, float* __restrict__ mean,
                                                              float* __restrict__ rstd, int64_t rows, float eps, int rev) {
   constexpr int D = NC * 256;
+  pdl_launch_dependents();
+  pdl_wait();   // programmatic dependent launch (common.cuh): hides the launch latency, there is no prologue to overlap
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -106,6 +108,8 @@ __global__ void __launch_bounds__(kBlock) ln_bwd_bf16_kernel(const bf16* __restr
                                                              int64_t rows, int rev) {
   constexpr int D = NC * 256;
   __shared__ float red[2][D];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -189,10 +193,14 @@ int layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, voi
                        float eps, cudaStream_t st) {
   const int grid = grid_rows(rows, 148 * 8, 2);
   const int rev = next_stream_dir();
-  if (D == 256)
-    ln_fwd_bf16_kernel<1><<<grid, kBlock, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, rows, eps, rev);
-  else
-    ln_fwd_bf16_kernel<2><<<grid, kBlock, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, rows, eps, rev);
+  const bool small = pdl_force_all() || rows <= 65536;
+  cudaError_t le = D == 256 ? launch_pdl(small, ln_fwd_bf16_kernel<1>, dim3(grid), dim3(kBlock), 0, st, (const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, rows, eps, rev)
+                            : launch_pdl(small, ln_fwd_bf16_kernel<2>, dim3(grid), dim3(kBlock), 0, st, (const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, rows, eps, rev);
+  if (le != cudaSuccess) {
+    set_error("layernorm_fwd_bf16: launch failed: %s", cudaGetErrorString(le));
+    (void)cudaGetLastError();
+    return (int)le;
+  }
   return check_launch("layernorm_fwd_bf16");
 }
 
@@ -200,12 +208,16 @@ int layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, const 
                        void* dx, float* dgamma, float* dbeta, int64_t rows, int D, cudaStream_t st) {
   const int grid = grid_rows(rows, 148 * 6, 8);   // every block ends with 2*D global atomics
   const int rev = next_stream_dir();
-  if (D == 256)
-    ln_bwd_bf16_kernel<1><<<grid, kBlock, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (const bf16*)dres, (bf16*)dx, dgamma,
-                                                    dbeta, rows, rev);
-  else
-    ln_bwd_bf16_kernel<2><<<grid, kBlock, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (const bf16*)dres, (bf16*)dx, dgamma,
-                                                    dbeta, rows, rev);
+  const bool small = pdl_force_all() || rows <= 65536;
+  cudaError_t le = D == 256 ? launch_pdl(small, ln_bwd_bf16_kernel<1>, dim3(grid), dim3(kBlock), 0, st, (const bf16*)dy, (const bf16*)x, gamma, mean, rstd,
+                                         (const bf16*)dres, (bf16*)dx, dgamma, dbeta, rows, rev)
+                            : launch_pdl(small, ln_bwd_bf16_kernel<2>, dim3(grid), dim3(kBlock), 0, st, (const bf16*)dy, (const bf16*)x, gamma, mean, rstd,
+                                         (const bf16*)dres, (bf16*)dx, dgamma, dbeta, rows, rev);
+  if (le != cudaSuccess) {
+    set_error("layernorm_bwd_bf16: launch failed: %s", cudaGetErrorString(le));
+    (void)cudaGetLastError();
+    return (int)le;
+  }
   return check_launch("layernorm_bwd_bf16");
 }
 
