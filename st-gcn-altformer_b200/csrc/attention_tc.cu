@@ -1,5 +1,5 @@
-// Short-sequence multi-head attention forward on the Blackwell paths: TMA loads, tcgen05.mma with the scores and the
-// output in TMEM, softmax out of tcgen05.ld, TMA stores.  (reference: model/AltFormer/model_ST.py:49-67, q @ k^T -> softmax
+// Short-sequence multi-head attention, forward (below) and backward (second half of the file), on the Blackwell paths: TMA
+// loads, tcgen05.mma with the scores and the outputs in TMEM, softmax out of tcgen05.ld, TMA stores.  (reference: model/AltFormer/model_ST.py:49-67, q @ k^T -> softmax
 // -> @ v per (sequence, head); L = 22 joints / 32 frames on SHREC, 46 / 64 on LMDHG.)
 //
 // One problem is far smaller than an MMA (22 x 22 scores per head), so G = 128 / LP sequences are PACKED into one
@@ -13,11 +13,14 @@
 //   * tile row r = TMEM lane r, and the keys of ITS sequence are the LP consecutive TMEM columns (r / LP) * LP ..: each
 //     softmax warp owns one lane quarter, so its 32 rows belong to one sequence and ONE warp-uniform tcgen05.ld hands
 //     every thread exactly its own row of scores -- the softmax is thread-local (no shuffles, no shared memory);
-//   * P goes back to shared memory as the block-diagonal A operand [128 x 128] (bf16, K-major, 128B swizzle; the
-//     off-diagonal blocks are zeroed once per CTA and never written), O = P V is a second MMA chain (N = dh, K = 128,
-//     V read in place from its TMA box as an MN-major B operand), the finished 128 x dh tile is read back with
-//     tcgen05.ld, scaled by 1 / rowsum (and the optional DropPath factor), staged and written with a TMA store whose
-//     box clips the padded rows.
+//   * P goes back to TENSOR memory (tcgen05.st, bf16 pairs; PTMEM = true, the default) as the block-diagonal A operand
+//     [128 x 128] whose off-diagonal blocks are zeroed once per CTA and never written -- or, PTMEM = false, to shared memory
+//     (K-major, 128B swizzle); O = P V is a second MMA chain (N = dh, K = 128, A from TMEM, V read in place from its TMA
+//     box as an MN-major B operand whose 32-column slice starts mid-swizzle-span at dh 32), the finished 128 x dh tile is
+//     read back with tcgen05.ld, scaled by 1 / rowsum (and the optional DropPath factor), staged and written with a TMA
+//     store whose box clips the padded rows;
+//   * the sequence length is a template constant (LC) for the dataset lengths 22 / 32 / 46 / 64: masked key columns then
+//     cost nothing (the compare + select per column was a sixth of the instructions); other lengths run the LC = 0 variant.
 // Warp roles: 0 = TMA producer, 1 = S issuer (+ TMEM owner), 10 = P V issuer, 2..5 and 6..9 = two softmax / epilogue groups (thread = tile
 // row; group b owns the items i = b mod 2 and the S / P / O buffers b), so two heads are in the softmax at any time while
 // the tensor pipe works on the products either side of them.
