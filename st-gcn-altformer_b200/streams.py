@@ -42,23 +42,30 @@ def augment(x, kind, params):
     return ops.augment(x.contiguous(), kind, params)
 
 
-def random_augment(x, generator=None):
-    """The reference's random policy drawn on the device: one of the four transforms per sample with equal probability
-    (`randint(0, 3)`, :146-147), factor ~ U(0.8, 1.2) (:87-90), offsets ~ U(-0.1, 0.1) (:99-101, :110-118), four distinct
-    joints (`shuffle(all_joint)[0:4]`, :113-115), r ~ U(0, 1) (:129).  Returns (augmented batch, kind, params)."""
-    N, _, V, _ = x.shape
-    dev = x.device
-    u = torch.rand((N, 16), device=dev, generator=generator)
-    kind = torch.randint(0, 4, (N,), device=dev, generator=generator, dtype=torch.int32)
-    joints = torch.rand((N, V), device=dev, generator=generator).argsort(dim=1)[:, :4].float()
-    params = torch.empty((N, 16), device=dev, dtype=torch.float32)
+def draw_augment_params(N, V, device, generator=None):
+    """The reference's random policy as tensors (pure torch, any device): one of the four transforms per sample with equal
+    probability (`randint(0, 3)`, Hand_Dataset.py:146-147), factor ~ U(0.8, 1.2) (:87-90), offsets ~ U(-0.1, 0.1) (:99-101,
+    :110-118), four distinct joints (`shuffle(all_joint)[0:4]`, :113-115), r ~ U(0, 1) (:129).
+    Returns (kind (N,) int32, params (N, 16) float32) in the layout afb_augment takes."""
+    u = torch.rand((N, 16), device=device, generator=generator)
+    kind = torch.randint(0, 4, (N,), device=device, generator=generator, dtype=torch.int32)
+    joints = torch.rand((N, V), device=device, generator=generator).argsort(dim=1)[:, :4].float()
+    zeros = lambda c: torch.zeros((N, c), device=device)  # noqa: E731
     k = kind[:, None]
-    scale = torch.cat([0.8 + 0.4 * u[:, :1], torch.zeros((N, 15), device=dev)], 1)
-    shift = torch.cat([-0.1 + 0.2 * u[:, :3], torch.zeros((N, 13), device=dev)], 1)
+    scale = torch.cat([0.8 + 0.4 * u[:, :1], zeros(15)], 1)
+    shift = torch.cat([-0.1 + 0.2 * u[:, :3], zeros(13)], 1)
     noise = torch.cat([joints, -0.1 + 0.2 * u[:, 4:16]], 1)
-    tint = torch.cat([u[:, :1], torch.zeros((N, 15), device=dev)], 1)
+    tint = torch.cat([u[:, :1], zeros(15)], 1)
     params = torch.where(k == AUG_SCALE, scale, torch.where(k == AUG_SHIFT, shift, torch.where(k == AUG_NOISE, noise, tint)))
-    return augment(x, kind, params.contiguous()), kind, params
+    return kind, params.contiguous()
+
+
+def random_augment(x, generator=None):
+    """Hand_Dataset.data_aug with its random policy drawn on the device (draw_augment_params) and applied in one launch.
+    Returns (augmented batch, kind, params)."""
+    N, _, V, _ = x.shape
+    kind, params = draw_augment_params(N, V, x.device, generator)
+    return augment(x, kind, params), kind, params
 
 
 def combine(logits_st, logits_ts, w_st=0.8, w_ts=0.2):

@@ -1,4 +1,4 @@
-"""Host-side logic of the pooled DropPath masks (model_ST.prefill_drop_paths): one draw per forward, queued per Block in
+"""Host-side random policies: the pooled DropPath masks (model_ST.prefill_drop_paths): one draw per forward, queued per Block in
 the order Block.forward_rows consumes them, timm semantics (0 or 1/(1-p), reference model_ST.py:84-87)."""
 import torch
 
@@ -41,3 +41,33 @@ def test_eval_and_pinned_masks_bypass_the_pool():
     prefill_drop_paths([(a, 8)], torch.device("cpu"))
     assert a[1].drop_path.queue == [] and a[1].drop_path.row_scale(8, torch.device("cpu")) is pin
     assert len(a[0].drop_path.queue) == 2
+
+
+def test_augment_policy_draws_stay_in_the_reference_ranges():
+    """streams.draw_augment_params (host logic of the device augmentation): the four transforms with equal probability, factor in
+    [0.8, 1.2], offsets in [-0.1, 0.1], four DISTINCT joints, r in [0, 1] (data_process/Hand_Dataset.py:84-157); applying the
+    oracle's explicit-parameter augmentation with them reproduces each transform's definition."""
+    from altformer_b200 import streams
+    from oracle import altformer_oracle as O
+    g = torch.Generator().manual_seed(4)
+    N, T, V = 4000, 6, 22
+    kind, p = streams.draw_augment_params(N, V, torch.device("cpu"), g)
+    assert kind.dtype == torch.int32 and p.shape == (N, 16) and p.dtype == torch.float32
+    counts = torch.bincount(kind.long(), minlength=4).float() / N
+    assert (counts - 0.25).abs().max() < 0.03
+    assert ((p[kind == 0, 0] >= 0.8) & (p[kind == 0, 0] <= 1.2)).all() and (p[kind == 0, 1:] == 0).all()
+    assert (p[kind == 1, :3].abs() <= 0.1).all() and (p[kind == 1, 3:] == 0).all()
+    j = p[kind == 2, :4]
+    assert ((j >= 0) & (j < V) & (j == j.round())).all() and all(len(set(r.tolist())) == 4 for r in j[:200])
+    assert (p[kind == 2, 4:].abs() <= 0.1).all()
+    assert ((p[kind == 3, 0] >= 0) & (p[kind == 3, 0] <= 1)).all() and (p[kind == 3, 1:] == 0).all()
+    x = torch.randn(8, T, V, 3, generator=g)
+    y = O.augment(x, kind[:8], p[:8])
+    for n in range(8):
+        k = int(kind[n])
+        if k == 0:
+            assert torch.allclose(y[n], x[n] * p[n, 0])
+        elif k == 1:
+            assert torch.allclose(y[n], x[n] + p[n, :3])
+        elif k == 3:
+            assert torch.allclose(y[n, :-1], x[n, :-1] + p[n, 0] * (x[n, 1:] - x[n, :-1])) and torch.equal(y[n, -1], y[n, -2])
